@@ -1,0 +1,242 @@
+/*
+ * clengine.h — C-ABI of the B200-native CrowdLlama worker decode engine (libclengine.so).
+ *
+ * This is the drop-in boundary for the ONE hot path this repository accelerates: the
+ * worker-side model step that the reference reaches through
+ *     crowdllama.UnifiedAPIHandler            /root/reference/pkg/crowdllama/api.go:19
+ *     crowdllama.WorkerAPIHandler             /root/reference/pkg/crowdllama/api.go:45-96
+ *     callOllamaAPI (HTTP POST /api/chat)     /root/reference/pkg/crowdllama/api.go:108-160
+ * and, behind that HTTP call, the un-vendored github.com/ollama/ollama v0.9.6
+ * (/root/reference/go.mod:12) llama.cpp decode loop.  A Go cgo shim (go/b200handler/handler.go,
+ * shown in INTEGRATION.md) builds a UnifiedAPIHandler closure over cl_generate(); Python tests
+ * and bench.py bind the same symbols with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns 0 (CL_OK) or a negative cl_status; nothing throws across the ABI.
+ *   - the library never retains caller pointers after a call returns (cgo rule); strings and
+ *     id arrays handed back in cl_result are malloc()'d by the library and released with
+ *     cl_result_free().
+ *   - cl_generate*/cl_engine_stats are thread-safe and re-entrant (one goroutine per inbound
+ *     libp2p stream calls the handler concurrently: /root/reference/pkg/peer/peer.go:177-182).
+ *     The token-level cl_seq_* / cl_prefill / cl_decode_step calls are serialised internally by one engine lock.
+ *   - there is NO CPU fallback: if no sm_100 device is present cl_engine_create fails with
+ *     CL_ERR_NO_DEVICE.
+ */
+#ifndef CLENGINE_H_
+#define CLENGINE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CL_ABI_VERSION 1
+
+typedef enum cl_status {
+  CL_OK = 0,
+  CL_ERR_INVALID_ARG = -1,
+  CL_ERR_NO_DEVICE = -2,     /* no CUDA device / not sm_100 */
+  CL_ERR_CUDA = -3,          /* CUDA runtime error; see cl_last_error() */
+  CL_ERR_OOM = -4,           /* device memory or KV pages exhausted */
+  CL_ERR_UNKNOWN_MODEL = -5, /* model name not served by this engine */
+  CL_ERR_TOO_LONG = -6,      /* prompt + generation exceeds max_seq_len */
+  CL_ERR_BAD_SEQ = -7,       /* unknown / freed sequence handle */
+  CL_ERR_SHUTDOWN = -8,      /* engine is being destroyed */
+  CL_ERR_IO = -9,            /* weight / tokenizer file error */
+  CL_ERR_INTERNAL = -10,
+  CL_ERR_BAD_MESSAGE = -11   /* cl_handle_message: not a GenerateRequest (api.go:48-51) */
+} cl_status;
+
+/* Llama-family architecture description (public architecture facts; SURVEY.md §8). */
+typedef struct cl_model_config {
+  int32_t n_layers;
+  int32_t d_model;
+  int32_t n_heads;
+  int32_t n_kv_heads;
+  int32_t head_dim;
+  int32_t d_ff;
+  int32_t vocab_size;
+  int32_t max_seq_len;   /* positions covered by the RoPE table and block tables */
+  float rope_theta;
+  float rms_eps;
+} cl_model_config;
+
+typedef struct cl_engine_config {
+  int32_t abi_version;     /* must be CL_ABI_VERSION */
+  int32_t device;          /* CUDA ordinal (one engine process per GPU) */
+  const char* model_name;  /* name advertised / matched exactly, like Resource.SupportedModels
+                              (/root/reference/pkg/peermanager/manager.go:349-354) */
+  const char* preset;      /* "llama3-8b" | "mistral-7b" | "tinyllama-1.1b" | "tiny-test" | NULL
+                              (NULL => take `model` below) */
+  cl_model_config model;   /* used when preset == NULL */
+  const char* weights_path;/* NULL => synthetic seeded weights (no checkpoints exist offline) */
+  uint64_t weights_seed;   /* seed of the counter-based synthetic weight generator */
+  int64_t kv_pool_bytes;   /* bytes of HBM for the paged KV pool; 0 => derive from max_seqs */
+  int32_t page_size;       /* tokens per KV page: 16, 32 or 64 (0 => 32) */
+  int32_t max_batch;       /* max concurrently decoding sequences (0 => 8) */
+  int32_t max_seqs;        /* max live sequence handles (0 => max_batch) */
+  int32_t use_cuda_graph;  /* 1 => capture the token step in a CUDA graph (default 1; -1 => 0) */
+  int32_t decode_path;     /* 0 auto, 1 = generic LDG GEMV kernels, 2 = TMA-ring streaming GEMV */
+  int32_t start_scheduler; /* 1 => start the continuous-batching thread behind cl_generate */
+  int32_t reserved[8];
+} cl_engine_config;
+
+/* Sampler.  The reference sends no options (api.go:109-118), so Ollama defaults apply upstream:
+ * temperature 0.8, top_k 40, top_p 0.9, repeat_penalty 1.1 over the last 64 tokens, random seed.
+ * temperature <= 0 selects greedy argmax with lowest-index tie-break (the parity mode). */
+typedef struct cl_sampling {
+  float temperature;
+  int32_t top_k;
+  float top_p;
+  float repeat_penalty;
+  int32_t repeat_last_n;
+  uint64_t seed;
+  int32_t max_new_tokens;  /* num_predict; <= 0 => until EOS or context full */
+  int32_t ignore_eos;      /* 1 => never stop on EOS (benchmarks) */
+} cl_sampling;
+
+typedef struct cl_result {
+  char* text;            /* NUL-terminated UTF-8, malloc'd */
+  size_t text_len;
+  char* done_reason;     /* "stop" | "length", malloc'd (GenerateResponse.DoneReason, api.go:82) */
+  int32_t* token_ids;    /* generated ids, malloc'd */
+  int32_t n_prompt;
+  int32_t n_generated;
+  int64_t prefill_ns;
+  int64_t decode_ns;
+  int64_t total_ns;
+  int32_t n_preempted;   /* times this request was evicted and recomputed */
+} cl_result;
+
+typedef struct cl_stats {
+  double tokens_per_sec;     /* EWMA decode throughput -> Resource.TokensThroughput (types.go:33) */
+  double load;               /* active / max_batch in [0,1] -> Resource.Load (types.go:35) */
+  int32_t queue_depth;
+  int32_t active_seqs;
+  int32_t kv_pages_total;
+  int32_t kv_pages_used;
+  int64_t tokens_generated;
+  int64_t requests_completed;
+  int64_t preemptions;
+  int32_t vram_gb;           /* -> Resource.VRAMGB */
+  char gpu_model[64];        /* -> Resource.GPUModel */
+  int64_t kernel_launches;   /* kernels of this library launched so far (graph nodes counted) */
+} cl_stats;
+
+typedef struct cl_engine cl_engine;
+typedef int32_t cl_seq_t;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int cl_abi_version(void);
+const char* cl_strerror(int status);
+/* thread-local description of the last failing call on this thread ("" if none) */
+const char* cl_last_error(void);
+void cl_default_engine_config(cl_engine_config* cfg);
+void cl_default_sampling(cl_sampling* s);        /* Ollama defaults listed above */
+void cl_greedy_sampling(cl_sampling* s, int32_t max_new_tokens);
+int cl_model_preset(const char* name, cl_model_config* out);
+
+/* replaces: embedded Ollama server start, /root/reference/cmd/crowdllama/main.go:283-297 */
+int cl_engine_create(const cl_engine_config* cfg, cl_engine** out);
+void cl_engine_destroy(cl_engine* e);
+int cl_engine_model_config(const cl_engine* e, cl_model_config* out);
+int cl_engine_stats(cl_engine* e, cl_stats* out);
+
+/* ---- request level (what the Go shim calls) --------------------------------------------- */
+/* replaces: callOllamaAPI, api.go:108-160.  Blocking; enqueues into the continuous-batching
+ * scheduler.  `model` must equal the engine's model_name (else CL_ERR_UNKNOWN_MODEL).  The
+ * prompt is raw user text (api.go:111-116 forces role "user"); it is copied before return. */
+int cl_generate(cl_engine* e, const char* model, const char* prompt, size_t prompt_len,
+                const cl_sampling* s, cl_result* out);
+/* token-id variant of the same path (tokenizer bypass; used by parity tests and bench.py) */
+int cl_generate_ids(cl_engine* e, const int32_t* prompt_ids, int32_t n_prompt,
+                    const cl_sampling* s, cl_result* out);
+void cl_result_free(cl_result* r);
+
+/* replaces: WorkerAPIHandler, api.go:45-96, at the byte level.  `req`/`req_len` is a serialised
+ * llama.v1.BaseMessage (the payload pbwire.go:14-41 length-prefixes); on success *resp is a
+ * malloc'd serialised BaseMessage{GenerateResponse} (free with cl_buffer_free).  A request that
+ * is not a GenerateRequest returns CL_ERR_BAD_MESSAGE (api.go:48-51). */
+int cl_handle_message(cl_engine* e, const uint8_t* req, size_t req_len, const cl_sampling* s,
+                      uint8_t** resp, size_t* resp_len);
+void cl_buffer_free(void* p);
+
+/* tokenizer of the served model (byte-level fallback when no vocab file is configured) */
+int cl_tokenize(cl_engine* e, const char* text, size_t len, int32_t* ids, int32_t cap, int32_t* n_out);
+int cl_detokenize(cl_engine* e, const int32_t* ids, int32_t n, char* buf, size_t cap, size_t* len_out);
+
+/* ---- token level (parity tests, benchmarks) --------------------------------------------- */
+int cl_seq_create(cl_engine* e, cl_seq_t* out);
+int cl_seq_free(cl_engine* e, cl_seq_t seq);
+int cl_seq_len(cl_engine* e, cl_seq_t seq, int32_t* len_out);
+/* Append n prompt tokens to the sequence.  logits_out (host, may be NULL) receives the
+ * vocab_size fp32 logits of the LAST position. */
+int cl_prefill(cl_engine* e, cl_seq_t seq, const int32_t* ids, int32_t n, float* logits_out);
+/* Append one token and compute the next-token logits (host, may be NULL);
+ * argmax_out (may be NULL) receives the greedy next id (lowest index on ties). */
+int cl_decode_step(cl_engine* e, cl_seq_t seq, int32_t id, float* logits_out, int32_t* argmax_out);
+/* Run n_steps greedy decode steps entirely on the device (each step feeds its argmax to the
+ * next); ids_out receives the n_steps generated ids.  device_ms (may be NULL) receives the
+ * CUDA-event time of the loop.  This is the timed region of bench.py's `value`. */
+int cl_decode_greedy(cl_engine* e, cl_seq_t seq, int32_t first_id, int32_t n_steps,
+                     int32_t* ids_out, float* device_ms);
+/* Batched greedy decode: n_seqs sequences advance together for n_steps (continuous-batching
+ * inner loop without the scheduler).  first_ids[n_seqs]; ids_out[n_steps * n_seqs]. */
+int cl_decode_greedy_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs,
+                           const int32_t* first_ids, int32_t n_steps, int32_t* ids_out,
+                           float* device_ms);
+/* debugging / parity: copy the residual stream after `layer` (or the final norm input when
+ * layer == n_layers) of the most recent single-sequence step to host (d_model floats). */
+int cl_debug_hidden(cl_engine* e, float* out, int32_t n);
+
+/* ---- single-op entry points (host buffers in/out; kernel parity tests and microbenches) --
+ * Each runs exactly the CUDA kernel the token step uses.  bf16 data is passed as uint16_t.
+ * `variant`: 0 = generic LDG kernel, 1 = TMA-ring streaming kernel.  iters>0 => repeat and
+ * report the average device time (ms) through *ms (may be NULL). */
+int cl_op_gemv(int device, int variant, const uint16_t* w, const float* x, float* y,
+               int32_t n_rows, int32_t k, int32_t iters, float* ms);
+/* y = resid + W x */
+int cl_op_gemv_residual(int device, int variant, const uint16_t* w, const float* x,
+                        const float* resid, float* y, int32_t n_rows, int32_t k);
+/* xn = bf16round(rmsnorm(h) * gain); y = W xn (norm fused in the GEMV prologue) */
+int cl_op_rmsnorm_gemv(int device, int variant, const uint16_t* w, const float* h,
+                       const float* gain, float eps, float* y, int32_t n_rows, int32_t k);
+/* w_gu interleaved rows (2i = gate_i, 2i+1 = up_i); act_i = bf16round(silu(g_i) * u_i) */
+int cl_op_rmsnorm_gateup(int device, int variant, const uint16_t* w_gu, const float* h,
+                         const float* gain, float eps, float* act, int32_t d_ff, int32_t k);
+/* paged GQA decode attention for one sequence: q [n_heads*head_dim] fp32 (pre-RoPE),
+ * k_new/v_new [n_kv*head_dim] fp32 (pre-RoPE) for position ctx_len (appended by the kernel),
+ * k_cache/v_cache [ctx_len][n_kv][head_dim] bf16 (already roped), out [n_heads*head_dim]. */
+int cl_op_attn_decode(int device, const float* q, const float* k_new, const float* v_new,
+                      const uint16_t* k_cache, const uint16_t* v_cache, int32_t ctx_len,
+                      int32_t n_heads, int32_t n_kv, int32_t head_dim, float rope_theta,
+                      int32_t page_size, float* out);
+/* prefill GEMM on tcgen05: Y[t][n] = sum_k X[t][k] W[n][k]; X,W bf16, Y fp32 */
+int cl_op_gemm_bf16(int device, const uint16_t* x, const uint16_t* w, float* y, int32_t t,
+                    int32_t n, int32_t k, int32_t iters, float* ms);
+/* causal prefill attention: q [t][n_heads][d], k,v [t][n_kv][d] bf16 (roped), out bf16-rounded fp32 */
+int cl_op_attn_prefill(int device, const uint16_t* q, const uint16_t* k, const uint16_t* v,
+                       int32_t t, int32_t n_heads, int32_t n_kv, int32_t head_dim, float* out);
+/* synthetic weight generator (device kernel) -> host copy, for known-answer tests */
+int cl_op_synth_weights(int device, uint64_t seed, int32_t tensor_key, int64_t n, float scale,
+                        uint16_t* out_bf16);
+
+/* ---- paged-KV allocator (host logic; usable without a GPU) ------------------------------ */
+typedef struct cl_kvpool cl_kvpool;
+int cl_kvpool_create(int32_t n_pages, int32_t page_size, cl_kvpool** out);
+void cl_kvpool_destroy(cl_kvpool* p);
+/* grow `owner`'s page list so it covers n_tokens; CL_ERR_OOM if the free list runs dry
+ * (nothing is allocated in that case). */
+int cl_kvpool_reserve(cl_kvpool* p, int32_t owner, int32_t n_tokens);
+int cl_kvpool_release(cl_kvpool* p, int32_t owner);
+int cl_kvpool_pages_of(cl_kvpool* p, int32_t owner, int32_t* pages, int32_t cap, int32_t* n_out);
+int cl_kvpool_free_pages(cl_kvpool* p);
+int cl_kvpool_used_pages(cl_kvpool* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLENGINE_H_ */

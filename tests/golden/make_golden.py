@@ -1,0 +1,91 @@
+"""Generate the golden fixtures that pin the CPU oracle (run in the build container, CPU only).
+
+The reference (crowdllama) holds no numerical code and no golden vectors for the model step
+(SURVEY.md §8c), and its arithmetic dependency (ollama v0.9.6 / llama.cpp) is not available
+offline.  The fixtures below therefore come from the public implementation of the same
+architecture that IS importable here: HF transformers' LlamaForCausalLM / MistralForCausalLM,
+run on CPU in float32 over bf16-representable seeded weights.
+
+  python tests/golden/make_golden.py      -> tests/golden/hf_tiny_llama.npz, hf_tiny_mistral.npz,
+                                              synth_kat.npz
+
+Fixtures are small (< 1 MB each) and committed; tests never import transformers.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import oracle as oc  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def hf_fixture(kind: str, path: Path, seed: int):
+    from transformers import LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM
+    cfg = dict(n_layers=3, d_model=64, n_heads=4, n_kv_heads=2, head_dim=16, d_ff=160, vocab_size=384,
+               max_seq_len=64, rope_theta=10000.0 if kind == "llama" else 1e6, rms_eps=1e-5)
+    common = dict(hidden_size=cfg["d_model"], intermediate_size=cfg["d_ff"], num_hidden_layers=cfg["n_layers"],
+                  num_attention_heads=cfg["n_heads"], num_key_value_heads=cfg["n_kv_heads"],
+                  vocab_size=cfg["vocab_size"], max_position_embeddings=cfg["max_seq_len"],
+                  rms_norm_eps=cfg["rms_eps"], rope_theta=cfg["rope_theta"], tie_word_embeddings=False,
+                  attention_bias=False, hidden_act="silu")
+    torch.manual_seed(seed)
+    if kind == "llama":
+        model = LlamaForCausalLM(LlamaConfig(mlp_bias=False, **common))
+    else:
+        model = MistralForCausalLM(MistralConfig(sliding_window=None, **common))
+    model.eval()
+    tensors = {}
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "norm" in name:
+                p.copy_(1.0 + 0.1 * torch.randn_like(p))
+            else:
+                p.copy_(0.08 * torch.randn_like(p))
+            p.copy_(p.to(torch.bfloat16).to(torch.float32))       # bf16-representable weights
+            tensors[name] = p.detach().clone()
+    ids = torch.tensor([[(i * 7919 + 13) % cfg["vocab_size"] for i in range(24)]])
+    with torch.no_grad():
+        out = model(ids, output_hidden_states=True)
+    logits = out.logits[0].float().numpy()
+    hidden_last = out.hidden_states[-1][0].float().numpy()  # after final norm in HF (norm applied)
+    save = {"cfg_keys": np.array(list(cfg.keys())), "cfg_vals": np.array([float(v) for v in cfg.values()]),
+            "ids": ids[0].numpy().astype(np.int32), "logits": logits.astype(np.float32),
+            "hidden_last_normed": hidden_last.astype(np.float32)}
+
+    def b16(t):
+        return oc.np_bf16_from_f32(t.numpy().astype(np.float32).ravel())
+    save["embed"] = b16(tensors["model.embed_tokens.weight"])
+    save["lm_head"] = b16(tensors["lm_head.weight"])
+    save["final_norm"] = b16(tensors["model.norm.weight"])
+    for l in range(cfg["n_layers"]):
+        pre = f"model.layers.{l}."
+        m = {"ATTN_NORM": "input_layernorm.weight", "FFN_NORM": "post_attention_layernorm.weight",
+             "WQ": "self_attn.q_proj.weight", "WK": "self_attn.k_proj.weight", "WV": "self_attn.v_proj.weight",
+             "WO": "self_attn.o_proj.weight", "WGATE": "mlp.gate_proj.weight", "WUP": "mlp.up_proj.weight",
+             "WDOWN": "mlp.down_proj.weight"}
+        for k, v in m.items():
+            save[f"L{l}.{k}"] = b16(tensors[pre + v])
+    np.savez_compressed(path, **save)
+    print("wrote", path, path.stat().st_size, "bytes")
+
+
+def synth_kat(path: Path):
+    """Known-answer vectors of the counter-based synthetic weight generator (numpy mirror)."""
+    save = {}
+    for seed, key, first, n in [(1234, 0, 0, 64), (1234, 4 + 16 * 31, 4096 * 4096 - 32, 32),
+                                (0, 1, 525336576 - 16, 16), (2**63 + 12345, 11, 7, 33)]:
+        save[f"int_{seed}_{key}_{first}_{n}"] = oc.np_synth_int(seed, key, first, n).astype(np.int32)
+        save[f"bf16_{seed}_{key}_{first}_{n}"] = oc.np_synth_bf16(seed, key, first, n)
+    np.savez_compressed(path, **save)
+    print("wrote", path, path.stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    hf_fixture("llama", OUT / "hf_tiny_llama.npz", 0)
+    hf_fixture("mistral", OUT / "hf_tiny_mistral.npz", 1)
+    synth_kat(OUT / "synth_kat.npz")
