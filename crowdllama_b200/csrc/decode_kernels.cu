@@ -1,0 +1,724 @@
+// decode_kernels.cu — single-token (and small-batch) decode kernels for sm_100a.
+//
+// These implement the arithmetic that the reference reaches through callOllamaAPI
+// (/root/reference/pkg/crowdllama/api.go:108-160 -> ollama v0.9.6 llama.cpp decode loop; SURVEY.md
+// §8a row a8): RMSNorm-fused weight GEMVs (HBM-bound), RoPE + paged-KV append + split-KV GQA
+// attention, embedding gather, argmax.  All of them are HBM-bound byte streaming: no tensor cores.
+//
+//   variant 0  gemv_ldg_kernel : coalesced 128-bit LDG (L1 no-allocate, L2 evict-first), warp per row pair
+//   variant 1  gemv_ring_kernel: weights streamed by a producer warp with 1-D TMA bulk copies
+//                                (cp.async.bulk -> UBLKCP) into an mbarrier ring; 8 consumer warps
+//                                keep their x slice in registers.  The producer never waits for
+//                                activations, so with PDL the next kernel's ring fills while the
+//                                previous kernel drains.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cl {
+
+static int g_sm_count = 0;
+int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+template <typename Kern, typename Args>
+static cudaError_t launch_ex(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Args& args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
+// ================================================================================================
+// shared epilogue
+// ================================================================================================
+template <int EPI>
+__device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, int slot, int row0, float v0, float v1) {
+  // (row0, row0+1) is a row pair
+  if (EPI == EPI_STORE) {
+    float* y = a.y + (size_t)slot * a.y_stride;
+    y[row0] = v0;
+    y[row0 + 1] = v1;
+  } else if (EPI == EPI_RESID) {
+    const float* r = a.resid + (size_t)slot * a.y_stride;
+    float* y = a.y + (size_t)slot * a.y_stride;
+    float r0 = r[row0], r1 = r[row0 + 1];
+    y[row0] = r0 + v0;
+    y[row0 + 1] = r1 + v1;
+  } else {  // gate/up: v0 = gate_i, v1 = up_i
+    float* y = a.y + (size_t)slot * a.y_stride;
+    float si = v0 / (1.0f + __expf(-v0));
+    y[row0 >> 1] = bf16_round(si * v1);
+  }
+}
+
+// ================================================================================================
+// variant 0: LDG GEMV.  block = 256 threads (8 warps), x (normalised) staged in shared memory.
+// ================================================================================================
+template <int EPI, bool NORM>
+__global__ void __launch_bounds__(256, 2) gemv_ldg_kernel(const GemvArgs a) {
+  extern __shared__ __align__(16) float xs[];
+  __shared__ float red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int slot = a.slots ? a.slots[b] : b;
+  const int K = a.K;
+
+  if (NORM) {
+    const float* h = a.h + (size_t)slot * a.x_stride;
+    float ss = 0.f;
+    for (int i = tid * 4; i < K; i += 256 * 4) {
+      float4 v = *reinterpret_cast<const float4*>(h + i);
+      *reinterpret_cast<float4*>(xs + i) = v;
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float inv = 1.0f / sqrtf(tot / (float)K + a.eps);
+    for (int i = tid * 4; i < K; i += 256 * 4) {
+      float4 v = *reinterpret_cast<float4*>(xs + i);
+      float4 g = *reinterpret_cast<const float4*>(a.gain + i);
+      v.x = bf16_round(v.x * inv * g.x); v.y = bf16_round(v.y * inv * g.y);
+      v.z = bf16_round(v.z * inv * g.z); v.w = bf16_round(v.w * inv * g.w);
+      *reinterpret_cast<float4*>(xs + i) = v;
+    }
+  } else {
+    const float* x = a.x + (size_t)slot * a.x_stride;
+    for (int i = tid * 4; i < K; i += 256 * 4)
+      *reinterpret_cast<float4*>(xs + i) = *reinterpret_cast<const float4*>(x + i);
+  }
+  __syncthreads();
+
+  const int total_warps = gridDim.x * 8;
+  const int gw = blockIdx.x * 8 + warp;
+  const int npairs = a.N >> 1;
+  const int p0 = (int)(((long long)npairs * gw) / total_warps);
+  const int p1 = (int)(((long long)npairs * (gw + 1)) / total_warps);
+  const int nchunk = K >> 4;  // 16 bf16 = 32 bytes per lane per load
+  const float4* xs4 = reinterpret_cast<const float4*>(xs);
+
+  for (int p = p0; p < p1; ++p) {
+    const uint8_t* w0 = reinterpret_cast<const uint8_t*>(a.W + (size_t)(2 * p) * K);
+    const uint8_t* w1 = w0 + (size_t)K * 2;
+    float acc0 = 0.f, acc1 = 0.f;
+    int c = lane;
+    for (; c + 32 < nchunk; c += 64) {
+      const u32x8 a0 = ldg_stream256(w0 + (size_t)c * 32), a1 = ldg_stream256(w0 + (size_t)(c + 32) * 32);
+      const u32x8 b0 = ldg_stream256(w1 + (size_t)c * 32), b1 = ldg_stream256(w1 + (size_t)(c + 32) * 32);
+      acc0 = dot16(a0, xs4 + 4 * c, acc0); acc1 = dot16(b0, xs4 + 4 * c, acc1);
+      acc0 = dot16(a1, xs4 + 4 * (c + 32), acc0); acc1 = dot16(b1, xs4 + 4 * (c + 32), acc1);
+    }
+    for (; c < nchunk; c += 32) {
+      const u32x8 a0 = ldg_stream256(w0 + (size_t)c * 32);
+      const u32x8 b0 = ldg_stream256(w1 + (size_t)c * 32);
+      acc0 = dot16(a0, xs4 + 4 * c, acc0);
+      acc1 = dot16(b0, xs4 + 4 * c, acc1);
+    }
+    acc0 = warp_sum(acc0);
+    acc1 = warp_sum(acc1);
+    if (lane == 0) gemv_epilogue<EPI>(a, slot, 2 * p, acc0, acc1);
+  }
+}
+
+// ================================================================================================
+// variant 1: TMA-ring streaming GEMV.
+//   block = 288 threads: warps 0..7 consume, warp 8 produces.  A stage holds TR full rows
+//   (TR*K bf16, contiguous in W -> ONE bulk copy).  Consumer warp w works on row (w / S) of the
+//   stage, K-slice (w % S); its CPL*8 x values per lane live in registers for the whole kernel.
+//   Per-row partials go to shared memory; one barrier at the end, then a coalesced epilogue.
+// ================================================================================================
+template <int EPI, bool NORM, int TR, int S, int CPL, int NST>
+__global__ void __launch_bounds__(288, 1) gemv_ring_kernel(const GemvArgs a) {
+  static_assert(TR * S == 8, "8 consumer warps");
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int K = S * CPL * 256;
+  constexpr uint32_t STAGE_BYTES = (uint32_t)TR * K * 2;
+  uint8_t* ring = smem_raw;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NST * STAGE_BYTES);
+  uint64_t* empty = full + NST;
+  float* ssw = reinterpret_cast<float*>(empty + NST);  // [8]
+  float* part = ssw + 8;                                // [local_rows][S]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  // split in units that keep every row pair (2i, 2i+1) inside one CTA
+  constexpr int U = (TR == 1) ? 2 : 1;
+  const int NU = a.N / (TR * U);
+  const int tile0 = U * (int)(((long long)NU * blockIdx.x) / gridDim.x);
+  const int tile1 = U * (int)(((long long)NU * (blockIdx.x + 1)) / gridDim.x);
+  const int ntiles = tile1 - tile0;
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+
+  if (warp == 8) {
+    // ---------------- producer: weights do not depend on the previous kernel -> no pdl_wait here
+    if (elect_one()) {
+      const uint64_t pol = policy_evict_first();
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.W) + (size_t)tile0 * STAGE_BYTES;
+      for (int it = 0; it < ntiles; ++it) {
+        const int st = it % NST;
+        const uint32_t par = (uint32_t)(it / NST) & 1u;
+        mbar_wait(&empty[st], par ^ 1u);
+        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+        bulk_g2s(ring + (size_t)st * STAGE_BYTES, src + (size_t)it * STAGE_BYTES, STAGE_BYTES, &full[st], pol);
+      }
+    }
+    // the producer warp must stay until the consumers are done with the barriers it arms
+  } else {
+    // ---------------- consumers
+    const int r = warp / S, s = warp % S;
+    const int kbase = s * (K / S);
+    pdl_wait();
+    const int slot = a.slots ? a.slots[b] : b;
+    float xr[CPL][8];
+    if (NORM) {
+      const float* h = a.h + (size_t)slot * a.x_stride;
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int k = kbase + (c * 32 + lane) * 8;
+        float4 v0 = *reinterpret_cast<const float4*>(h + k);
+        float4 v1 = *reinterpret_cast<const float4*>(h + k + 4);
+        xr[c][0] = v0.x; xr[c][1] = v0.y; xr[c][2] = v0.z; xr[c][3] = v0.w;
+        xr[c][4] = v1.x; xr[c][5] = v1.y; xr[c][6] = v1.z; xr[c][7] = v1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(xr[c][j], xr[c][j], ss);
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) ssw[warp] = ss;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < S; ++i) tot += ssw[i];  // warps 0..S-1 are row 0, slices 0..S-1: cover K once
+      const float inv = 1.0f / sqrtf(tot / (float)K + a.eps);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int k = kbase + (c * 32 + lane) * 8;
+        float4 g0 = *reinterpret_cast<const float4*>(a.gain + k);
+        float4 g1 = *reinterpret_cast<const float4*>(a.gain + k + 4);
+        xr[c][0] = bf16_round(xr[c][0] * inv * g0.x); xr[c][1] = bf16_round(xr[c][1] * inv * g0.y);
+        xr[c][2] = bf16_round(xr[c][2] * inv * g0.z); xr[c][3] = bf16_round(xr[c][3] * inv * g0.w);
+        xr[c][4] = bf16_round(xr[c][4] * inv * g1.x); xr[c][5] = bf16_round(xr[c][5] * inv * g1.y);
+        xr[c][6] = bf16_round(xr[c][6] * inv * g1.z); xr[c][7] = bf16_round(xr[c][7] * inv * g1.w);
+      }
+    } else {
+      const float* x = a.x + (size_t)slot * a.x_stride;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int k = kbase + (c * 32 + lane) * 8;
+        float4 v0 = *reinterpret_cast<const float4*>(x + k);
+        float4 v1 = *reinterpret_cast<const float4*>(x + k + 4);
+        xr[c][0] = v0.x; xr[c][1] = v0.y; xr[c][2] = v0.z; xr[c][3] = v0.w;
+        xr[c][4] = v1.x; xr[c][5] = v1.y; xr[c][6] = v1.z; xr[c][7] = v1.w;
+      }
+    }
+
+    const uint32_t row_off = (uint32_t)(r * K + kbase + lane * 8) * 2u;
+    for (int it = 0; it < ntiles; ++it) {
+      const int st = it % NST;
+      const uint32_t par = (uint32_t)(it / NST) & 1u;
+      mbar_wait(&full[st], par);
+      const uint8_t* base = ring + (size_t)st * STAGE_BYTES + row_off;
+      uint4 w[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) w[c] = *reinterpret_cast<const uint4*>(base + c * 512);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        acc = fmaf(bf16_lo(w[c].x), xr[c][0], acc); acc = fmaf(bf16_hi(w[c].x), xr[c][1], acc);
+        acc = fmaf(bf16_lo(w[c].y), xr[c][2], acc); acc = fmaf(bf16_hi(w[c].y), xr[c][3], acc);
+        acc = fmaf(bf16_lo(w[c].z), xr[c][4], acc); acc = fmaf(bf16_hi(w[c].z), xr[c][5], acc);
+        acc = fmaf(bf16_lo(w[c].w), xr[c][6], acc); acc = fmaf(bf16_hi(w[c].w), xr[c][7], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) part[(it * TR + r) * S + s] = acc;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---------------- epilogue: one thread per row pair, coalesced
+    const int local_pairs = (ntiles * TR) >> 1;
+    const int row_base = tile0 * TR;
+    for (int p = tid; p < local_pairs; p += 256) {
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < S; ++i) { v0 += part[(2 * p) * S + i]; v1 += part[(2 * p + 1) * S + i]; }
+      gemv_epilogue<EPI>(a, slot, row_base + 2 * p, v0, v1);
+    }
+  }
+}
+
+struct RingCfg { int TR, S, CPL, NST; };
+static bool ring_cfg_for(int K, RingCfg* c) {
+  switch (K) {
+    case 1024: *c = {2, 4, 1, 6}; return true;
+    case 2048: *c = {2, 4, 2, 6}; return true;
+    case 4096: *c = {2, 4, 4, 6}; return true;
+    case 8192: *c = {1, 8, 4, 4}; return true;
+    case 14336: *c = {1, 8, 7, 3}; return true;
+    default: return false;
+  }
+}
+
+bool gemv_variant_supported(int variant, int N, int K) {
+  if (N <= 0 || K <= 0 || (N & 1) || (K & 15)) return false;
+  if (variant == 0) return (size_t)K * 4 <= 200 * 1024;
+  RingCfg c;
+  if (!ring_cfg_for(K, &c)) return false;
+  if (N % (2 * c.TR)) return false;  // each CTA owns whole row pairs
+  return true;
+}
+
+template <int EPI, bool NORM, int TR, int S, int CPL, int NST>
+static cudaError_t launch_ring_inst(const GemvArgs& a, cudaStream_t st, bool pdl) {
+  constexpr int K = S * CPL * 256;
+  constexpr int U = (TR == 1) ? 2 : 1;
+  const int NU = a.N / (TR * U);
+  int G = sm_count();
+  if (G > NU) G = NU;
+  const int max_tiles = U * ((NU + G - 1) / G);
+  size_t smem = (size_t)NST * TR * K * 2 + (size_t)2 * NST * 8 + 8 * 4 + (size_t)(max_tiles + 1) * TR * S * 4 + 64;
+  auto kern = gemv_ring_kernel<EPI, NORM, TR, S, CPL, NST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_set = true;
+  }
+  if (smem > 160 * 1024) return cudaErrorInvalidValue;
+  return launch_ex(kern, dim3(G, a.batch), dim3(288), smem, st, pdl, a);
+}
+
+template <int EPI, bool NORM>
+static cudaError_t launch_ring(const GemvArgs& a, cudaStream_t st, bool pdl) {
+  switch (a.K) {
+    case 1024: return launch_ring_inst<EPI, NORM, 2, 4, 1, 6>(a, st, pdl);
+    case 2048: return launch_ring_inst<EPI, NORM, 2, 4, 2, 6>(a, st, pdl);
+    case 4096: return launch_ring_inst<EPI, NORM, 2, 4, 4, 6>(a, st, pdl);
+    case 8192: return launch_ring_inst<EPI, NORM, 1, 8, 4, 4>(a, st, pdl);
+    case 14336: return launch_ring_inst<EPI, NORM, 1, 8, 7, 3>(a, st, pdl);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int EPI, bool NORM>
+static cudaError_t launch_ldg(const GemvArgs& a, cudaStream_t st, bool pdl) {
+  auto kern = gemv_ldg_kernel<EPI, NORM>;
+  size_t smem = (size_t)a.K * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  int G = sm_count() * 2;
+  int npairs = a.N / 2;
+  if (G * 8 > npairs) G = (npairs + 7) / 8;
+  return launch_ex(kern, dim3(G, a.batch), dim3(256), smem, st, pdl, a);
+}
+
+int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t st, bool pdl) {
+  if (variant == 1 && !gemv_variant_supported(1, a.N, a.K)) variant = 0;
+  // with TR==1 configs row-pair ownership needs even tile splits; handled in launch_ring_inst
+  cudaError_t e = cudaErrorInvalidValue;
+#define CL_DISPATCH(FN)                                                                   \
+  if (epi == EPI_STORE) e = norm ? FN<EPI_STORE, true>(a, st, pdl) : FN<EPI_STORE, false>(a, st, pdl);   \
+  else if (epi == EPI_RESID) e = norm ? FN<EPI_RESID, true>(a, st, pdl) : FN<EPI_RESID, false>(a, st, pdl); \
+  else e = norm ? FN<EPI_GATEUP, true>(a, st, pdl) : FN<EPI_GATEUP, false>(a, st, pdl);
+  if (variant == 1) { CL_DISPATCH(launch_ring) } else { CL_DISPATCH(launch_ldg) }
+#undef CL_DISPATCH
+  return e == cudaSuccess ? 1 : -1;
+}
+
+// ================================================================================================
+// paged GQA decode attention (split-KV), fused RoPE(q,k) + KV append + split combine.
+// grid = (n_kv, nsplit, batch), block = 256.  LPT lanes cooperate on one cached token.
+// ================================================================================================
+template <int REP, int HD>
+__global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeArgs a) {
+  constexpr int LPT = HD / 8;        // lanes per token (16-byte chunk each)
+  constexpr int TPW = 32 / LPT;      // tokens per warp iteration
+  constexpr int HALF = HD / 2;
+  constexpr float LOG2E = 1.4426950408889634f;
+  __shared__ __align__(16) float q_s[REP][HD];
+  __shared__ __align__(16) float knew_s[HD];
+  __shared__ __align__(16) float vnew_s[HD];
+  __shared__ float red_m[8][REP], red_l[8][REP];
+  __shared__ __align__(16) float red_acc[8][REP][HD];
+  __shared__ int is_last_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int slot = a.slots ? a.slots[b] : b;
+  const int pos = a.pos[slot];
+  const int P = a.page_size;
+  const int* bt = a.block_tables + (size_t)slot * a.bt_stride;
+  const float* qkv = a.qkv + (size_t)slot * a.qkv_stride;
+  const float2* rope = a.rope + (size_t)pos * HALF;
+  const float scale2 = rsqrtf((float)HD) * LOG2E;
+  const bool owns_new = (split == a.nsplit - 1);
+
+  // ---- RoPE(q) for this kv head's REP query heads (bf16-rounded, cl-llama v1)
+  for (int t = tid; t < REP * HALF; t += 256) {
+    const int hh = t / HALF, i = t % HALF;
+    const float* qh = qkv + (size_t)(g * REP + hh) * HD;
+    const float2 cs = rope[i];
+    const float x0 = qh[i], x1 = qh[i + HALF];
+    q_s[hh][i] = bf16_round(x0 * cs.x - x1 * cs.y);
+    q_s[hh][i + HALF] = bf16_round(x1 * cs.x + x0 * cs.y);
+  }
+  // ---- RoPE(k) + KV append of the current token (one split does it)
+  if (owns_new) {
+    const int page = bt[pos / P], off = pos % P;
+    const size_t base = (((size_t)page * a.n_kv + g) * P + off) * HD;
+    const float* kr = qkv + (size_t)a.n_heads * HD + (size_t)g * HD;
+    const float* vr = qkv + (size_t)(a.n_heads + a.n_kv) * HD + (size_t)g * HD;
+    for (int i = tid; i < HALF; i += 256) {
+      const float2 cs = rope[i];
+      const float x0 = kr[i], x1 = kr[i + HALF];
+      const float k0 = bf16_round(x0 * cs.x - x1 * cs.y), k1 = bf16_round(x1 * cs.x + x0 * cs.y);
+      knew_s[i] = k0; knew_s[i + HALF] = k1;
+      a.kpool[base + i] = __float2bfloat16_rn(k0);
+      a.kpool[base + i + HALF] = __float2bfloat16_rn(k1);
+    }
+    for (int i = tid; i < HD; i += 256) {
+      const float v = bf16_round(vr[i]);
+      vnew_s[i] = v;
+      a.vpool[base + i] = __float2bfloat16_rn(v);
+    }
+  }
+  __syncthreads();
+
+  // ---- this split's cached-token range
+  int chunk = (pos + a.nsplit - 1) / a.nsplit;
+  chunk = (chunk + 15) & ~15;
+  const int t0 = split * chunk;
+  const int t1 = min(pos, t0 + chunk);
+
+  const int sub = lane / LPT, j = lane % LPT;
+  float qr[REP][8];
+#pragma unroll
+  for (int hh = 0; hh < REP; ++hh)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qr[hh][i] = q_s[hh][j * 8 + i];
+  float m[REP], l[REP], acc[REP][8];
+#pragma unroll
+  for (int hh = 0; hh < REP; ++hh) {
+    m[hh] = -INFINITY; l[hh] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[hh][i] = 0.f;
+  }
+
+  auto consume = [&](const float (&kf)[8], const float (&vf)[8], bool active) {
+    float sc[REP];
+#pragma unroll
+    for (int hh = 0; hh < REP; ++hh) {
+      float p = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p = fmaf(qr[hh][i], kf[i], p);
+      sc[hh] = p;
+    }
+#pragma unroll
+    for (int o = LPT / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int hh = 0; hh < REP; ++hh) sc[hh] += __shfl_xor_sync(0xffffffffu, sc[hh], o);
+    if (active) {
+#pragma unroll
+      for (int hh = 0; hh < REP; ++hh) {
+        const float s2 = sc[hh] * scale2;
+        const float mn = fmaxf(m[hh], s2);
+        const float corr = exp2f(m[hh] - mn);   // m = -inf -> 0
+        const float p = exp2f(s2 - mn);
+        l[hh] = l[hh] * corr + p;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[hh][i] = fmaf(p, vf[i], acc[hh][i] * corr);
+        m[hh] = mn;
+      }
+    }
+  };
+
+  for (int tb = t0 + warp * TPW; tb < t1; tb += 8 * TPW) {
+    const int t = tb + sub;
+    const bool active = t < t1;
+    float kf[8], vf[8];
+    if (active) {
+      const int page = bt[t / P], off = t % P;
+      const size_t base = (((size_t)page * a.n_kv + g) * P + off) * HD + j * 8;
+      const uint4 kk = ldg_stream(a.kpool + base);
+      const uint4 vv = ldg_stream(a.vpool + base);
+      kf[0] = bf16_lo(kk.x); kf[1] = bf16_hi(kk.x); kf[2] = bf16_lo(kk.y); kf[3] = bf16_hi(kk.y);
+      kf[4] = bf16_lo(kk.z); kf[5] = bf16_hi(kk.z); kf[6] = bf16_lo(kk.w); kf[7] = bf16_hi(kk.w);
+      vf[0] = bf16_lo(vv.x); vf[1] = bf16_hi(vv.x); vf[2] = bf16_lo(vv.y); vf[3] = bf16_hi(vv.y);
+      vf[4] = bf16_lo(vv.z); vf[5] = bf16_hi(vv.z); vf[6] = bf16_lo(vv.w); vf[7] = bf16_hi(vv.w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+    }
+    consume(kf, vf, active);
+  }
+  if (owns_new && warp == 0) {  // the current token, from shared memory
+    float kf[8], vf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { kf[i] = knew_s[j * 8 + i]; vf[i] = vnew_s[j * 8 + i]; }
+    consume(kf, vf, sub == 0);
+  }
+
+  // ---- merge the TPW token groups of a warp
+#pragma unroll
+  for (int o = LPT; o < 32; o <<= 1) {
+#pragma unroll
+    for (int hh = 0; hh < REP; ++hh) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m[hh], o);
+      const float lo = __shfl_xor_sync(0xffffffffu, l[hh], o);
+      const float mn = fmaxf(m[hh], mo);
+      const float c0 = (m[hh] == -INFINITY) ? 0.f : exp2f(m[hh] - mn);
+      const float c1 = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+      l[hh] = l[hh] * c0 + lo * c1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ao = __shfl_xor_sync(0xffffffffu, acc[hh][i], o);
+        acc[hh][i] = acc[hh][i] * c0 + ao * c1;
+      }
+      m[hh] = mn;
+    }
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int hh = 0; hh < REP; ++hh) {
+      if (j == 0) { red_m[warp][hh] = m[hh]; red_l[warp][hh] = l[hh]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red_acc[warp][hh][j * 8 + i] = acc[hh][i];
+    }
+  }
+  __syncthreads();
+
+  // ---- CTA partial -> global
+  float* part = a.part + ((((size_t)slot * a.n_kv + g) * a.nsplit + split) * REP) * (HD + 2);
+  for (int t = tid; t < REP * HD; t += 256) {
+    const int hh = t / HD, i = t % HD;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, red_m[w][hh]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float c = (red_m[w][hh] == -INFINITY) ? 0.f : exp2f(red_m[w][hh] - M);
+      L = fmaf(red_l[w][hh], c, L);
+      A = fmaf(red_acc[w][hh][i], c, A);
+    }
+    float* ph = part + (size_t)hh * (HD + 2);
+    if (i == 0) { ph[0] = M; ph[1] = L; }
+    ph[2 + i] = A;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned* cnt = a.counters + (size_t)slot * a.n_kv + g;
+    const unsigned old = atomicAdd(cnt, 1u);
+    is_last_s = (old == (unsigned)a.nsplit - 1u);
+    if (is_last_s) *cnt = 0u;  // re-arm for the next launch (graph replay)
+  }
+  __syncthreads();
+  if (!is_last_s) return;
+  __threadfence();
+
+  // ---- last split to finish combines all partials of this kv head
+  const float* pall = a.part + (((size_t)slot * a.n_kv + g) * a.nsplit) * REP * (HD + 2);
+  float* out = a.out + (size_t)slot * a.out_stride;
+  for (int t = tid; t < REP * HD; t += 256) {
+    const int hh = t / HD, i = t % HD;
+    float M = -INFINITY;
+    for (int s = 0; s < a.nsplit; ++s) M = fmaxf(M, __ldcg(pall + ((size_t)s * REP + hh) * (HD + 2)));
+    float L = 0.f, A = 0.f;
+    for (int s = 0; s < a.nsplit; ++s) {
+      const float* ph = pall + ((size_t)s * REP + hh) * (HD + 2);
+      const float ms = __ldcg(ph);
+      const float c = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+      L = fmaf(__ldcg(ph + 1), c, L);
+      A = fmaf(__ldcg(ph + 2 + i), c, A);
+    }
+    out[(size_t)(g * REP + hh) * HD + i] = bf16_round(A / L);
+  }
+}
+
+int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
+  const int rep = a.n_heads / a.n_kv;
+  dim3 grid(a.n_kv, a.nsplit, a.batch), block(256);
+  cudaError_t e = cudaErrorInvalidValue;
+#define CL_ATT(R, D) e = launch_ex(attn_decode_kernel<R, D>, grid, block, 0, st, pdl, a)
+  if (a.head_dim == 128) {
+    if (rep == 1) CL_ATT(1, 128); else if (rep == 2) CL_ATT(2, 128); else if (rep == 4) CL_ATT(4, 128);
+    else if (rep == 8) CL_ATT(8, 128);
+  } else if (a.head_dim == 64) {
+    if (rep == 1) CL_ATT(1, 64); else if (rep == 2) CL_ATT(2, 64); else if (rep == 4) CL_ATT(4, 64);
+    else if (rep == 8) CL_ATT(8, 64);
+  }
+#undef CL_ATT
+  return e == cudaSuccess ? 1 : -1;
+}
+
+// ================================================================================================
+// embedding gather, argmax + sequence advance, synthetic weights
+// ================================================================================================
+__global__ void embed_kernel(const __nv_bfloat16* __restrict__ table, int d, const int* __restrict__ tok, float* h,
+                             int h_stride, const int* __restrict__ slots) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int slot = slots ? slots[blockIdx.y] : blockIdx.y;
+  const int id = tok[slot];
+  const uint4* row = reinterpret_cast<const uint4*>(table + (size_t)id * d);
+  float* out = h + (size_t)slot * h_stride;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d / 8; c += gridDim.x * blockDim.x) {
+    const uint4 w = row[c];
+    float4 a = make_float4(bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y));
+    float4 b2 = make_float4(bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w));
+    *reinterpret_cast<float4*>(out + c * 8) = a;
+    *reinterpret_cast<float4*>(out + c * 8 + 4) = b2;
+  }
+}
+
+int launch_embed(const __nv_bfloat16* table, int d, const int* tok, float* h, int h_stride, const int* slots, int batch,
+                 cudaStream_t st) {
+  int threads = 128;
+  int blocks = (d / 8 + threads - 1) / threads;
+  embed_kernel<<<dim3(blocks, batch), threads, 0, st>>>(table, d, tok, h, h_stride, slots);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+constexpr int kTailBlocks = 64;
+__global__ void __launch_bounds__(256) step_tail_kernel(const StepTailArgs a) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ int is_last_s;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int slot = a.slots ? a.slots[b] : b;
+  const float* lg = a.logits + (size_t)slot * a.vocab;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = blockIdx.x * 256 + tid; i < a.vocab; i += gridDim.x * 256) {
+    const float v = lg[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    a.part_val[(size_t)slot * gridDim.x + blockIdx.x] = best;
+    a.part_idx[(size_t)slot * gridDim.x + blockIdx.x] = bi;
+    __threadfence();
+    const unsigned old = atomicAdd(a.counters + slot, 1u);
+    is_last_s = (old == gridDim.x - 1);
+    if (is_last_s) a.counters[slot] = 0u;
+  }
+  __syncthreads();
+  if (!is_last_s || tid != 0) return;
+  __threadfence();
+  best = -INFINITY; bi = 0x7fffffff;
+  for (int i = 0; i < (int)gridDim.x; ++i) {
+    const float v = __ldcg(a.part_val + (size_t)slot * gridDim.x + i);
+    const int id = __ldcg(a.part_idx + (size_t)slot * gridDim.x + i);
+    if (v > best || (v == best && id < bi)) { best = v; bi = id; }
+  }
+  if (bi == 0x7fffffff) bi = 0;  // all-NaN logits: stay in range
+  a.tok[slot] = bi;
+  a.pos[slot] += 1;
+  const int step = *a.step_counter;  // same value for every batch entry of this step
+  a.ids_ring[(size_t)(step % a.ring_steps) * a.ring_stride + b] = bi;
+  // the step counter itself is bumped by step_bump_kernel after every batch entry has read it
+}
+
+// step counter bump: tiny kernel keeps the protocol obviously correct (1 thread).
+__global__ void step_bump_kernel(int* step_counter) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step_counter += 1;
+}
+
+int launch_step_tail(const StepTailArgs& a, cudaStream_t st) {
+  step_tail_kernel<<<dim3(kTailBlocks, a.batch), 256, 0, st>>>(a);
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  step_bump_kernel<<<1, 1, 0, st>>>(a.step_counter);
+  return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+__global__ void synth_bf16_kernel(__nv_bfloat16* out, int64_t n, int k_cols, int row_mult, int row_off, uint64_t seed,
+                                  int key, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k_cols, c = i - r * k_cols;
+    const float v = (float)synth_int(seed, key, (uint64_t)i) * scale;
+    out[(r * row_mult + row_off) * k_cols + c] = __float2bfloat16_rn(v);
+  }
+}
+int launch_synth_bf16(__nv_bfloat16* out, int64_t n_logical, int k_cols, int row_mult, int row_off, uint64_t seed,
+                      int key, float scale, cudaStream_t st) {
+  int blocks = (int)((n_logical + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  synth_bf16_kernel<<<blocks, 256, 0, st>>>(out, n_logical, k_cols, row_mult, row_off, seed, key, scale);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+__global__ void synth_gain_kernel(float* out, int n, uint64_t seed, int key, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = 1.0f + (float)synth_int(seed, key, (uint64_t)i) * scale;
+}
+int launch_synth_gain(float* out, int n, uint64_t seed, int key, float scale, cudaStream_t st) {
+  synth_gain_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, n, seed, key, scale);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* in, float* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, int64_t n, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  bf16_to_f32_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+__global__ void fill_u16_kernel(uint16_t* p, int64_t n, uint16_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+int launch_fill_u16(uint16_t* p, int64_t n, uint16_t v, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  fill_u16_kernel<<<blocks, 256, 0, st>>>(p, n, v);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace cl

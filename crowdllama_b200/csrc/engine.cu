@@ -1,0 +1,540 @@
+// engine.cu — the worker-side decode engine: weights, paged KV cache, the token step (CUDA graph
+// of hand-written sm_100a kernels), prefill, and the token-level entry points of the C-ABI.
+//
+// Replaces, behind crowdllama.UnifiedAPIHandler (/root/reference/pkg/crowdllama/api.go:19), the
+// whole chain WorkerAPIHandler -> callOllamaAPI -> embedded Ollama server -> llama.cpp runner
+// (api.go:45-160, /root/reference/cmd/crowdllama/main.go:283-297).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "engine.h"
+
+namespace cl {
+
+enum { K_EMBED = 0, K_LM_HEAD = 1, K_FINAL_NORM = 2, K_ATTN_NORM = 3, K_WQ = 4, K_WK = 5, K_WV = 6, K_WO = 7,
+       K_FFN_NORM = 8, K_WGATE = 9, K_WUP = 10, K_WDOWN = 11 };
+static constexpr float kLinearScale = 1.35e-4f;
+static constexpr float kNormScale = 1.0f / 4096.0f;
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+Engine::~Engine() {
+  stop_scheduler();
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+  for (void* p : allocs_) cudaFree(p);
+  if (h_logits_pinned_) cudaFreeHost(h_logits_pinned_);
+  if (h_ids_pinned_) cudaFreeHost(h_ids_pinned_);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+#define DMALLOC(ptr, bytes)                                          \
+  do {                                                               \
+    void* _p = nullptr;                                              \
+    cudaError_t _e = cudaMalloc(&_p, (bytes));                       \
+    if (_e != cudaSuccess) {                                         \
+      set_last_error(std::string("cudaMalloc(") + #ptr + ", " + std::to_string((size_t)(bytes)) + "): " + cudaGetErrorString(_e)); \
+      return _e == cudaErrorMemoryAllocation ? CL_ERR_OOM : CL_ERR_CUDA; \
+    }                                                                \
+    allocs_.push_back(_p);                                           \
+    ptr = reinterpret_cast<decltype(ptr)>(_p);                       \
+  } while (0)
+
+int Engine::init(const cl_engine_config& c) {
+  if (c.abi_version != CL_ABI_VERSION) { set_last_error("abi_version mismatch"); return CL_ERR_INVALID_ARG; }
+  if (c.preset) {
+    if (cl_model_preset(c.preset, &cfg) != CL_OK) { set_last_error("unknown preset"); return CL_ERR_UNKNOWN_MODEL; }
+  } else {
+    cfg = c.model;
+  }
+  model_name = c.model_name ? c.model_name : (c.preset ? c.preset : "model");
+  const int rep = cfg.n_kv_heads > 0 ? cfg.n_heads / cfg.n_kv_heads : 0;
+  if (cfg.n_layers <= 0 || cfg.d_model <= 0 || cfg.n_heads <= 0 || cfg.n_kv_heads <= 0 || cfg.d_ff <= 0 ||
+      cfg.vocab_size <= 1 || cfg.max_seq_len <= 0 || (cfg.head_dim != 64 && cfg.head_dim != 128) ||
+      cfg.n_heads % cfg.n_kv_heads || (rep != 1 && rep != 2 && rep != 4 && rep != 8) || cfg.d_model % 16 || cfg.d_ff % 16 ||
+      (cfg.vocab_size & 1)) {
+    set_last_error("unsupported model shape (need head_dim 64|128, heads/kv in {1,2,4,8}, d_model,d_ff %16==0, even vocab)");
+    return CL_ERR_INVALID_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_last_error("no CUDA device visible (libclengine has no CPU fallback)");
+    return CL_ERR_NO_DEVICE;
+  }
+  device_ = c.device;
+  if (device_ < 0 || device_ >= ndev) { set_last_error("bad device ordinal"); return CL_ERR_NO_DEVICE; }
+  CL_CUDA_OK(cudaSetDevice(device_));
+  cudaDeviceProp prop{};
+  CL_CUDA_OK(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major != 10) {
+    set_last_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", kernels are built for sm_100a only");
+    return CL_ERR_NO_DEVICE;
+  }
+  snprintf(gpu_name_, sizeof gpu_name_, "%s", prop.name);
+  vram_gb_ = (int)(prop.totalGlobalMem >> 30);
+
+  page_size_ = c.page_size ? c.page_size : 32;
+  if (page_size_ != 16 && page_size_ != 32 && page_size_ != 64) { set_last_error("page_size must be 16, 32 or 64"); return CL_ERR_INVALID_ARG; }
+  max_batch_ = c.max_batch > 0 ? c.max_batch : 8;
+  max_seqs_ = c.max_seqs > 0 ? c.max_seqs : max_batch_;
+  if (max_seqs_ < max_batch_) max_seqs_ = max_batch_;
+  use_graph_ = c.use_cuda_graph >= 0 && env_int("CL_GRAPH", 1) != 0;
+  use_pdl_ = env_int("CL_PDL", 1) != 0;
+  gemv_variant_ = c.decode_path == 1 ? 0 : 1;
+  gemv_variant_ = env_int("CL_GEMV_VARIANT", gemv_variant_);
+  q_dim_ = cfg.n_heads * cfg.head_dim;
+  kv_dim_ = cfg.n_kv_heads * cfg.head_dim;
+  qkv_dim_ = q_dim_ + 2 * kv_dim_;
+  nsplit_ = std::max(1, std::min(32, sm_count() / cfg.n_kv_heads));
+  nsplit_ = env_int("CL_ATTN_NSPLIT", nsplit_);
+  max_pages_per_seq_ = (cfg.max_seq_len + page_size_ - 1) / page_size_;
+
+  const size_t kv_bytes_per_token = (size_t)2 * cfg.n_layers * kv_dim_ * 2;
+  int64_t pool_bytes = c.kv_pool_bytes;
+  if (pool_bytes <= 0) pool_bytes = (int64_t)max_seqs_ * max_pages_per_seq_ * page_size_ * (int64_t)kv_bytes_per_token;
+  n_pages_ = (int)(pool_bytes / ((int64_t)page_size_ * (int64_t)kv_bytes_per_token));
+  if (n_pages_ < 1) { set_last_error("kv_pool_bytes too small for one page"); return CL_ERR_INVALID_ARG; }
+
+  CL_CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CL_CUDA_OK(cudaEventCreate(&ev0_));
+  CL_CUDA_OK(cudaEventCreate(&ev1_));
+  int rc = alloc_weights();
+  if (rc) return rc;
+  if (c.weights_path && *c.weights_path) {
+    set_last_error("weights_path: no checkpoint loader in this round; push tensors with cl_engine_set_tensor");
+    return CL_ERR_IO;
+  }
+  rc = fill_synthetic(c.weights_seed);
+  if (rc) return rc;
+  rc = alloc_state();
+  if (rc) return rc;
+  pool_.reset(new KvPool(n_pages_, page_size_));
+  seqs_.assign(max_seqs_, SeqState());
+  tok.reset(new Tokenizer(cfg.vocab_size));
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  if (c.start_scheduler) start_scheduler();
+  return CL_OK;
+}
+
+int Engine::alloc_weights() {
+  const size_t d = cfg.d_model, F = cfg.d_ff, V = cfg.vocab_size;
+  DMALLOC(embed_, V * d * 2);
+  DMALLOC(lm_head_, V * d * 2);
+  DMALLOC(final_norm_, d * 4);
+  layers_.resize(cfg.n_layers);
+  for (auto& L : layers_) {
+    DMALLOC(L.attn_norm, d * 4);
+    DMALLOC(L.ffn_norm, d * 4);
+    DMALLOC(L.wqkv, (size_t)qkv_dim_ * d * 2);
+    DMALLOC(L.wo, d * (size_t)q_dim_ * 2);
+    DMALLOC(L.wgu, 2 * F * d * 2);
+    DMALLOC(L.wdown, d * F * 2);
+  }
+  // RoPE table: computed on the host in double, rounded to fp32 — the same expression as
+  // oracle/llama_oracle.c build_rope(), so both sides use bit-identical cos/sin.
+  const int half = cfg.head_dim / 2;
+  std::vector<float2> tab((size_t)cfg.max_seq_len * half);
+  for (int p = 0; p < cfg.max_seq_len; ++p)
+    for (int i = 0; i < half; ++i) {
+      const double inv = pow((double)cfg.rope_theta, -2.0 * (double)i / (double)cfg.head_dim);
+      const double ang = (double)p * inv;
+      tab[(size_t)p * half + i] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+  DMALLOC(rope_, tab.size() * sizeof(float2));
+  CL_CUDA_OK(cudaMemcpy(rope_, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  kv_layer_elems_ = (size_t)n_pages_ * cfg.n_kv_heads * page_size_ * cfg.head_dim;
+  DMALLOC(kpool_, kv_layer_elems_ * cfg.n_layers * 2);
+  DMALLOC(vpool_, kv_layer_elems_ * cfg.n_layers * 2);
+  CL_CUDA_OK(cudaMemsetAsync(kpool_, 0, kv_layer_elems_ * cfg.n_layers * 2, stream_));
+  CL_CUDA_OK(cudaMemsetAsync(vpool_, 0, kv_layer_elems_ * cfg.n_layers * 2, stream_));
+  return CL_OK;
+}
+
+int Engine::fill_synthetic(uint64_t seed) {
+  const int d = cfg.d_model, F = cfg.d_ff, V = cfg.vocab_size;
+  int n = 0;
+  n += launch_synth_bf16(embed_, (int64_t)V * d, d, 1, 0, seed, K_EMBED, kLinearScale, stream_);
+  n += launch_synth_bf16(lm_head_, (int64_t)V * d, d, 1, 0, seed, K_LM_HEAD, kLinearScale, stream_);
+  n += launch_synth_gain(final_norm_, d, seed, K_FINAL_NORM, kNormScale, stream_);
+  for (int l = 0; l < cfg.n_layers; ++l) {
+    auto& L = layers_[l];
+    const int b = l * 16;
+    n += launch_synth_gain(L.attn_norm, d, seed, b + K_ATTN_NORM, kNormScale, stream_);
+    n += launch_synth_gain(L.ffn_norm, d, seed, b + K_FFN_NORM, kNormScale, stream_);
+    n += launch_synth_bf16(L.wqkv, (int64_t)q_dim_ * d, d, 1, 0, seed, b + K_WQ, kLinearScale, stream_);
+    n += launch_synth_bf16(L.wqkv + (size_t)q_dim_ * d, (int64_t)kv_dim_ * d, d, 1, 0, seed, b + K_WK, kLinearScale, stream_);
+    n += launch_synth_bf16(L.wqkv + (size_t)(q_dim_ + kv_dim_) * d, (int64_t)kv_dim_ * d, d, 1, 0, seed, b + K_WV, kLinearScale, stream_);
+    n += launch_synth_bf16(L.wo, (int64_t)d * q_dim_, q_dim_, 1, 0, seed, b + K_WO, kLinearScale, stream_);
+    n += launch_synth_bf16(L.wgu, (int64_t)F * d, d, 2, 0, seed, b + K_WGATE, kLinearScale, stream_);
+    n += launch_synth_bf16(L.wgu, (int64_t)F * d, d, 2, 1, seed, b + K_WUP, kLinearScale, stream_);
+    n += launch_synth_bf16(L.wdown, (int64_t)d * F, F, 1, 0, seed, b + K_WDOWN, kLinearScale, stream_);
+  }
+  launches_ += n;
+  CL_CUDA_OK(cudaGetLastError());
+  return CL_OK;
+}
+
+int Engine::set_tensor(int layer, int kind, const uint16_t* data, int64_t n) {
+  const int64_t d = cfg.d_model, F = cfg.d_ff, V = cfg.vocab_size;
+  auto copy16 = [&](__nv_bfloat16* dst, int64_t want) -> int {
+    if (n != want) { set_last_error("set_tensor: wrong element count"); return CL_ERR_INVALID_ARG; }
+    CL_CUDA_OK(cudaMemcpy(dst, data, (size_t)n * 2, cudaMemcpyHostToDevice));
+    return CL_OK;
+  };
+  auto copy_gain = [&](float* dst, int64_t want) -> int {
+    if (n != want) { set_last_error("set_tensor: wrong element count"); return CL_ERR_INVALID_ARG; }
+    std::vector<float> f((size_t)n);
+    for (int64_t i = 0; i < n; ++i) { uint32_t u = (uint32_t)data[i] << 16; memcpy(&f[i], &u, 4); }
+    CL_CUDA_OK(cudaMemcpy(dst, f.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    return CL_OK;
+  };
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  if (kind == K_EMBED) return copy16(embed_, V * d);
+  if (kind == K_LM_HEAD) return copy16(lm_head_, V * d);
+  if (kind == K_FINAL_NORM) return copy_gain(final_norm_, d);
+  if (layer < 0 || layer >= cfg.n_layers) { set_last_error("set_tensor: bad layer"); return CL_ERR_INVALID_ARG; }
+  auto& L = layers_[layer];
+  switch (kind) {
+    case K_ATTN_NORM: return copy_gain(L.attn_norm, d);
+    case K_FFN_NORM: return copy_gain(L.ffn_norm, d);
+    case K_WQ: return copy16(L.wqkv, (int64_t)q_dim_ * d);
+    case K_WK: return copy16(L.wqkv + (size_t)q_dim_ * d, (int64_t)kv_dim_ * d);
+    case K_WV: return copy16(L.wqkv + (size_t)(q_dim_ + kv_dim_) * d, (int64_t)kv_dim_ * d);
+    case K_WO: return copy16(L.wo, d * q_dim_);
+    case K_WDOWN: return copy16(L.wdown, d * F);
+    case K_WGATE:
+    case K_WUP: {
+      if (n != F * d) { set_last_error("set_tensor: wrong element count"); return CL_ERR_INVALID_ARG; }
+      // interleave on the device side with a strided 2-D copy: row r -> row 2r (+1 for up)
+      CL_CUDA_OK(cudaMemcpy2D(L.wgu + (kind == K_WUP ? d : 0), (size_t)2 * d * 2, data, (size_t)d * 2, (size_t)d * 2, (size_t)F,
+                              cudaMemcpyHostToDevice));
+      return CL_OK;
+    }
+    default: set_last_error("set_tensor: bad kind"); return CL_ERR_INVALID_ARG;
+  }
+}
+
+int Engine::alloc_state() {
+  const size_t S = max_seqs_, d = cfg.d_model;
+  DMALLOC(d_tok_, S * 4);
+  DMALLOC(d_pos_, S * 4);
+  DMALLOC(d_bt_, S * max_pages_per_seq_ * 4);
+  DMALLOC(d_slots_, (size_t)max_batch_ * 4);
+  DMALLOC(d_h_, S * d * 4);
+  DMALLOC(d_qkv_, S * qkv_dim_ * 4);
+  DMALLOC(d_attn_, S * q_dim_ * 4);
+  DMALLOC(d_act_, S * (size_t)cfg.d_ff * 4);
+  DMALLOC(d_logits_, S * (size_t)cfg.vocab_size * 4);
+  const int rep = cfg.n_heads / cfg.n_kv_heads;
+  DMALLOC(d_attn_part_, S * cfg.n_kv_heads * nsplit_ * rep * (cfg.head_dim + 2) * 4);
+  DMALLOC(d_attn_cnt_, S * cfg.n_kv_heads * 4);
+  DMALLOC(d_tail_val_, S * 64 * 4);
+  DMALLOC(d_tail_idx_, S * 64 * 4);
+  DMALLOC(d_tail_cnt_, S * 4);
+  DMALLOC(d_ids_ring_, (size_t)ring_steps_ * max_batch_ * 4);
+  DMALLOC(d_step_counter_, 4);
+  prompt_cap_ = cfg.max_seq_len;
+  DMALLOC(d_prompt_, (size_t)prompt_cap_ * 4);
+  CL_CUDA_OK(cudaMemsetAsync(d_tok_, 0, S * 4, stream_));
+  CL_CUDA_OK(cudaMemsetAsync(d_pos_, 0, S * 4, stream_));
+  CL_CUDA_OK(cudaMemsetAsync(d_bt_, 0, S * max_pages_per_seq_ * 4, stream_));
+  CL_CUDA_OK(cudaMemsetAsync(d_slots_, 0, (size_t)max_batch_ * 4, stream_));
+  CL_CUDA_OK(cudaMemsetAsync(d_attn_cnt_, 0, S * cfg.n_kv_heads * 4, stream_));
+  CL_CUDA_OK(cudaMemsetAsync(d_tail_cnt_, 0, S * 4, stream_));
+  CL_CUDA_OK(cudaMemsetAsync(d_step_counter_, 0, 4, stream_));
+  CL_CUDA_OK(cudaMallocHost(&h_logits_pinned_, (size_t)cfg.vocab_size * 4));
+  CL_CUDA_OK(cudaMallocHost(&h_ids_pinned_, (size_t)ring_steps_ * max_batch_ * 4));
+  return CL_OK;
+}
+
+// ---- sequences ----------------------------------------------------------------------------------
+int Engine::seq_create(cl_seq_t* out) {
+  for (int i = 0; i < max_seqs_; ++i)
+    if (!seqs_[i].live) {
+      seqs_[i] = SeqState();
+      seqs_[i].live = true;
+      *out = i;
+      return CL_OK;
+    }
+  set_last_error("no free sequence slot (max_seqs)");
+  return CL_ERR_OOM;
+}
+int Engine::seq_free(cl_seq_t s) {
+  if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+  pool_->release(s);
+  seqs_[s] = SeqState();
+  return CL_OK;
+}
+
+int Engine::ensure_capacity(cl_seq_t s, int n_tokens) {
+  if (n_tokens > cfg.max_seq_len) { set_last_error("sequence exceeds max_seq_len"); return CL_ERR_TOO_LONG; }
+  const size_t before = pool_->pages_of(s).size();
+  const int rc = pool_->reserve(s, n_tokens);
+  if (rc) { set_last_error("KV page pool exhausted"); return rc; }
+  const auto& pages = pool_->pages_of(s);
+  if (pages.size() != before)
+    CL_CUDA_OK(cudaMemcpyAsync(d_bt_ + (size_t)s * max_pages_per_seq_ + before, pages.data() + before,
+                               (pages.size() - before) * 4, cudaMemcpyHostToDevice, stream_));
+  return CL_OK;
+}
+
+// ---- one token step for the sequences listed in d_slots_[0..B) -----------------------------------
+int Engine::enqueue_step(int B, bool tail) {
+  const int d = cfg.d_model, F = cfg.d_ff;
+  int n = 0, r;
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; } while (0)
+  CL_LAUNCH(launch_embed(embed_, d, d_tok_, d_h_, d, d_slots_, B, stream_));
+  for (int l = 0; l < cfg.n_layers; ++l) {
+    const auto& L = layers_[l];
+    GemvArgs g;
+    g.slots = d_slots_; g.batch = B;
+    // (1) RMSNorm + fused q|k|v projection
+    g.W = L.wqkv; g.N = qkv_dim_; g.K = d; g.h = d_h_; g.gain = L.attn_norm; g.eps = cfg.rms_eps;
+    g.y = d_qkv_; g.x_stride = d; g.y_stride = qkv_dim_;
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_STORE, true, g, stream_, use_pdl_));
+    // (2) RoPE + KV append + paged GQA attention
+    AttnDecodeArgs a;
+    a.qkv = d_qkv_; a.qkv_stride = qkv_dim_; a.rope = rope_;
+    a.kpool = kpool_ + (size_t)l * kv_layer_elems_; a.vpool = vpool_ + (size_t)l * kv_layer_elems_;
+    a.block_tables = d_bt_; a.bt_stride = max_pages_per_seq_; a.pos = d_pos_;
+    a.out = d_attn_; a.out_stride = q_dim_; a.part = d_attn_part_; a.counters = d_attn_cnt_;
+    a.slots = d_slots_; a.batch = B; a.n_heads = cfg.n_heads; a.n_kv = cfg.n_kv_heads; a.head_dim = cfg.head_dim;
+    a.page_size = page_size_; a.nsplit = nsplit_;
+    CL_LAUNCH(launch_attn_decode(a, stream_, use_pdl_));
+    // (3) o projection + residual
+    GemvArgs o;
+    o.slots = d_slots_; o.batch = B;
+    o.W = L.wo; o.N = d; o.K = q_dim_; o.x = d_attn_; o.x_stride = q_dim_; o.y = d_h_; o.resid = d_h_; o.y_stride = d;
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, o, stream_, use_pdl_));
+    // (4) RMSNorm + gate/up + SiLU*mul
+    GemvArgs u;
+    u.slots = d_slots_; u.batch = B;
+    u.W = L.wgu; u.N = 2 * F; u.K = d; u.h = d_h_; u.gain = L.ffn_norm; u.eps = cfg.rms_eps; u.y = d_act_;
+    u.x_stride = d; u.y_stride = F;
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_GATEUP, true, u, stream_, use_pdl_));
+    // (5) down projection + residual
+    GemvArgs w;
+    w.slots = d_slots_; w.batch = B;
+    w.W = L.wdown; w.N = d; w.K = F; w.x = d_act_; w.x_stride = F; w.y = d_h_; w.resid = d_h_; w.y_stride = d;
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, w, stream_, use_pdl_));
+  }
+  GemvArgs lm;
+  lm.slots = d_slots_; lm.batch = B;
+  lm.W = lm_head_; lm.N = cfg.vocab_size; lm.K = d; lm.h = d_h_; lm.gain = final_norm_; lm.eps = cfg.rms_eps;
+  lm.y = d_logits_; lm.x_stride = d; lm.y_stride = cfg.vocab_size;
+  CL_LAUNCH(launch_gemv(gemv_variant_, EPI_STORE, true, lm, stream_, use_pdl_));
+  if (tail) {
+    StepTailArgs t;
+    t.logits = d_logits_; t.vocab = cfg.vocab_size; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
+    t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
+    t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = B;
+    CL_LAUNCH(launch_step_tail(t, stream_));
+  }
+#undef CL_LAUNCH
+  return n;
+}
+
+int Engine::run_step_graph(int B) {
+  if (use_graph_ && !graph_failed_) {
+    auto it = graphs_.find(B);
+    if (it == graphs_.end()) {
+      for (int attempt = 0; attempt < 2 && it == graphs_.end(); ++attempt) {
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ex = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal);
+        int n = e == cudaSuccess ? enqueue_step(B, true) : -1;
+        cudaError_t e2 = cudaStreamEndCapture(stream_, &g);
+        if (e == cudaSuccess && n > 0 && e2 == cudaSuccess && g) e = cudaGraphInstantiate(&ex, g, 0);
+        else e = cudaErrorUnknown;
+        if (g) cudaGraphDestroy(g);
+        if (e == cudaSuccess && ex) {
+          graphs_[B] = ex;
+          graph_nodes_[B] = n;
+          it = graphs_.find(B);
+        } else {
+          cudaGetLastError();
+          if (use_pdl_) {
+            fprintf(stderr, "[clengine] graph capture with PDL failed (%s); retrying without PDL\n", cudaGetErrorString(e));
+            use_pdl_ = false;
+          } else {
+            fprintf(stderr, "[clengine] graph capture failed (%s); falling back to eager launches\n", cudaGetErrorString(e));
+            graph_failed_ = true;
+            break;
+          }
+        }
+      }
+    }
+    if (it != graphs_.end()) {
+      CL_CUDA_OK(cudaGraphLaunch(it->second, stream_));
+      launches_ += graph_nodes_[B];
+      return CL_OK;
+    }
+  }
+  const int n = enqueue_step(B, true);
+  if (n < 0) return n;
+  launches_ += n;
+  return CL_OK;
+}
+
+int Engine::read_logits(int slot, float* out) {
+  CL_CUDA_OK(cudaMemcpyAsync(h_logits_pinned_, d_logits_ + (size_t)slot * cfg.vocab_size, (size_t)cfg.vocab_size * 4,
+                             cudaMemcpyDeviceToHost, stream_));
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  memcpy(out, h_logits_pinned_, (size_t)cfg.vocab_size * 4);
+  return CL_OK;
+}
+
+int Engine::set_single_slot(cl_seq_t s) {
+  if (last_single_slot_ != s) {
+    CL_CUDA_OK(cudaMemcpyAsync(d_slots_, &s, 4, cudaMemcpyHostToDevice, stream_));
+    last_single_slot_ = s;
+  }
+  return CL_OK;
+}
+
+int Engine::decode_step(cl_seq_t s, int32_t id, float* logits_out, int32_t* argmax_out) {
+  if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+  if (id < 0 || id >= cfg.vocab_size) { set_last_error("token id out of range"); return CL_ERR_INVALID_ARG; }
+  auto& q = seqs_[s];
+  int rc = ensure_capacity(s, q.len + 1);
+  if (rc) return rc;
+  const int hdr[2] = {id, q.len};
+  CL_CUDA_OK(cudaMemcpyAsync(d_tok_ + s, &hdr[0], 4, cudaMemcpyHostToDevice, stream_));
+  CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &hdr[1], 4, cudaMemcpyHostToDevice, stream_));
+  rc = set_single_slot(s);
+  if (rc) return rc;
+  rc = run_step_graph(1);
+  if (rc) return rc;
+  q.len += 1;
+  q.history.push_back(id);
+  if (logits_out) { rc = read_logits(s, logits_out); if (rc) return rc; }
+  if (argmax_out) {
+    CL_CUDA_OK(cudaMemcpyAsync(h_ids_pinned_, d_tok_ + s, 4, cudaMemcpyDeviceToHost, stream_));
+    CL_CUDA_OK(cudaStreamSynchronize(stream_));
+    *argmax_out = h_ids_pinned_[0];
+  } else {
+    CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  }
+  return CL_OK;
+}
+
+int Engine::prefill_tokenwise(cl_seq_t s, const int32_t* ids, int n, float* logits_out) {
+  auto& q = seqs_[s];
+  int rc = ensure_capacity(s, q.len + n);
+  if (rc) return rc;
+  CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+  CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &q.len, 4, cudaMemcpyHostToDevice, stream_));
+  rc = set_single_slot(s);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    CL_CUDA_OK(cudaMemcpyAsync(d_tok_ + s, d_prompt_ + i, 4, cudaMemcpyDeviceToDevice, stream_));
+    rc = run_step_graph(1);
+    if (rc) return rc;
+  }
+  q.len += n;
+  q.history.insert(q.history.end(), ids, ids + n);
+  if (logits_out) return read_logits(s, logits_out);
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  return CL_OK;
+}
+
+int Engine::prefill(cl_seq_t s, const int32_t* ids, int n, float* logits_out) {
+  if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+  if (n <= 0) { set_last_error("empty prompt"); return CL_ERR_INVALID_ARG; }
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= cfg.vocab_size) { set_last_error("token id out of range"); return CL_ERR_INVALID_ARG; }
+  if (seqs_[s].len + n > cfg.max_seq_len) { set_last_error("sequence exceeds max_seq_len"); return CL_ERR_TOO_LONG; }
+  if (n >= prefill_min_tokens_ && prefill_path_ok()) return prefill_chunked(s, ids, n, logits_out);
+  return prefill_tokenwise(s, ids, n, logits_out);
+}
+
+int Engine::decode_greedy(const cl_seq_t* ss, int B, const int32_t* first_ids, int n_steps, int32_t* ids_out, float* device_ms) {
+  if (B <= 0 || B > max_batch_ || n_steps <= 0) { set_last_error("bad batch / steps"); return CL_ERR_INVALID_ARG; }
+  for (int b = 0; b < B; ++b) {
+    const int s = ss[b];
+    if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+    for (int c = 0; c < b; ++c) if (ss[c] == s) { set_last_error("duplicate sequence in batch"); return CL_ERR_INVALID_ARG; }
+    if (first_ids[b] < 0 || first_ids[b] >= cfg.vocab_size) { set_last_error("token id out of range"); return CL_ERR_INVALID_ARG; }
+    const int rc = ensure_capacity(s, seqs_[s].len + n_steps);
+    if (rc) return rc;
+  }
+  for (int b = 0; b < B; ++b) {
+    const int s = ss[b];
+    CL_CUDA_OK(cudaMemcpyAsync(d_tok_ + s, &first_ids[b], 4, cudaMemcpyHostToDevice, stream_));
+    CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &seqs_[s].len, 4, cudaMemcpyHostToDevice, stream_));
+  }
+  CL_CUDA_OK(cudaMemcpyAsync(d_slots_, ss, (size_t)B * 4, cudaMemcpyHostToDevice, stream_));
+  last_single_slot_ = B == 1 ? ss[0] : -1;
+  float total_ms = 0.f;
+  for (int done = 0; done < n_steps;) {
+    const int chunk = std::min(ring_steps_, n_steps - done);
+    CL_CUDA_OK(cudaMemsetAsync(d_step_counter_, 0, 4, stream_));
+    CL_CUDA_OK(cudaEventRecord(ev0_, stream_));
+    for (int i = 0; i < chunk; ++i) {
+      const int rc = run_step_graph(B);
+      if (rc) return rc;
+    }
+    CL_CUDA_OK(cudaEventRecord(ev1_, stream_));
+    CL_CUDA_OK(cudaMemcpyAsync(h_ids_pinned_, d_ids_ring_, (size_t)chunk * max_batch_ * 4, cudaMemcpyDeviceToHost, stream_));
+    CL_CUDA_OK(cudaStreamSynchronize(stream_));
+    float ms = 0.f;
+    CL_CUDA_OK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    total_ms += ms;
+    for (int i = 0; i < chunk; ++i)
+      for (int b = 0; b < B; ++b) ids_out[(size_t)(done + i) * B + b] = h_ids_pinned_[(size_t)i * max_batch_ + b];
+    done += chunk;
+  }
+  for (int b = 0; b < B; ++b) {
+    auto& q = seqs_[ss[b]];
+    q.history.push_back(first_ids[b]);
+    for (int i = 0; i + 1 < n_steps; ++i) q.history.push_back(ids_out[(size_t)i * B + b]);
+    q.len += n_steps;
+  }
+  tokens_generated_ += (int64_t)n_steps * B;
+  if (total_ms > 0.f) {
+    const double tps = (double)n_steps * B / (total_ms * 1e-3);
+    tok_per_sec_ewma_ = tok_per_sec_ewma_ == 0.0 ? tps : 0.8 * tok_per_sec_ewma_ + 0.2 * tps;
+  }
+  if (device_ms) *device_ms = total_ms;
+  return CL_OK;
+}
+
+int Engine::debug_hidden(float* out, int n) {
+  if (last_single_slot_ < 0 || n != cfg.d_model) return CL_ERR_INVALID_ARG;
+  CL_CUDA_OK(cudaMemcpyAsync(out, d_h_ + (size_t)last_single_slot_ * cfg.d_model, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  return CL_OK;
+}
+
+int Engine::stats(cl_stats* out) {
+  memset(out, 0, sizeof *out);
+  out->tokens_per_sec = tok_per_sec_ewma_;
+  int active = 0;
+  for (auto& s : seqs_) active += s.live ? 1 : 0;
+  out->active_seqs = active;
+  out->load = std::min(1.0, (double)active / (double)max_batch_);
+  {
+    std::lock_guard<std::mutex> lk(q_mu_);
+    out->queue_depth = (int)queue_.size();
+  }
+  out->kv_pages_total = n_pages_;
+  out->kv_pages_used = pool_ ? pool_->used_pages() : 0;
+  out->tokens_generated = tokens_generated_;
+  out->requests_completed = requests_completed_;
+  out->preemptions = preemptions_;
+  out->vram_gb = vram_gb_;
+  memcpy(out->gpu_model, gpu_name_, sizeof out->gpu_model);
+  out->kernel_launches = launches_;
+  return CL_OK;
+}
+
+}  // namespace cl

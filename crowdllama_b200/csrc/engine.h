@@ -1,0 +1,218 @@
+// engine.h — internal C++ interface of libclengine.so (the C-ABI lives in include/clengine.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/clengine.h"
+#include "kernels.h"
+
+namespace cl {
+
+void set_last_error(const std::string& s);
+const char* get_last_error();
+
+#define CL_CUDA_OK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::cl::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+      return CL_ERR_CUDA;                                                                         \
+    }                                                                                             \
+  } while (0)
+
+// ---- paged-KV allocator: host-side free list + per-owner page lists (no GPU needed) -----------
+class KvPool {
+ public:
+  KvPool(int n_pages, int page_size);
+  int reserve(int owner, int n_tokens);  // CL_OK / CL_ERR_OOM (atomic: nothing taken on failure)
+  int release(int owner);
+  const std::vector<int>& pages_of(int owner);
+  int free_pages() const { return (int)free_.size(); }
+  int used_pages() const { return n_pages_ - (int)free_.size(); }
+  int n_pages() const { return n_pages_; }
+  int page_size() const { return page_size_; }
+
+ private:
+  int n_pages_, page_size_;
+  std::vector<int> free_;  // stack; low page ids are handed out first
+  std::map<int, std::vector<int>> owned_;
+  std::vector<int> empty_;
+};
+
+// ---- tokenizer: byte-level fallback (no vocab files exist offline) --------
+class Tokenizer {
+ public:
+  explicit Tokenizer(int vocab_size) : vocab_(vocab_size) {}
+  // ids 0..2 = <pad>, <bos>, <eos>; byte b -> 3 + b.  Needs vocab >= 259.
+  std::vector<int32_t> encode(const std::string& text, bool add_bos) const;
+  std::string decode(const std::vector<int32_t>& ids) const;
+  int bos() const { return 1; }
+  int eos() const { return 2; }
+  // chat framing the Ollama server applies upstream of the model (role forced to "user",
+  // api.go:111-116).  A neutral, documented framing is used because template files are absent.
+  std::string apply_chat_template(const std::string& user_prompt) const;
+
+ private:
+  int vocab_;
+};
+
+// ---- sampler (host; mirrors oracle oc_sample) ---------------------------------------------------
+int32_t sample_token(const float* logits, int32_t vocab, const cl_sampling& sp, const int32_t* history, int32_t n_history,
+                     uint64_t step);
+
+// ---- minimal protobuf codec for llama.v1.BaseMessage (pbmsg.cpp) -------------------------------
+struct PbGenerateRequest { std::string model, prompt; bool stream = false; };
+struct PbGenerateResponse {
+  std::string model, response, done_reason, worker_id;
+  int64_t created_at_sec = 0; int32_t created_at_nanos = 0;
+  bool done = false; int64_t total_duration = 0;
+};
+bool pb_decode_request(const uint8_t* data, size_t len, PbGenerateRequest* out);  // false: not a GenerateRequest
+std::vector<uint8_t> pb_encode_response(const PbGenerateResponse& r);
+
+struct LayerWeights {
+  float* attn_norm = nullptr;
+  float* ffn_norm = nullptr;
+  __nv_bfloat16* wqkv = nullptr;   // [(H + 2 KV) * D][d]   rows: q | k | v
+  __nv_bfloat16* wo = nullptr;     // [d][H * D]
+  __nv_bfloat16* wgu = nullptr;    // [2 F][d]             row 2i = gate_i, row 2i+1 = up_i
+  __nv_bfloat16* wdown = nullptr;  // [d][F]
+};
+
+struct SeqState {
+  bool live = false;
+  int len = 0;            // tokens whose K/V are in the cache
+  std::vector<int32_t> history;
+};
+
+struct Request;  // scheduler.cpp
+
+class Engine {
+ public:
+  Engine() = default;
+  ~Engine();
+  int init(const cl_engine_config& cfg);
+
+  // token-level API (callers hold mu_)
+  int seq_create(cl_seq_t* out);
+  int seq_free(cl_seq_t s);
+  int seq_len(cl_seq_t s, int32_t* out) { if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ; *out = seqs_[s].len; return CL_OK; }
+  int prefill(cl_seq_t s, const int32_t* ids, int n, float* logits_out);
+  int decode_step(cl_seq_t s, int32_t id, float* logits_out, int32_t* argmax_out);
+  int decode_greedy(const cl_seq_t* seqs, int n_seqs, const int32_t* first_ids, int n_steps, int32_t* ids_out,
+                    float* device_ms);
+  int set_tensor(int layer, int kind, const uint16_t* data, int64_t n);
+  int debug_hidden(float* out, int n);
+  int stats(cl_stats* out);
+
+  // request-level (scheduler.cpp)
+  int generate_ids(const int32_t* prompt, int n_prompt, const cl_sampling& sp, cl_result* out);
+  void scheduler_main();
+  void start_scheduler();
+  void stop_scheduler();
+
+  cl_model_config cfg{};
+  std::string model_name;
+  std::mutex mu_;               // serialises every GPU-touching call
+  std::unique_ptr<Tokenizer> tok;
+
+ private:
+  int alloc_weights();
+  int fill_synthetic(uint64_t seed);
+  int alloc_state();
+  int ensure_capacity(cl_seq_t s, int n_tokens);  // reserve pages + upload block table row
+  int enqueue_step(int B, bool tail);              // kernels of one token step for d_slots_[0..B)
+  int run_step_graph(int B);                       // graph launch (or eager enqueue)
+  int read_logits(int slot, float* out);
+  int prefill_tokenwise(cl_seq_t s, const int32_t* ids, int n, float* logits_out);
+  int prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits_out);  // tcgen05 path (prefill.cu)
+  bool prefill_path_ok() const;
+  int set_single_slot(cl_seq_t s);
+
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  int page_size_ = 32, max_batch_ = 8, max_seqs_ = 8, n_pages_ = 0, max_pages_per_seq_ = 0;
+  int gemv_variant_ = 1, nsplit_ = 16;
+  bool use_graph_ = true, use_pdl_ = true;
+  int qkv_dim_ = 0, q_dim_ = 0, kv_dim_ = 0;
+
+  // weights
+  std::vector<void*> allocs_;
+  __nv_bfloat16* embed_ = nullptr;
+  __nv_bfloat16* lm_head_ = nullptr;
+  float* final_norm_ = nullptr;
+  std::vector<LayerWeights> layers_;
+  float2* rope_ = nullptr;
+  __nv_bfloat16* kpool_ = nullptr;  // [L][n_pages][KV][P][D]
+  __nv_bfloat16* vpool_ = nullptr;
+  size_t kv_layer_elems_ = 0;
+
+  // per-slot state
+  int* d_tok_ = nullptr; int* d_pos_ = nullptr; int* d_bt_ = nullptr; int* d_slots_ = nullptr;
+  float* d_h_ = nullptr; float* d_qkv_ = nullptr; float* d_attn_ = nullptr; float* d_act_ = nullptr;
+  float* d_logits_ = nullptr; float* d_attn_part_ = nullptr; unsigned* d_attn_cnt_ = nullptr;
+  float* d_tail_val_ = nullptr; int* d_tail_idx_ = nullptr; unsigned* d_tail_cnt_ = nullptr;
+  int* d_ids_ring_ = nullptr; int* d_step_counter_ = nullptr; int* d_prompt_ = nullptr;
+  int ring_steps_ = 1024, prompt_cap_ = 0;
+  float* h_logits_pinned_ = nullptr; int* h_ids_pinned_ = nullptr;
+
+  // prefill workspace (allocated lazily)
+  struct PrefillWs {
+    int cap_tokens = 0;
+    __nv_bfloat16* xn = nullptr;    // [T][d]
+    float* qkv = nullptr;           // [T][qkv_dim]
+    __nv_bfloat16* q = nullptr;     // [T][q_dim]
+    __nv_bfloat16* attn = nullptr;  // [T][q_dim]
+    float* h = nullptr;             // [T][d]
+    float* gu = nullptr;            // [T][2F]
+    __nv_bfloat16* act = nullptr;   // [T][F]
+  };
+  std::unique_ptr<PrefillWs> pws_;
+  int prefill_chunk_tokens_ = 2048;
+
+  std::unique_ptr<KvPool> pool_;
+  std::vector<SeqState> seqs_;
+  std::map<int, cudaGraphExec_t> graphs_;
+  std::map<int, int> graph_nodes_;
+  int prefill_min_tokens_ = 16;
+  bool graph_failed_ = false;
+  int last_single_slot_ = -1;
+
+  // stats
+  std::atomic<int64_t> launches_{0}, tokens_generated_{0}, requests_completed_{0}, preemptions_{0};
+  double tok_per_sec_ewma_ = 0.0;
+  char gpu_name_[64] = {0};
+  int vram_gb_ = 0;
+
+  // scheduler
+  std::thread sched_thread_;
+  std::mutex q_mu_;
+  std::condition_variable q_cv_;
+  std::deque<std::shared_ptr<Request>> queue_;
+  std::vector<std::shared_ptr<Request>> active_;
+  std::atomic<bool> stop_{false};
+  bool sched_started_ = false;
+  friend struct Request;
+};
+
+}  // namespace cl
+
+struct cl_engine {
+  cl::Engine impl;
+};
+struct cl_kvpool {
+  cl::KvPool pool;
+  std::mutex mu;
+  cl_kvpool(int n, int p) : pool(n, p) {}
+};

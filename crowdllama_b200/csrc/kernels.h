@@ -1,0 +1,102 @@
+// kernels.h — host-side launch interface of the sm_100a kernels (internal to libclengine.so).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cl {
+
+enum GemvEpi { EPI_STORE = 0, EPI_RESID = 1, EPI_GATEUP = 2 };
+
+// y[slot] = epi(W * x[slot]).  Row pairs (2i, 2i+1) are always processed together so the
+// gate/up interleaving (row 2i = gate_i, row 2i+1 = up_i) needs no special casing.
+struct GemvArgs {
+  const __nv_bfloat16* W = nullptr;  // [N][K] row-major
+  int N = 0, K = 0;
+  const float* x = nullptr;          // !norm: [slot][x_stride] bf16-rounded fp32 inputs
+  const float* h = nullptr;          // norm: residual stream [slot][x_stride]
+  const float* gain = nullptr;       // norm gains [K]
+  float eps = 0.f;
+  float* y = nullptr;                // [slot][y_stride]
+  const float* resid = nullptr;      // EPI_RESID (may alias y)
+  int x_stride = 0, y_stride = 0;
+  const int* slots = nullptr;        // blockIdx.y = b -> slot (nullptr => identity)
+  int batch = 1;
+};
+
+struct AttnDecodeArgs {
+  const float* qkv = nullptr;        // [slot][qkv_stride] raw q | k | v of the current token
+  int qkv_stride = 0;
+  const float2* rope = nullptr;      // [max_pos][head_dim/2] (cos, sin)
+  __nv_bfloat16* kpool = nullptr;    // this layer: [n_pages][n_kv][page][head_dim]
+  __nv_bfloat16* vpool = nullptr;
+  const int* block_tables = nullptr; // [slot][bt_stride]
+  int bt_stride = 0;
+  const int* pos = nullptr;          // [slot] index of the current token
+  float* out = nullptr;              // [slot][out_stride] bf16-rounded fp32
+  int out_stride = 0;
+  float* part = nullptr;             // [slot][n_kv][nsplit][rep][head_dim + 2]
+  unsigned* counters = nullptr;      // [slot][n_kv]
+  const int* slots = nullptr;
+  int batch = 1;
+  int n_heads = 0, n_kv = 0, head_dim = 0, page_size = 0, nsplit = 0;
+};
+
+struct StepTailArgs {                // argmax over logits, advance the sequence
+  const float* logits = nullptr;     // [slot][vocab]
+  int vocab = 0;
+  int* tok = nullptr;                // [slot] next input token (written)
+  int* pos = nullptr;                // [slot] incremented
+  int* ids_ring = nullptr;           // [ring_steps][max_batch] generated ids
+  int* step_counter = nullptr;       // device scalar, incremented once per step
+  int ring_steps = 0, ring_stride = 0;
+  float* part_val = nullptr;         // [slot][nblk]
+  int* part_idx = nullptr;
+  unsigned* counters = nullptr;      // [slot]
+  const int* slots = nullptr;
+  int batch = 1;
+};
+
+// every launcher returns the number of kernels it enqueued (for cl_stats.kernel_launches)
+int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t st, bool pdl);
+int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
+int launch_embed(const __nv_bfloat16* table, int d, const int* tok, float* h, int h_stride, const int* slots,
+                 int batch, cudaStream_t st);
+int launch_step_tail(const StepTailArgs& a, cudaStream_t st);
+int launch_synth_bf16(__nv_bfloat16* out, int64_t n_logical, int k_cols, int row_mult, int row_off, uint64_t seed,
+                      int key, float scale, cudaStream_t st);
+int launch_synth_gain(float* out, int n, uint64_t seed, int key, float scale, cudaStream_t st);
+int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, int64_t n, cudaStream_t st);
+int launch_fill_u16(uint16_t* p, int64_t n, uint16_t v, cudaStream_t st);
+
+bool gemv_variant_supported(int variant, int N, int K);
+int sm_count();
+
+// ---- prefill path (prefill_kernels.cu / gemm_tcgen05.cu) -----------------------------------------
+// X bf16 [T][K] row-major, W bf16 [N][K] row-major -> Y fp32 [T][N] (+= resid when resid != nullptr)
+int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, const float* resid, int T, int N, int K,
+                     cudaStream_t st);
+bool gemm_tcgen05_supported(int T, int N, int K);
+// xn[t] = bf16(rmsnorm(h[t]) * gain)
+int launch_rmsnorm_bf16(const float* h, const float* gain, float eps, __nv_bfloat16* out, int T, int d, cudaStream_t st);
+// rope q,k of T tokens starting at pos0; q -> bf16 [T][H][D]; k,v -> paged cache (bf16) and optional dense copies
+struct RopeScatterArgs {
+  const float* qkv; int qkv_stride; const float2* rope; int pos0; int T;
+  __nv_bfloat16* q_out;              // [T][H*D]
+  __nv_bfloat16* kpool; __nv_bfloat16* vpool; const int* block_table; int page_size;
+  int n_heads, n_kv, head_dim;
+};
+int launch_rope_scatter(const RopeScatterArgs& a, cudaStream_t st);
+// causal attention of T new tokens (positions pos0..pos0+T-1) against the paged cache
+struct AttnPrefillArgs {
+  const __nv_bfloat16* q;            // [T][H*D] roped
+  const __nv_bfloat16* kpool; const __nv_bfloat16* vpool; const int* block_table; int page_size;
+  int pos0, T, n_heads, n_kv, head_dim;
+  __nv_bfloat16* out;                // [T][H*D]
+};
+int launch_attn_prefill(const AttnPrefillArgs& a, cudaStream_t st);
+// act = bf16(silu(gu[:, 2i]) * gu[:, 2i+1])
+int launch_silu_mul_bf16(const float* gu, __nv_bfloat16* act, int T, int d_ff, cudaStream_t st);
+int launch_embed_rows(const __nv_bfloat16* table, int d, const int* ids_dev, float* h, int T, cudaStream_t st);
+
+}  // namespace cl

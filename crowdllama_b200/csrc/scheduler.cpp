@@ -1,0 +1,307 @@
+// scheduler.cpp — request-level path: continuous-batching scheduler behind cl_generate().
+//
+// Replaces what the reference gets from the Ollama server's own scheduler (UPSTREAM of
+// /root/reference/pkg/crowdllama/api.go:129-139).  Callers are the per-stream goroutines of
+// Peer.handleInferenceRequest (/root/reference/pkg/peer/peer.go:190-256): many may block in
+// cl_generate at once; the scheduler thread batches their decode steps (iteration-level
+// scheduling) and preempts-by-recompute when the paged KV pool runs dry.
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+
+#include "engine.h"
+
+namespace cl {
+
+static int64_t now_ns() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Request {
+  std::vector<int32_t> prompt;
+  cl_sampling sp{};
+  std::vector<int32_t> out;
+  cl_seq_t seq = -1;
+  int max_new = 0;
+  int n_preempted = 0;
+  int status = CL_OK;
+  std::string done_reason, err;
+  bool done = false;
+  std::mutex m;
+  std::condition_variable cv;
+  int64_t t_arrive = 0, prefill_ns = 0, decode_ns = 0, t_done = 0;
+  uint64_t arrival = 0;
+  bool greedy() const { return sp.temperature <= 0.f; }
+};
+
+static void fill_result(const Request& r, cl_result* out, const Tokenizer* tok) {
+  memset(out, 0, sizeof *out);
+  out->n_prompt = (int32_t)r.prompt.size();
+  out->n_generated = (int32_t)r.out.size();
+  out->token_ids = (int32_t*)malloc(sizeof(int32_t) * std::max<size_t>(1, r.out.size()));
+  if (!r.out.empty()) memcpy(out->token_ids, r.out.data(), r.out.size() * 4);
+  std::string text = tok ? tok->decode(r.out) : std::string();
+  out->text = (char*)malloc(text.size() + 1);
+  memcpy(out->text, text.c_str(), text.size() + 1);
+  out->text_len = text.size();
+  out->done_reason = strdup(r.done_reason.c_str());
+  out->prefill_ns = r.prefill_ns;
+  out->decode_ns = r.decode_ns;
+  out->total_ns = r.t_done - r.t_arrive;
+  out->n_preempted = r.n_preempted;
+}
+
+static bool finished(Request& r, int eos, int max_seq_len) {
+  if (!r.out.empty() && !r.sp.ignore_eos && r.out.back() == eos) { r.done_reason = "stop"; return true; }
+  if ((int)r.out.size() >= r.max_new) { r.done_reason = "length"; return true; }
+  if ((int)(r.prompt.size() + r.out.size()) >= max_seq_len) { r.done_reason = "length"; return true; }
+  return false;
+}
+
+// ---- synchronous path (no scheduler thread): one request at a time under the engine lock --------
+static int generate_sync(Engine& e, Request& r) {
+  std::lock_guard<std::mutex> lk(e.mu_);
+  const int V = e.cfg.vocab_size;
+  int rc = e.seq_create(&r.seq);
+  if (rc) return rc;
+  std::vector<float> logits(V);
+  int64_t t0 = now_ns();
+  rc = e.prefill(r.seq, r.prompt.data(), (int)r.prompt.size(), logits.data());
+  r.prefill_ns = now_ns() - t0;
+  if (rc) { e.seq_free(r.seq); return rc; }
+  t0 = now_ns();
+  std::vector<int32_t> hist(r.prompt);
+  int32_t next = sample_token(logits.data(), V, r.sp, hist.data(), (int)hist.size(), 0);
+  r.out.push_back(next);
+  while (!finished(r, e.tok->eos(), e.cfg.max_seq_len)) {
+    if (r.greedy()) {
+      int room = std::min(r.max_new - (int)r.out.size(), e.cfg.max_seq_len - (int)(r.prompt.size() + r.out.size()));
+      int chunk = std::min(room, 32);
+      std::vector<int32_t> ids(chunk);
+      rc = e.decode_greedy(&r.seq, 1, &next, chunk, ids.data(), nullptr);
+      if (rc) break;
+      for (int i = 0; i < chunk; ++i) {
+        r.out.push_back(ids[i]);
+        if (finished(r, e.tok->eos(), e.cfg.max_seq_len)) break;
+      }
+      next = r.out.back();
+    } else {
+      rc = e.decode_step(r.seq, next, logits.data(), nullptr);
+      if (rc) break;
+      hist.push_back(next);
+      next = sample_token(logits.data(), V, r.sp, hist.data(), (int)hist.size(), (uint64_t)r.out.size());
+      r.out.push_back(next);
+    }
+  }
+  r.decode_ns = now_ns() - t0;
+  e.seq_free(r.seq);
+  r.seq = -1;
+  return rc;
+}
+
+int Engine::generate_ids(const int32_t* prompt, int n_prompt, const cl_sampling& sp, cl_result* out) {
+  if (!prompt || n_prompt <= 0 || !out) { set_last_error("empty prompt"); return CL_ERR_INVALID_ARG; }
+  if (n_prompt >= cfg.max_seq_len) { set_last_error("prompt longer than max_seq_len"); return CL_ERR_TOO_LONG; }
+  for (int i = 0; i < n_prompt; ++i)
+    if (prompt[i] < 0 || prompt[i] >= cfg.vocab_size) { set_last_error("token id out of range"); return CL_ERR_INVALID_ARG; }
+  auto r = std::make_shared<Request>();
+  r->prompt.assign(prompt, prompt + n_prompt);
+  r->sp = sp;
+  r->max_new = sp.max_new_tokens > 0 ? sp.max_new_tokens : cfg.max_seq_len - n_prompt;
+  r->max_new = std::min(r->max_new, cfg.max_seq_len - n_prompt);
+  r->t_arrive = now_ns();
+  if (!sched_started_) {
+    r->status = generate_sync(*this, *r);
+    if (r->status == CL_OK) { requests_completed_++; tokens_generated_ += (int64_t)r->out.size(); }
+  } else {
+    {
+      std::lock_guard<std::mutex> lk(q_mu_);
+      if (stop_) { set_last_error("engine shutting down"); return CL_ERR_SHUTDOWN; }
+      static std::atomic<uint64_t> counter{0};
+      r->arrival = counter++;
+      queue_.push_back(r);
+    }
+    q_cv_.notify_all();
+    std::unique_lock<std::mutex> lk(r->m);
+    r->cv.wait(lk, [&] { return r->done; });
+  }
+  r->t_done = now_ns();
+  if (r->status != CL_OK) {
+    if (!r->err.empty()) set_last_error(r->err);
+    return r->status;
+  }
+  fill_result(*r, out, tok.get());
+  return CL_OK;
+}
+
+void Engine::start_scheduler() {
+  if (sched_started_) return;
+  stop_ = false;
+  sched_started_ = true;
+  sched_thread_ = std::thread([this] { scheduler_main(); });
+}
+
+void Engine::stop_scheduler() {
+  if (!sched_started_) return;
+  {
+    std::lock_guard<std::mutex> lk(q_mu_);
+    stop_ = true;
+  }
+  q_cv_.notify_all();
+  if (sched_thread_.joinable()) sched_thread_.join();
+  sched_started_ = false;
+}
+
+static void complete(std::shared_ptr<Request>& r, int status, const std::string& err) {
+  std::lock_guard<std::mutex> lk(r->m);
+  r->status = status;
+  r->err = err;
+  r->done = true;
+  r->cv.notify_all();
+}
+
+void Engine::scheduler_main() {
+  cudaSetDevice(device_);
+  const int V = cfg.vocab_size;
+  std::vector<float> logits(V);
+  std::vector<int32_t> toks(max_seqs_);
+  std::vector<int> slots;
+  std::vector<int> last_slots;
+  while (true) {
+    {
+      std::unique_lock<std::mutex> lk(q_mu_);
+      q_cv_.wait(lk, [&] { return stop_ || !queue_.empty() || !active_.empty(); });
+      if (stop_) break;
+    }
+    std::lock_guard<std::mutex> elk(mu_);
+    // ---- admit (prefill) while there is batch room
+    while ((int)active_.size() < max_batch_) {
+      std::shared_ptr<Request> r;
+      {
+        std::lock_guard<std::mutex> lk(q_mu_);
+        if (queue_.empty()) break;
+        r = queue_.front();
+      }
+      std::vector<int32_t> full(r->prompt);
+      full.insert(full.end(), r->out.begin(), r->out.end());
+      const int need_pages = ((int)full.size() + 1 + page_size_ - 1) / page_size_;
+      if (need_pages > pool_->free_pages()) {
+        if (active_.empty()) {
+          { std::lock_guard<std::mutex> lk(q_mu_); queue_.pop_front(); }
+          complete(r, CL_ERR_OOM, "prompt does not fit in the KV page pool");
+          continue;
+        }
+        break;  // wait for running requests to release pages
+      }
+      { std::lock_guard<std::mutex> lk(q_mu_); queue_.pop_front(); }
+      int rc = seq_create(&r->seq);
+      if (rc) { complete(r, rc, get_last_error()); continue; }
+      const int64_t t0 = now_ns();
+      rc = prefill(r->seq, full.data(), (int)full.size(), logits.data());
+      r->prefill_ns += now_ns() - t0;
+      if (rc) { seq_free(r->seq); complete(r, rc, get_last_error()); continue; }
+      const int32_t next = sample_token(logits.data(), V, r->sp, full.data(), (int)full.size(), (uint64_t)r->out.size());
+      r->out.push_back(next);
+      if (!r->greedy()) cudaMemcpyAsync(d_tok_ + r->seq, &r->out.back(), 4, cudaMemcpyHostToDevice, stream_);
+      if (finished(*r, tok->eos(), cfg.max_seq_len)) {
+        seq_free(r->seq);
+        requests_completed_++;
+        tokens_generated_ += 1;
+        complete(r, CL_OK, "");
+        continue;
+      }
+      active_.push_back(r);
+    }
+    if (active_.empty()) continue;
+    // ---- make room for one more token per active request; preempt the youngest on OOM
+    for (size_t i = 0; i < active_.size();) {
+      auto& r = active_[i];
+      int rc = ensure_capacity(r->seq, seqs_[r->seq].len + 1);
+      if (rc == CL_ERR_OOM && active_.size() > 1) {
+        size_t victim = 0;
+        for (size_t k = 1; k < active_.size(); ++k) if (active_[k]->arrival > active_[victim]->arrival) victim = k;
+        auto v = active_[victim];
+        seq_free(v->seq);
+        v->seq = -1;
+        v->n_preempted++;
+        preemptions_++;
+        active_.erase(active_.begin() + victim);
+        { std::lock_guard<std::mutex> lk(q_mu_); queue_.push_front(v); }
+        i = 0;  // restart the capacity pass
+        continue;
+      }
+      if (rc) {
+        seq_free(r->seq);
+        auto dead = r;
+        active_.erase(active_.begin() + i);
+        complete(dead, rc, get_last_error());
+        continue;
+      }
+      ++i;
+    }
+    if (active_.empty()) continue;
+    // ---- one batched decode step
+    const int B = (int)active_.size();
+    slots.resize(B);
+    for (int b = 0; b < B; ++b) slots[b] = active_[b]->seq;
+    if (slots != last_slots) {
+      cudaMemcpyAsync(d_slots_, slots.data(), (size_t)B * 4, cudaMemcpyHostToDevice, stream_);
+      last_slots = slots;
+      last_single_slot_ = B == 1 ? slots[0] : -1;
+    }
+    const int64_t t0 = now_ns();
+    int rc = run_step_graph(B);
+    if (rc == CL_OK) {
+      cudaMemcpyAsync(toks.data(), d_tok_, (size_t)max_seqs_ * 4, cudaMemcpyDeviceToHost, stream_);
+      if (cudaStreamSynchronize(stream_) != cudaSuccess) rc = CL_ERR_CUDA;
+    }
+    if (rc) {
+      const std::string err = get_last_error();
+      for (auto& r : active_) { seq_free(r->seq); complete(r, rc, err); }
+      active_.clear();
+      last_slots.clear();
+      continue;
+    }
+    for (int b = 0; b < B; ++b) {
+      auto& r = active_[b];
+      auto& st = seqs_[r->seq];
+      st.history.push_back(r->out.back());
+      st.len += 1;
+      int32_t next = toks[r->seq];
+      if (!r->greedy()) {
+        read_logits(r->seq, logits.data());
+        next = sample_token(logits.data(), V, r->sp, st.history.data(), (int)st.history.size(), (uint64_t)r->out.size());
+        cudaMemcpyAsync(d_tok_ + r->seq, &next, 4, cudaMemcpyHostToDevice, stream_);
+        cudaStreamSynchronize(stream_);
+      }
+      r->out.push_back(next);
+    }
+    const int64_t dt = now_ns() - t0;
+    for (auto& r : active_) r->decode_ns += dt;
+    tokens_generated_ += B;
+    const double tps = (double)B / ((double)dt * 1e-9);
+    tok_per_sec_ewma_ = tok_per_sec_ewma_ == 0.0 ? tps : 0.9 * tok_per_sec_ewma_ + 0.1 * tps;
+    // ---- retire finished requests
+    for (size_t i = 0; i < active_.size();) {
+      auto r = active_[i];
+      if (finished(*r, tok->eos(), cfg.max_seq_len)) {
+        seq_free(r->seq);
+        active_.erase(active_.begin() + i);
+        requests_completed_++;
+        complete(r, CL_OK, "");
+      } else {
+        ++i;
+      }
+    }
+  }
+  // shutdown: fail whatever is left
+  std::lock_guard<std::mutex> elk(mu_);
+  for (auto& r : active_) { if (r->seq >= 0) seq_free(r->seq); complete(r, CL_ERR_SHUTDOWN, "engine shutting down"); }
+  active_.clear();
+  std::deque<std::shared_ptr<Request>> rest;
+  { std::lock_guard<std::mutex> lk(q_mu_); rest.swap(queue_); }
+  for (auto& r : rest) complete(r, CL_ERR_SHUTDOWN, "engine shutting down");
+}
+
+}  // namespace cl

@@ -17,7 +17,7 @@
  *   - the library never retains caller pointers after a call returns (cgo rule); strings and
  *     id arrays handed back in cl_result are malloc()'d by the library and released with
  *     cl_result_free().
- *   - cl_generate*/cl_engine_stats are thread-safe and re-entrant (one goroutine per inbound
+ *   - cl_generate(), cl_generate_ids(), cl_engine_stats() are thread-safe and re-entrant (one goroutine per inbound
  *     libp2p stream calls the handler concurrently: /root/reference/pkg/peer/peer.go:177-182).
  *     The token-level cl_seq_* / cl_prefill / cl_decode_step calls are serialised internally by one engine lock.
  *   - there is NO CPU fallback: if no sm_100 device is present cl_engine_create fails with
@@ -144,6 +144,11 @@ int cl_engine_create(const cl_engine_config* cfg, cl_engine** out);
 void cl_engine_destroy(cl_engine* e);
 int cl_engine_model_config(const cl_engine* e, cl_model_config* out);
 int cl_engine_stats(cl_engine* e, cl_stats* out);
+/* Overwrite one weight tensor from host memory (bf16 bits, logical [out][in] row-major; norm
+ * gains as bf16 too).  kind: 0 embed, 1 lm_head, 2 final_norm, 3 attn_norm, 4 wq, 5 wk, 6 wv,
+ * 7 wo, 8 ffn_norm, 9 w_gate, 10 w_up, 11 w_down (same numbering as the synthetic generator).
+ * Used to load real checkpoints tensor by tensor and by the HF golden-vector parity tests. */
+int cl_engine_set_tensor(cl_engine* e, int32_t layer, int32_t kind, const uint16_t* data, int64_t n);
 
 /* ---- request level (what the Go shim calls) --------------------------------------------- */
 /* replaces: callOllamaAPI, api.go:108-160.  Blocking; enqueues into the continuous-batching

@@ -26,12 +26,19 @@ OUT = Path(__file__).resolve().parent
 
 def hf_fixture(kind: str, path: Path, seed: int):
     from transformers import LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM
-    cfg = dict(n_layers=3, d_model=64, n_heads=4, n_kv_heads=2, head_dim=16, d_ff=160, vocab_size=384,
-               max_seq_len=64, rope_theta=10000.0 if kind == "llama" else 1e6, rms_eps=1e-5)
+    # head_dim 64 and heads/kv in {2, 4} so the same fixtures also drive the CUDA engine
+    # (its attention kernels are built for head_dim 64|128).
+    if kind == "llama":
+        cfg = dict(n_layers=2, d_model=128, n_heads=2, n_kv_heads=1, head_dim=64, d_ff=256, vocab_size=256,
+                   max_seq_len=64, rope_theta=10000.0, rms_eps=1e-5)
+    else:
+        cfg = dict(n_layers=2, d_model=128, n_heads=4, n_kv_heads=1, head_dim=64, d_ff=192, vocab_size=320,
+                   max_seq_len=64, rope_theta=1e6, rms_eps=1e-5)
     common = dict(hidden_size=cfg["d_model"], intermediate_size=cfg["d_ff"], num_hidden_layers=cfg["n_layers"],
                   num_attention_heads=cfg["n_heads"], num_key_value_heads=cfg["n_kv_heads"],
                   vocab_size=cfg["vocab_size"], max_position_embeddings=cfg["max_seq_len"],
                   rms_norm_eps=cfg["rms_eps"], rope_theta=cfg["rope_theta"], tie_word_embeddings=False,
+                  head_dim=cfg["head_dim"],
                   attention_bias=False, hidden_act="silu")
     torch.manual_seed(seed)
     if kind == "llama":

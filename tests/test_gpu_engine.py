@@ -1,0 +1,188 @@
+"""End-to-end parity of the CUDA engine (through the C-ABI) against the CPU oracle and the HF golden vectors."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from crowdllama_b200 import engine as eng
+from oracle import oracle as oc
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+
+LOGIT_TOL = 0.125          # max-abs on logits; observed errors are ~1e-3
+MARGIN_TOL = 2e-2          # a greedy mismatch is only tolerated where the oracle's top-2 margin is below this
+
+
+def _prompt(n, vocab):
+    return np.array([(i * 7919 + 13) % vocab for i in range(n)], np.int32)
+
+
+def _compare_greedy(e, m, prompt, n_steps):
+    """Teacher-forced comparison: both sides consume the ORACLE's greedy tokens; logits must agree
+    within LOGIT_TOL at every step and argmax must be identical unless the oracle's margin is tiny."""
+    so = m.new_seq()
+    lo = so.forward(prompt)
+    s = e.seq_create()
+    lg = e.prefill(s, prompt)
+    errs, mism = [float(np.abs(lg - lo).max())], 0
+    tok = int(lo.argmax())
+    for _ in range(n_steps):
+        if int(lg.argmax()) != tok:
+            top2 = np.sort(lo)[-2:]
+            assert top2[1] - top2[0] < MARGIN_TOL, "greedy token differs at a clear margin"
+            mism += 1
+        lo = so.forward([tok])
+        lg, _ = e.decode_step(s, tok)
+        errs.append(float(np.abs(lg - lo).max()))
+        tok = int(lo.argmax())
+    e.seq_free(s)
+    assert max(errs) < LOGIT_TOL, max(errs)
+    return max(errs), mism
+
+
+@pytest.mark.parametrize("decode_path", [1, 2])
+@pytest.mark.parametrize("graph", [True, False])
+def test_tiny_engine_matches_oracle(decode_path, graph):
+    cfg = oc.PRESETS["tiny-test"]
+    m = oc.Model(cfg, seed=1234)
+    with eng.Engine(preset="tiny-test", seed=1234, decode_path=decode_path, use_cuda_graph=graph) as e:
+        err, mism = _compare_greedy(e, m, _prompt(12, cfg["vocab_size"]), 40)
+        assert mism == 0
+        # free-running greedy: device loop vs oracle loop
+        prompt = _prompt(9, cfg["vocab_size"])
+        so = m.new_seq()
+        first = int(so.forward(prompt).argmax())
+        ref_ids, margins = so.greedy(first, 48)
+        s = e.seq_create()
+        lg = e.prefill(s, prompt)
+        assert int(lg.argmax()) == first
+        ids, ms = e.decode_greedy(s, first, 48)
+        if margins.min() > MARGIN_TOL:
+            np.testing.assert_array_equal(ids, ref_ids)
+        else:
+            k = int(np.argmax(margins <= MARGIN_TOL))
+            np.testing.assert_array_equal(ids[:k], ref_ids[:k])
+        assert e.seq_len(s) == 9 + 48
+        assert e.stats()["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz"])
+def test_engine_matches_hf_golden(fixture):
+    """The HF transformers logits (tests/golden/make_golden.py) pin the CUDA engine directly."""
+    z = np.load(G / fixture)
+    cfg = {k: (float(v) if k in ("rope_theta", "rms_eps") else int(v)) for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    with eng.Engine(model=cfg, decode_path=1) as e:
+        e.set_tensor(0, "EMBED", z["embed"])
+        e.set_tensor(0, "LM_HEAD", z["lm_head"])
+        e.set_tensor(0, "FINAL_NORM", z["final_norm"])
+        for l in range(cfg["n_layers"]):
+            for k in ("ATTN_NORM", "FFN_NORM", "WQ", "WK", "WV", "WO", "WGATE", "WUP", "WDOWN"):
+                e.set_tensor(l, k, z[f"L{l}.{k}"])
+        ids, ref = z["ids"], z["logits"]
+        s = e.seq_create()
+        got = [e.prefill(s, ids[:1])]
+        for t in ids[1:]:
+            got.append(e.decode_step(s, int(t))[0])
+        got = np.stack(got)
+        rms = float(np.sqrt((ref ** 2).mean()))
+        assert np.abs(got - ref).max() < 5e-2 * rms       # bf16 rounding points vs HF fp32 math
+        agree = (got.argmax(-1) == ref.argmax(-1)).mean()
+        assert agree >= 0.9
+
+
+def test_batched_decode_equals_single():
+    with eng.Engine(preset="tiny-test", seed=5, max_batch=4) as e:
+        V = e.cfg["vocab_size"]
+        prompts = [_prompt(5 + 3 * i, V) + i for i in range(3)]
+        singles = []
+        for p in prompts:
+            s = e.seq_create()
+            first = int(e.prefill(s, p % V).argmax())
+            ids, _ = e.decode_greedy(s, first, 20)
+            singles.append((first, ids))
+            e.seq_free(s)
+        seqs, firsts = [], []
+        for p in prompts:
+            s = e.seq_create()
+            firsts.append(int(e.prefill(s, p % V).argmax()))
+            seqs.append(s)
+        ids, _ = e.decode_greedy_batch(seqs, firsts, 20)
+        for b, (first, ref) in enumerate(singles):
+            assert firsts[b] == first
+            np.testing.assert_array_equal(ids[:, b], ref)
+
+
+def test_page_boundaries_and_pool_exhaustion():
+    # 4 pages of 16 tokens: a 2-layer tiny model; one sequence may hold at most 64 tokens
+    cfg = oc.PRESETS["tiny-test"]
+    kv_bytes_per_token = 2 * cfg["n_layers"] * cfg["n_kv_heads"] * cfg["head_dim"] * 2
+    with eng.Engine(preset="tiny-test", seed=9, page_size=16, kv_pool_bytes=4 * 16 * kv_bytes_per_token) as e:
+        m = oc.Model(cfg, seed=9)
+        p = _prompt(15, cfg["vocab_size"])
+        so = m.new_seq()
+        first = int(so.forward(p).argmax())
+        ref, margins = so.greedy(first, 40)           # crosses pages at 16, 32, 48
+        s = e.seq_create()
+        assert int(e.prefill(s, p).argmax()) == first
+        ids, _ = e.decode_greedy(s, first, 40)
+        if margins.min() > MARGIN_TOL:
+            np.testing.assert_array_equal(ids, ref)
+        assert e.stats()["kv_pages_used"] == 4
+        with pytest.raises(eng.EngineError) as ei:
+            e.decode_greedy(s, int(ids[-1]), 20)       # 55 + 20 > 64 tokens of pool
+        assert ei.value.status == eng.CL_ERR_OOM
+        e.seq_free(s)
+        assert e.stats()["kv_pages_used"] == 0
+
+
+def test_generate_ids_greedy_and_sampled_match_oracle_sampler():
+    cfg = oc.PRESETS["tiny-test"]
+    m = oc.Model(cfg, seed=21)
+    with eng.Engine(preset="tiny-test", seed=21) as e:
+        p = _prompt(7, cfg["vocab_size"])
+        r = e.generate_ids(p, eng.greedy(16, ignore_eos=True))
+        so = m.new_seq()
+        first = int(so.forward(p).argmax())
+        ref, margins = so.greedy(first, 15)
+        assert r.n_generated == 16 and r.done_reason == "length"
+        assert r.token_ids[0] == first
+        if margins.min() > MARGIN_TOL:
+            np.testing.assert_array_equal(r.token_ids[1:], ref)
+        # stochastic path: the engine's host sampler equals the oracle sampler on the engine's own logits
+        sp = eng.ollama_default_sampling(seed=77, max_new_tokens=12)
+        sp.ignore_eos = 1
+        r2 = e.generate_ids(p, sp)
+        s = e.seq_create()
+        lg = e.prefill(s, p)
+        hist = list(p)
+        for i in range(12):
+            t = oc.sample(lg, 0.8, 40, 0.9, 1.1, 64, seed=77, history=hist, step=i)
+            assert t == r2.token_ids[i]
+            lg, _ = e.decode_step(s, t)
+            hist.append(t)
+
+
+@pytest.mark.parametrize("preset", ["tinyllama-1.1b"])
+def test_tinyllama_shapes_match_oracle(preset):
+    cfg = dict(oc.PRESETS[preset])
+    cfg["max_seq_len"] = 256
+    m = oc.Model(cfg, seed=1234)
+    mc = dict(cfg)
+    with eng.Engine(model=mc, seed=1234, max_batch=1) as e:
+        err, mism = _compare_greedy(e, m, _prompt(16, cfg["vocab_size"]), 16)
+        print(f"{preset}: max logit err {err:.4g}, near-tie mismatches {mism}")
+
+
+def test_llama3_8b_layer_shapes_match_oracle():
+    """Full Llama-3-8B shapes with 2 layers (the oracle needs ~5 GB and seconds per token at 32 layers;
+    every kernel shape of the 8B model is exercised here, the 32-layer run is covered by bench.py's
+    property checks)."""
+    cfg = dict(oc.PRESETS["llama3-8b"])
+    cfg["n_layers"] = 2
+    cfg["max_seq_len"] = 128
+    m = oc.Model(cfg, seed=1234)
+    with eng.Engine(model=cfg, seed=1234, max_batch=1) as e:
+        err, mism = _compare_greedy(e, m, _prompt(8, cfg["vocab_size"]), 8)
+        print(f"llama3-8b(2 layers): max logit err {err:.4g}, near-tie mismatches {mism}")
+        assert mism == 0
