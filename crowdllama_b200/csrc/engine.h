@@ -179,7 +179,7 @@ class Engine {
     __nv_bfloat16* act = nullptr;   // [T][F]
   };
   std::unique_ptr<PrefillWs> pws_;
-  int prefill_chunk_tokens_ = 2048;
+  int prefill_chunk_tokens_ = 4096;
 
   std::unique_ptr<KvPool> pool_;
   std::vector<SeqState> seqs_;

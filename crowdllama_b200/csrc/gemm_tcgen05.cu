@@ -1,0 +1,276 @@
+// gemm_tcgen05.cu — prefill / batched-decode weight projections on the 5th-gen tensor cores.
+//
+//   Y[t][n] (+)= sum_k X[t][k] * W[n][k]        X bf16 [T][K], W bf16 [N][K] (both K-major), Y fp32
+//
+// This is the "weight projections as tcgen05/TMA tensor-core tiles for prefill" row of SURVEY.md
+// §8a (kernel table); upstream counterpart is ggml-cuda's cuBLAS / mma.sync mmq prefill path.
+//
+// Mapping (swap-AB so small token counts waste N, not M):
+//   UMMA A operand = W tile  [128 rows n ][64 k]  -> accumulator lanes  (TMEM lane  = n)
+//   UMMA B operand = X tile  [BT  rows t ][64 k]  -> accumulator columns (TMEM column = t)
+//   accumulator D[128][BT] fp32 in TMEM, double buffered (2*BT columns).
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0   TMA producer  : cp.async.bulk.tensor.2d (128B swizzle) into an NST-stage mbarrier ring
+//   warp 1   MMA issuer    : tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit -> frees smem stage /
+//                            signals the epilogue; also owns tcgen05.alloc / dealloc
+//   warps 2-5 epilogue     : tcgen05.ld 32x32b.x32 -> registers -> coalesced fp32 stores
+//                            (lane = n, so a warp writes 32 consecutive n of one token: 128 B)
+// Tile order: consecutive tiles share the W tile (t fastest), so W streams from HBM once and X
+// (<= 32 MB) stays L2-resident.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cl {
+
+namespace {
+
+constexpr int BM = 128;  // W rows per tile (UMMA M)
+constexpr int BK = 64;   // k per stage = one 128-byte swizzle atom of bf16
+constexpr int UK = 16;   // UMMA K for 16-bit inputs
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+  d |= (uint64_t)1 << 16;                            // leading byte offset (16 B units; unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4)                 // D format f32
+         | (1u << 7)               // A format bf16
+         | (1u << 10)              // B format bf16
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);  // both operands K-major
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct GemmParams {
+  float* Y;
+  int T, N, K, ldy;
+  int accumulate_into_y;  // 1: Y += result (residual add in place)
+};
+
+template <int BT, int NST>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t A_BYTES = BM * BK * 2;   // 16 KB
+  constexpr uint32_t B_BYTES = BT * BK * 2;
+  constexpr uint32_t STAGE = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BT < 32 ? 32 : 2 * BT;
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns: power of two <= 512");
+  // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for the 128B swizzle
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)NST * STAGE);
+  uint64_t* empty = full + NST;
+  uint64_t* tmem_full = empty + NST;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_t = (p.T + BT - 1) / BT, num_n = (p.N + BM - 1) / BM;
+  const int num_tiles = num_t * num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_w);
+    prefetch_tmap(&map_x);
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile / num_t) * BM, t0 = (tile % num_t) * BT;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], STAGE);
+          uint8_t* sa = base + (size_t)stage * STAGE;
+          tma_load_2d(sa, &map_w, kb * BK, n0, &full[stage]);
+          tma_load_2d(sa + A_BYTES, &map_x, kb * BK, t0, &full[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc(BM, BT);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BT);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(base + (size_t)stage * STAGE);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)  // advance 32 bytes (= 2 x 16 B units) per UMMA_K inside the swizzle atom
+            umma_f16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n0 = (tile / num_t) * BM, t0 = (tile % num_t) * BT;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int n = n0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BT + c0), v);
+        tmem_ld_wait();
+        if (n < p.N) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int t = t0 + c0 + c;
+            if (t < p.T) {
+              float* dst = p.Y + (size_t)t * p.ldy + n;
+              const float r = __uint_as_float(v[c]);
+              *dst = p.accumulate_into_y ? (*dst + r) : r;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows][K] tensor, box = {64 k, box_rows}, 128B swizzle, OOB -> zeros
+bool make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BT, int NST>
+cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_tcgen05_kernel<BT, NST>;
+  constexpr size_t smem = (size_t)NST * (BM * BK * 2 + BT * BK * 2) + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int tiles = ((p.T + BT - 1) / BT) * ((p.N + BM - 1) / BM);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, 192, smem, st>>>(mw, mx, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool gemm_tcgen05_supported(int T, int N, int K) { return T > 0 && N > 0 && K > 0 && K % 8 == 0 && get_encode() != nullptr; }
+
+int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, const float* resid, int T, int N, int K,
+                     cudaStream_t st) {
+  if (!gemm_tcgen05_supported(T, N, K)) return -1;
+  if (resid && resid != Y) return -1;  // residual add is in place
+  const int BT = T > 128 ? 256 : T > 64 ? 128 : T > 32 ? 64 : 32;
+  CUtensorMap mw, mx;
+  if (!make_map(&mw, W, N, K, BM) || !make_map(&mx, X, T, K, BT)) return -1;
+  GemmParams p{Y, T, N, K, N, resid ? 1 : 0};
+  cudaError_t e;
+  switch (BT) {
+    case 256: e = launch_inst<256, 4>(mw, mx, p, st); break;
+    case 128: e = launch_inst<128, 6>(mw, mx, p, st); break;
+    case 64: e = launch_inst<64, 8>(mw, mx, p, st); break;
+    default: e = launch_inst<32, 8>(mw, mx, p, st); break;
+  }
+  return e == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace cl

@@ -1,20 +1,205 @@
-// prefill.cu — prompt (prefill) path.  Placeholder until the tcgen05 GEMM lands in this file's
-// siblings (gemm_tcgen05.cu / prefill_kernels.cu): prompts are processed token by token through
-// the decode kernels, which is exact but HBM-bound.
+// prefill.cu — prompt (prefill) path of the engine: chunks of up to prefill_chunk_tokens_ tokens go
+// through tcgen05 GEMMs (gemm_tcgen05.cu) and the causal paged attention kernel
+// (prefill_kernels.cu); the last position's logits come from the decode LM-head GEMV so that
+// prefill and decode share one logits/argmax tail.  Also: cl_op_gemm_bf16 / cl_op_attn_prefill.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
 #include "engine.h"
 
 namespace cl {
-bool Engine::prefill_path_ok() const { return false; }
-int Engine::prefill_chunked(cl_seq_t, const int32_t*, int, float*) { return CL_ERR_INTERNAL; }
+
+bool Engine::prefill_path_ok() const {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* v = getenv("CL_PREFILL_TCGEN05");
+    disabled = (v && *v == '0') ? 1 : 0;
+  }
+  return !disabled && gemm_tcgen05_supported(16, cfg.d_model, cfg.d_model);
+}
+
+int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits_out) {
+  auto& q = seqs_[s];
+  int rc = ensure_capacity(s, q.len + n);
+  if (rc) return rc;
+  const int d = cfg.d_model, F = cfg.d_ff;
+  const int CH = std::min(n, prefill_chunk_tokens_);
+  if (!pws_) pws_.reset(new PrefillWs());
+  if (pws_->cap_tokens < CH) {
+    // (re)allocate the workspace; old buffers stay in allocs_ until the engine dies (grows at most once or twice)
+    const size_t T = (size_t)std::max(CH, std::min(prefill_chunk_tokens_, cfg.max_seq_len));
+    auto alloc = [&](auto*& p, size_t bytes) -> int {
+      void* v = nullptr;
+      if (cudaMalloc(&v, bytes) != cudaSuccess) { cudaGetLastError(); set_last_error("prefill workspace: out of memory"); return CL_ERR_OOM; }
+      allocs_.push_back(v);
+      p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(v);
+      return CL_OK;
+    };
+    if ((rc = alloc(pws_->xn, T * d * 2))) return rc;
+    if ((rc = alloc(pws_->qkv, T * qkv_dim_ * 4))) return rc;
+    if ((rc = alloc(pws_->q, T * q_dim_ * 2))) return rc;
+    if ((rc = alloc(pws_->attn, T * q_dim_ * 2))) return rc;
+    if ((rc = alloc(pws_->h, T * d * 4))) return rc;
+    if ((rc = alloc(pws_->gu, T * 2 * F * 4))) return rc;
+    if ((rc = alloc(pws_->act, T * F * 2))) return rc;
+    pws_->cap_tokens = (int)T;
+  }
+  PrefillWs& w = *pws_;
+  CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+  const int* bt = d_bt_ + (size_t)s * max_pages_per_seq_;
+  int launches = 0, r;
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; } while (0)
+  for (int c0 = 0; c0 < n; c0 += w.cap_tokens) {
+    const int T = std::min(w.cap_tokens, n - c0);
+    const int pos0 = q.len + c0;
+    CL_LAUNCH(launch_embed_rows(embed_, d, d_prompt_ + c0, w.h, T, stream_));
+    for (int l = 0; l < cfg.n_layers; ++l) {
+      const auto& L = layers_[l];
+      CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.attn_norm, cfg.rms_eps, w.xn, T, d, stream_));
+      CL_LAUNCH(launch_gemm_bf16(w.xn, L.wqkv, w.qkv, nullptr, T, qkv_dim_, d, stream_));
+      RopeScatterArgs ra{w.qkv, qkv_dim_, rope_, pos0, T, w.q, kpool_ + (size_t)l * kv_layer_elems_,
+                         vpool_ + (size_t)l * kv_layer_elems_, bt, page_size_, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim};
+      CL_LAUNCH(launch_rope_scatter(ra, stream_));
+      AttnPrefillArgs aa{w.q, kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_, bt, page_size_,
+                         pos0, T, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, w.attn};
+      CL_LAUNCH(launch_attn_prefill(aa, stream_));
+      CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.h, w.h, T, d, q_dim_, stream_));
+      CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.ffn_norm, cfg.rms_eps, w.xn, T, d, stream_));
+      CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.gu, nullptr, T, 2 * F, d, stream_));
+      CL_LAUNCH(launch_silu_mul_bf16(w.gu, w.act, T, F, stream_));
+      CL_LAUNCH(launch_gemm_bf16(w.act, L.wdown, w.h, w.h, T, d, F, stream_));
+    }
+    if (c0 + T == n) {
+      // last position -> slot residual row, then the shared decode tail (final norm + LM head + argmax)
+      CL_CUDA_OK(cudaMemcpyAsync(d_h_ + (size_t)s * d, w.h + (size_t)(T - 1) * d, (size_t)d * 4, cudaMemcpyDeviceToDevice, stream_));
+    }
+  }
+  const int last_pos = q.len + n - 1;
+  CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &last_pos, 4, cudaMemcpyHostToDevice, stream_));
+  rc = set_single_slot(s);
+  if (rc) return rc;
+  GemvArgs lm;
+  lm.slots = d_slots_; lm.batch = 1;
+  lm.W = lm_head_; lm.N = cfg.vocab_size; lm.K = d; lm.h = d_h_; lm.gain = final_norm_; lm.eps = cfg.rms_eps;
+  lm.y = d_logits_; lm.x_stride = d; lm.y_stride = cfg.vocab_size;
+  CL_LAUNCH(launch_gemv(gemv_variant_, EPI_STORE, true, lm, stream_, false));
+  StepTailArgs t;
+  t.logits = d_logits_; t.vocab = cfg.vocab_size; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
+  t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
+  t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = 1;
+  CL_LAUNCH(launch_step_tail(t, stream_));
+#undef CL_LAUNCH
+  launches_ += launches;
+  q.len += n;
+  q.history.insert(q.history.end(), ids, ids + n);
+  if (logits_out) return read_logits(s, logits_out);
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  return CL_OK;
+}
+
 }  // namespace cl
 
+// ================================================================================================
+using namespace cl;
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  cudaError_t upload(const void* h, size_t bytes) {
+    cudaError_t e = alloc(bytes);
+    return e != cudaSuccess ? e : cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+  }
+};
+int check_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    set_last_error("no CUDA device (libclengine has no CPU fallback)");
+    return CL_ERR_NO_DEVICE;
+  }
+  CL_CUDA_OK(cudaSetDevice(device));
+  return CL_OK;
+}
+}  // namespace
+
 extern "C" {
-int cl_op_gemm_bf16(int, const uint16_t*, const uint16_t*, float*, int32_t, int32_t, int32_t, int32_t, float*) {
-  cl::set_last_error("tcgen05 GEMM not built yet");
-  return CL_ERR_INTERNAL;
+
+int cl_op_gemm_bf16(int device, const uint16_t* x, const uint16_t* w, float* y, int32_t t, int32_t n, int32_t k, int32_t iters,
+                    float* ms) {
+  if (!x || !w || !y || t <= 0 || n <= 0 || k <= 0) return CL_ERR_INVALID_ARG;
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (!gemm_tcgen05_supported(t, n, k)) { set_last_error("shape not supported by the tcgen05 GEMM (K % 8)"); return CL_ERR_INVALID_ARG; }
+  DevBuf dx, dw, dy;
+  CL_CUDA_OK(dx.upload(x, (size_t)t * k * 2));
+  CL_CUDA_OK(dw.upload(w, (size_t)n * k * 2));
+  CL_CUDA_OK(dy.alloc((size_t)t * n * 4));
+  CL_CUDA_OK(cudaMemset(dy.p, 0xff, (size_t)t * n * 4));  // NaN pattern: every element must be written
+  if (launch_gemm_bf16(dx.as<__nv_bfloat16>(), dw.as<__nv_bfloat16>(), dy.as<float>(), nullptr, t, n, k, nullptr) < 0) {
+    CL_CUDA_OK(cudaGetLastError());
+    set_last_error("launch_gemm_bf16 failed");
+    return CL_ERR_CUDA;
+  }
+  CL_CUDA_OK(cudaDeviceSynchronize());
+  CL_CUDA_OK(cudaMemcpy(y, dy.p, (size_t)t * n * 4, cudaMemcpyDeviceToHost));
+  if (iters > 0 && ms) {
+    cudaEvent_t e0, e1;
+    CL_CUDA_OK(cudaEventCreate(&e0));
+    CL_CUDA_OK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch_gemm_bf16(dx.as<__nv_bfloat16>(), dw.as<__nv_bfloat16>(), dy.as<float>(), nullptr, t, n, k, nullptr);
+    CL_CUDA_OK(cudaDeviceSynchronize());
+    CL_CUDA_OK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) launch_gemm_bf16(dx.as<__nv_bfloat16>(), dw.as<__nv_bfloat16>(), dy.as<float>(), nullptr, t, n, k, nullptr);
+    CL_CUDA_OK(cudaEventRecord(e1));
+    CL_CUDA_OK(cudaDeviceSynchronize());
+    float tm = 0.f;
+    CL_CUDA_OK(cudaEventElapsedTime(&tm, e0, e1));
+    *ms = tm / (float)iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  return CL_OK;
 }
-int cl_op_attn_prefill(int, const uint16_t*, const uint16_t*, const uint16_t*, int32_t, int32_t, int32_t, int32_t, float*) {
-  cl::set_last_error("prefill attention not built yet");
-  return CL_ERR_INTERNAL;
+
+int cl_op_attn_prefill(int device, const uint16_t* q, const uint16_t* k, const uint16_t* v, int32_t t, int32_t n_heads, int32_t n_kv,
+                       int32_t head_dim, float* out) {
+  if (!q || !k || !v || !out || t <= 0) return CL_ERR_INVALID_ARG;
+  int rc = check_device(device);
+  if (rc) return rc;
+  if ((head_dim != 64 && head_dim != 128) || n_kv <= 0 || n_heads % n_kv) { set_last_error("unsupported attention shape"); return CL_ERR_INVALID_ARG; }
+  const int P = 32, HD = head_dim;
+  const int n_pages = (t + P - 1) / P;
+  std::vector<int> bt(n_pages);
+  for (int i = 0; i < n_pages; ++i) bt[i] = n_pages - 1 - i;  // reversed page order
+  const size_t pool = (size_t)n_pages * n_kv * P * HD;
+  std::vector<uint16_t> kp(pool, 0), vp(pool, 0);
+  for (int tt = 0; tt < t; ++tt)
+    for (int g = 0; g < n_kv; ++g) {
+      const size_t dst = (((size_t)bt[tt / P] * n_kv + g) * P + tt % P) * HD;
+      memcpy(&kp[dst], k + ((size_t)tt * n_kv + g) * HD, (size_t)HD * 2);
+      memcpy(&vp[dst], v + ((size_t)tt * n_kv + g) * HD, (size_t)HD * 2);
+    }
+  const size_t qd = (size_t)n_heads * HD;
+  DevBuf dq, dk, dv, dbt, dout, dout32;
+  CL_CUDA_OK(dq.upload(q, (size_t)t * qd * 2));
+  CL_CUDA_OK(dk.upload(kp.data(), pool * 2));
+  CL_CUDA_OK(dv.upload(vp.data(), pool * 2));
+  CL_CUDA_OK(dbt.upload(bt.data(), bt.size() * 4));
+  CL_CUDA_OK(dout.alloc((size_t)t * qd * 2));
+  CL_CUDA_OK(dout32.alloc((size_t)t * qd * 4));
+  AttnPrefillArgs a{dq.as<__nv_bfloat16>(), dk.as<__nv_bfloat16>(), dv.as<__nv_bfloat16>(), dbt.as<int>(), P, 0, t, n_heads, n_kv, HD,
+                    dout.as<__nv_bfloat16>()};
+  if (launch_attn_prefill(a, nullptr) < 0) { CL_CUDA_OK(cudaGetLastError()); return CL_ERR_CUDA; }
+  if (launch_bf16_to_f32(dout.as<__nv_bfloat16>(), dout32.as<float>(), (int64_t)t * qd, nullptr) < 0) return CL_ERR_CUDA;
+  CL_CUDA_OK(cudaDeviceSynchronize());
+  CL_CUDA_OK(cudaMemcpy(out, dout32.p, (size_t)t * qd * 4, cudaMemcpyDeviceToHost));
+  return CL_OK;
 }
-}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+"""Routing mirror: crowdllama.Resource (/root/reference/pkg/crowdllama/types.go:30-40) and
+Manager.FindBestWorker (/root/reference/pkg/peermanager/manager.go:338-387), plus truthful worker
+metadata fed from cl_engine_stats (replaces the constants at peer.go:319-358)."""
+from __future__ import annotations
+
+import json
+import random
+from dataclasses import asdict, dataclass, field
+from datetime import datetime, timezone
+
+
+@dataclass
+class Resource:
+    peer_id: str = ""
+    supported_models: list = field(default_factory=list)
+    tokens_throughput: float = 0.0
+    vram_gb: int = 0
+    load: float = 0.0
+    gpu_model: str = ""
+    last_updated: str = ""
+    version: str = "unknown"
+    worker_mode: bool = False
+
+    def to_json(self) -> bytes:                                      # types.go:58-64
+        return json.dumps(asdict(self)).encode()
+
+    @classmethod
+    def from_json(cls, data: bytes) -> "Resource":                   # types.go:67-74
+        try:
+            d = json.loads(data)
+        except Exception as ex:
+            raise ValueError(f"failed to unmarshal CrowdLlamaResource: {ex}") from ex
+        known = {k: d[k] for k in cls.__dataclass_fields__ if k in d}
+        return cls(**known)
+
+    def get_dht_key(self) -> str:                                    # types.go:77-79
+        return "/ipns/" + self.peer_id
+
+
+def resource_from_engine(peer_id: str, engine, version: str = "b200") -> Resource:
+    st = engine.stats()
+    return Resource(peer_id=peer_id, supported_models=[engine.model_name], tokens_throughput=float(st["tokens_per_sec"]),
+                    vram_gb=int(st["vram_gb"]), load=float(st["load"]), gpu_model=st["gpu_model"],
+                    last_updated=datetime.now(timezone.utc).isoformat(), version=version, worker_mode=True)
+
+
+def find_best_worker(workers, required_model: str, rng: random.Random | None = None):
+    """manager.go:338-387.  Exact-string model match, score = tokens_throughput / (1 + load), strict
+    '>' against a best score that starts at 0 — so workers with score 0 are never selected, and ties go
+    to whichever worker is visited first.  Go iterates a map (random order): modelled by a shuffle."""
+    workers = [w for w in workers if w.worker_mode]
+    if not workers:
+        return None
+    suitable = [w for w in workers if required_model in w.supported_models]
+    if not suitable:
+        return None
+    order = list(suitable)
+    (rng or random).shuffle(order)
+    selected, best = None, 0.0
+    for w in order:
+        score = w.tokens_throughput / (1 + w.load)
+        if score > best:
+            best, selected = score, w
+    return selected

@@ -1,0 +1,262 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the paged-KV allocator,
+framing / protobuf codec (mirrors /root/reference/pkg/crowdllama/pbwire_test.go), the handler
+envelope with a mock engine (mirrors /root/reference/pkg/ipc/ipc_test.go:44-146), routing
+(manager.go:338-387) and Resource JSON (types_test.go)."""
+import io
+import json
+import random
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from crowdllama_b200 import engine as eng
+from crowdllama_b200 import handler as H
+from crowdllama_b200 import pbwire
+from crowdllama_b200.pb import BaseMessage, GenerateRequest, GenerateResponse
+from crowdllama_b200.router import Resource, find_best_worker
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+# ---- C-ABI ---------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "clengine.h").read_text()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)              # strip comments
+    declared = set(re.findall(r"\b(cl_[a-z0-9_]+)\s*\(", body))
+    L = eng.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(eng.EXPORTS), declared ^ set(eng.EXPORTS)
+    assert L.cl_abi_version() == 1
+    assert b"GenerateRequest" in L.cl_strerror(eng.CL_ERR_BAD_MESSAGE)
+
+
+def test_presets_and_defaults():
+    p = eng.model_preset("llama3-8b")
+    assert (p["n_layers"], p["d_model"], p["n_heads"], p["n_kv_heads"], p["head_dim"], p["d_ff"], p["vocab_size"]) == \
+        (32, 4096, 32, 8, 128, 14336, 128256)
+    assert eng.model_preset("mistral-7b")["vocab_size"] == 32000
+    assert eng.model_preset("tinyllama-1.1b")["n_kv_heads"] == 4
+    with pytest.raises(eng.EngineError):
+        eng.model_preset("nope")
+    s = eng.ollama_default_sampling(seed=1)
+    assert (round(s.temperature, 3), s.top_k, round(s.top_p, 3), round(s.repeat_penalty, 3), s.repeat_last_n) == (0.8, 40, 0.9, 1.1, 64)
+    g = eng.greedy(5)
+    assert g.temperature == 0 and g.max_new_tokens == 5
+
+
+def test_no_cpu_fallback():
+    """Without a device the product path must fail loudly (never route to the oracle)."""
+    if eng.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(eng.EngineError) as ei:
+        eng.Engine(preset="tiny-test")
+    assert ei.value.status == eng.CL_ERR_NO_DEVICE
+    with pytest.raises(eng.EngineError) as ei:
+        eng.op_gemv(np.zeros((2, 16), np.uint16), np.zeros(16, np.float32))
+    assert ei.value.status == eng.CL_ERR_NO_DEVICE
+    src = "".join(p.read_text() for p in (ROOT / "crowdllama_b200").rglob("*.py"))
+    assert "oracle" not in src.replace("oracle oc_sample", "").replace("the oracle", "")
+
+
+# ---- paged-KV allocator ------------------------------------------------------------------------------
+def test_kvpool_reserve_release_and_oom():
+    p = eng.KvPool(8, 16)
+    assert p.free_pages == 8
+    assert p.reserve(1, 1) == 0 and p.pages_of(1) == [0]
+    assert p.reserve(1, 16) == 0 and len(p.pages_of(1)) == 1
+    assert p.reserve(1, 17) == 0 and p.pages_of(1) == [0, 1]
+    assert p.reserve(2, 16 * 5) == 0 and p.used_pages == 7
+    assert p.reserve(3, 33) == eng.CL_ERR_OOM            # needs 3, only 1 free
+    assert p.pages_of(3) == [] and p.free_pages == 1     # atomic: nothing taken
+    assert p.release(2) == 0 and p.free_pages == 6
+    assert p.reserve(3, 33) == 0
+    all_pages = p.pages_of(1) + p.pages_of(3)
+    assert len(set(all_pages)) == len(all_pages)
+    assert p.release(1) == 0 and p.release(3) == 0 and p.free_pages == 8
+    assert p.release(99) == 0
+
+
+def test_kvpool_randomised_never_double_allocates():
+    rng = random.Random(0)
+    p = eng.KvPool(64, 32)
+    want = {}
+    for _ in range(2000):
+        o = rng.randrange(10)
+        if rng.random() < 0.3:
+            p.release(o)
+            want.pop(o, None)
+        else:
+            n = rng.randrange(1, 400)
+            rc = p.reserve(o, n)
+            if rc == 0:
+                want[o] = max(want.get(o, 0), (n + 31) // 32)
+        owned = [pg for o2 in want for pg in p.pages_of(o2)]
+        assert len(owned) == len(set(owned)) == p.used_pages
+        for o2, cnt in want.items():
+            assert len(p.pages_of(o2)) == cnt
+
+
+# ---- framing + codec (pbwire_test.go) ----------------------------------------------------------------
+def test_length_prefixed_round_trip_request_and_response():
+    buf = io.BytesIO()
+    req = H.create_generate_request("test-model", "Hello, world!", False)
+    pbwire.write_length_prefixed_pb(buf, req)
+    raw = buf.getvalue()
+    assert int.from_bytes(raw[:4], "big") == len(raw) - 4
+    got = pbwire.read_length_prefixed_pb(io.BytesIO(raw))
+    r = H.extract_generate_request(got)
+    assert (r.model, r.prompt, r.stream) == ("test-model", "Hello, world!", False)
+    resp = BaseMessage(generate_response=GenerateResponse(model="test-model", response="Hello back!", done=True,
+                                                          done_reason="stop", worker_id="worker", total_duration=123,
+                                                          created_at_seconds=1700000000, created_at_nanos=5))
+    buf = io.BytesIO()
+    pbwire.write_length_prefixed_pb(buf, resp)
+    g = H.extract_generate_response(pbwire.read_length_prefixed_pb(io.BytesIO(buf.getvalue())))
+    assert g == resp.generate_response
+    with pytest.raises(H.HandlerError):
+        H.extract_generate_request(resp)
+
+
+def test_read_rejects_oversize_and_truncated():
+    with pytest.raises(ValueError, match="message too large"):
+        pbwire.read_length_prefixed_pb(io.BytesIO((10 * 1024 * 1024 + 1).to_bytes(4, "big")))
+    with pytest.raises(IOError, match="failed to read length prefix"):
+        pbwire.read_length_prefixed_pb(io.BytesIO(b"\x00\x00"))
+    with pytest.raises(IOError, match="failed to read protobuf data"):
+        pbwire.read_length_prefixed_pb(io.BytesIO((100).to_bytes(4, "big") + b"abc"))
+
+
+def test_codec_is_wire_compatible_with_google_protobuf():
+    """Build llama.v1 descriptors at run time with the protobuf runtime (same field table) and check
+    that bytes cross-parse both ways."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory, timestamp_pb2  # noqa: F401
+    fd = descriptor_pb2.FileDescriptorProto(name="llama_v1_test.proto", package="llama.v1t", syntax="proto3",
+                                            dependency=["google/protobuf/timestamp.proto"])
+    T = descriptor_pb2.FieldDescriptorProto
+    gr = fd.message_type.add(name="GenerateRequest")
+    gr.field.add(name="model", number=1, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
+    gr.field.add(name="prompt", number=2, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
+    gr.field.add(name="stream", number=3, type=T.TYPE_BOOL, label=T.LABEL_OPTIONAL)
+    gp = fd.message_type.add(name="GenerateResponse")
+    gp.field.add(name="model", number=1, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
+    gp.field.add(name="created_at", number=2, type=T.TYPE_MESSAGE, type_name=".google.protobuf.Timestamp", label=T.LABEL_OPTIONAL)
+    gp.field.add(name="response", number=3, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
+    gp.field.add(name="done", number=4, type=T.TYPE_BOOL, label=T.LABEL_OPTIONAL)
+    gp.field.add(name="done_reason", number=5, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
+    gp.field.add(name="worker_id", number=6, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
+    gp.field.add(name="total_duration", number=7, type=T.TYPE_INT64, label=T.LABEL_OPTIONAL)
+    bm = fd.message_type.add(name="BaseMessage")
+    bm.oneof_decl.add(name="message")
+    bm.field.add(name="generate_request", number=1, type=T.TYPE_MESSAGE, type_name=".llama.v1t.GenerateRequest",
+                 label=T.LABEL_OPTIONAL, oneof_index=0)
+    bm.field.add(name="generate_response", number=2, type=T.TYPE_MESSAGE, type_name=".llama.v1t.GenerateResponse",
+                 label=T.LABEL_OPTIONAL, oneof_index=0)
+    pool = descriptor_pool.Default()
+    try:
+        pool.Add(fd)
+    except TypeError:
+        pass
+    Base = message_factory.GetMessageClass(pool.FindMessageTypeByName("llama.v1t.BaseMessage"))
+    ours = H.create_generate_request("tinyllama", "why is the sky blue? ☃", True).encode()
+    g = Base.FromString(ours)
+    assert g.WhichOneof("message") == "generate_request"
+    assert (g.generate_request.model, g.generate_request.prompt, g.generate_request.stream) == ("tinyllama", "why is the sky blue? ☃", True)
+    g2 = Base()
+    g2.generate_response.model = "m"
+    g2.generate_response.response = "text"
+    g2.generate_response.done = True
+    g2.generate_response.done_reason = "length"
+    g2.generate_response.worker_id = "worker"
+    g2.generate_response.total_duration = 1 << 60
+    g2.generate_response.created_at.seconds = 1700000001
+    g2.generate_response.created_at.nanos = 999
+    back = BaseMessage.decode(g2.SerializeToString()).generate_response
+    assert back == GenerateResponse("m", 1700000001, 999, "text", True, "length", "worker", 1 << 60)
+    assert Base.FromString(BaseMessage(generate_response=back).encode()) == g2
+
+
+# ---- handler envelope with a mock engine (ipc_test.go:44-146) -----------------------------------------
+class _MockEngine:
+    model_name = "test-model"
+
+    def generate(self, model, prompt, sampling=None):
+        class R:
+            text, done_reason = "PB Hello, " + prompt, "stop"
+        if model != self.model_name:
+            raise eng.EngineError.__new__(eng.EngineError)
+        return R()
+
+
+def test_worker_handler_envelope():
+    h = H.worker_api_handler(_MockEngine())
+    resp = h(None, H.create_generate_request("test-model", "world", False))
+    g = H.extract_generate_response(resp)
+    assert g.model == "test-model" and g.response == "PB Hello, world" and g.done and g.done_reason == "stop"
+    assert g.worker_id == "worker" and g.total_duration > 0 and g.created_at_seconds > 0
+    with pytest.raises(H.HandlerError, match="expected GenerateRequest, got different message type"):
+        h(None, BaseMessage(generate_response=GenerateResponse()))
+
+
+def test_handle_inference_stream_error_becomes_text():
+    class Duplex(io.BytesIO):
+        def __init__(self, data):
+            super().__init__(data)
+            self.out = io.BytesIO()
+
+        def write(self, b):
+            return self.out.write(b)
+
+    def failing(ctx, req):
+        raise RuntimeError("boom")
+    wire = io.BytesIO()
+    pbwire.write_length_prefixed_pb(wire, H.create_generate_request("m", "p", False))
+    s = Duplex(wire.getvalue())
+    assert H.handle_inference_stream(failing, s)
+    g = pbwire.read_length_prefixed_pb(io.BytesIO(s.out.getvalue())).generate_response
+    assert g.response == "Error: boom" and g.done and g.model == ""        # peer.go:235-242
+    assert not H.handle_inference_stream(failing, Duplex(b""), worker_mode=False)
+    assert not H.handle_inference_stream(failing, Duplex(b"\x00"))
+    s = Duplex(wire.getvalue())
+    assert H.handle_inference_stream(H.default_api_handler, s)
+    g = pbwire.read_length_prefixed_pb(io.BytesIO(s.out.getvalue())).generate_response
+    assert g.response == "Generated response for model m with prompt: p" and g.worker_id == "default-worker"
+
+
+# ---- routing (manager.go:338-387) and Resource JSON (types_test.go) -----------------------------------
+def _w(pid, models, tput, load, worker=True):
+    return Resource(peer_id=pid, supported_models=models, tokens_throughput=tput, load=load, worker_mode=worker)
+
+
+def test_find_best_worker_rule():
+    ws = [_w("a", ["tinyllama"], 150, 0.3), _w("b", ["tinyllama", "llama3:8b"], 300, 0.5), _w("c", ["llama3:8b"], 100, 0.0),
+          _w("consumer", ["llama3:8b"], 1e9, 0.0, worker=False)]
+    assert find_best_worker(ws, "llama3:8b").peer_id == "b"        # 200 > 100
+    assert find_best_worker(ws, "tinyllama").peer_id == "b"        # 200 > 115.4
+    assert find_best_worker(ws, "llama3") is None                  # exact string match only
+    assert find_best_worker([], "x") is None
+    assert find_best_worker([_w("z", ["m"], 0.0, 0.0)], "m") is None   # score 0 never beats bestScore 0 (strict >)
+
+
+def test_ties_are_uniform_random():
+    ws = [_w(str(i), ["m"], 150.0, 0.3) for i in range(8)]
+    rng = random.Random(0)
+    counts = {}
+    for _ in range(4000):
+        p = find_best_worker(ws, "m", rng).peer_id
+        counts[p] = counts.get(p, 0) + 1
+    assert len(counts) == 8 and min(counts.values()) > 350
+
+
+def test_resource_json_round_trip():
+    r = _w("12D3KooW", ["llama3:8b"], 301.5, 0.25)
+    r.vram_gb, r.gpu_model = 179, "NVIDIA B200"
+    d = json.loads(r.to_json())
+    assert set(d) == {"peer_id", "supported_models", "tokens_throughput", "vram_gb", "load", "gpu_model", "last_updated",
+                      "version", "worker_mode"}
+    assert Resource.from_json(r.to_json()) == r
+    assert r.get_dht_key() == "/ipns/12D3KooW"
+    with pytest.raises(ValueError, match="failed to unmarshal CrowdLlamaResource"):
+        Resource.from_json(b"{nope")
