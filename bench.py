@@ -140,7 +140,7 @@ def cpu_baseline(steps_cap_s=25.0, max_tokens=8, warm=1):
     from oracle import oracle as oc
     cfg = dict(oc.PRESETS[PRESET])
     cfg["max_seq_len"] = CTX + 64
-    threads = os.cpu_count() or 1
+    threads = oc.effective_cpus()
     oc.set_threads(threads)
     t0 = time.time()
     m = oc.Model(cfg, seed=SEED)

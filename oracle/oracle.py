@@ -49,10 +49,31 @@ def _which(x):
 _lib = None
 
 
+def effective_cpus() -> int:
+    """CPUs this process may really use: affinity mask capped by the cgroup CPU quota (a container can
+    show 128 cores in nproc while being throttled to a few; spinning OpenMP threads then crawl)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]          # cgroup v2
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:  # noqa: BLE001
+        try:                                                                             # cgroup v1
+            quota = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            period = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, quota // period))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, n)
+
+
 def lib():
     global _lib
     if _lib is None:
         build()
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # do not spin between parallel regions
+        os.environ.setdefault("OMP_PROC_BIND", "false")
         L = C.CDLL(str(_LIB_PATH))
         vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
         P = C.POINTER
@@ -86,6 +107,7 @@ def lib():
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
+        L.oc_set_num_threads(min(effective_cpus(), int(os.environ.get("CL_ORACLE_THREADS", "32"))))
         _lib = L
     return _lib
 
