@@ -11,20 +11,33 @@
 //                                keep their x slice in registers.  The producer never waits for
 //                                activations, so with PDL the next kernel's ring fills while the
 //                                previous kernel drains.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace cl {
 
 static int g_sm_count = 0;
+static bool g_carveout_max = true;
 int sm_count() {
   if (!g_sm_count) {
+    const char* cv = getenv("CL_CARVEOUT_MAX");
+    if (cv && *cv == '0') g_carveout_max = false;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (g_sm_count <= 0) g_sm_count = 148;
   }
   return g_sm_count;
+}
+
+// Every kernel of the token step asks for the maximum shared-memory carve-out: a different L1/shared
+// split per kernel would force the SM to drain before the next kernel's CTAs can become resident,
+// which defeats the PDL overlap (and a 101 KB ring kernel would not co-reside with its successor).
+template <typename Kern>
+static void prefer_max_smem(Kern kern) {
+  if (g_carveout_max) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 template <typename Kern, typename Args>
@@ -58,10 +71,37 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, int slot, int r
     float r0 = r[row0], r1 = r[row0 + 1];
     y[row0] = r0 + v0;
     y[row0 + 1] = r1 + v1;
-  } else {  // gate/up: v0 = gate_i, v1 = up_i
+  } else if (EPI == EPI_GATEUP) {  // v0 = gate_i, v1 = up_i
     float* y = a.y + (size_t)slot * a.y_stride;
     float si = v0 / (1.0f + __expf(-v0));
     y[row0 >> 1] = bf16_round(si * v1);
+  } else {  // EPI_QKV: (v0, v1) = dims (j, j + half) of one head -> RoPE, bf16 round, q out / KV append
+    const QkvEpi& e = a.qkv;
+    const int HD = e.head_dim, half = HD >> 1;
+    const int p = row0 >> 1;
+    const int hh = p / half, j = p - hh * half;
+    const int pos = e.pos[slot];
+    if (hh < e.n_heads + e.n_kv) {
+      const float2 cs = e.rope[(size_t)pos * half + j];
+      const float r0 = bf16_round(v0 * cs.x - v1 * cs.y), r1 = bf16_round(v1 * cs.x + v0 * cs.y);
+      if (hh < e.n_heads) {
+        float* y = a.y + (size_t)slot * a.y_stride + (size_t)hh * HD;
+        y[j] = r0;
+        y[j + half] = r1;
+      } else {
+        const int g = hh - e.n_heads;
+        const int page = e.block_tables[(size_t)slot * e.bt_stride + pos / e.page_size];
+        const size_t base = (((size_t)page * e.n_kv + g) * e.page_size + pos % e.page_size) * HD;
+        e.kpool[base + j] = __float2bfloat16_rn(r0);
+        e.kpool[base + j + half] = __float2bfloat16_rn(r1);
+      }
+    } else {
+      const int g = hh - e.n_heads - e.n_kv;
+      const int page = e.block_tables[(size_t)slot * e.bt_stride + pos / e.page_size];
+      const size_t base = (((size_t)page * e.n_kv + g) * e.page_size + pos % e.page_size) * HD;
+      e.vpool[base + j] = __float2bfloat16_rn(v0);
+      e.vpool[base + j + half] = __float2bfloat16_rn(v1);
+    }
   }
 }
 
@@ -74,7 +114,7 @@ __global__ void __launch_bounds__(256, 2) gemv_ldg_kernel(const GemvArgs a) {
   __shared__ float red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
-  pdl_launch_dependents();
+  if (a.pdl_early) pdl_launch_dependents();
   pdl_wait();
   const int slot = a.slots ? a.slots[b] : b;
   const int K = a.K;
@@ -136,6 +176,7 @@ __global__ void __launch_bounds__(256, 2) gemv_ldg_kernel(const GemvArgs a) {
     acc0 = warp_sum(acc0);
     acc1 = warp_sum(acc1);
     if (lane == 0) gemv_epilogue<EPI>(a, slot, 2 * p, acc0, acc1);
+    if (!a.pdl_early && p == p1 - 2) pdl_launch_dependents();   // about to start the last row pair
   }
 }
 
@@ -172,7 +213,7 @@ __global__ void __launch_bounds__(288, 1) gemv_ring_kernel(const GemvArgs a) {
     fence_barrier_init();
   }
   __syncthreads();
-  pdl_launch_dependents();
+  if (a.pdl_early) pdl_launch_dependents();
 
   if (warp == 8) {
     // ---------------- producer: weights do not depend on the previous kernel -> no pdl_wait here
@@ -186,6 +227,9 @@ __global__ void __launch_bounds__(288, 1) gemv_ring_kernel(const GemvArgs a) {
         mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
         bulk_g2s(ring + (size_t)st * STAGE_BYTES, src + (size_t)it * STAGE_BYTES, STAGE_BYTES, &full[st], pol);
       }
+      // every byte this CTA will ever read from HBM is now in flight: let the next kernel's CTAs
+      // become resident and start streaming THEIR weights while this one drains
+      if (!a.pdl_early) pdl_launch_dependents();
     }
     // the producer warp must stay until the consumers are done with the barriers it arms
   } else {
@@ -306,6 +350,7 @@ static cudaError_t launch_ring_inst(const GemvArgs& a, cudaStream_t st, bool pdl
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    prefer_max_smem(kern);
     attr_set = true;
   }
   if (smem > 160 * 1024) return cudaErrorInvalidValue;
@@ -331,6 +376,7 @@ static cudaError_t launch_ldg(const GemvArgs& a, cudaStream_t st, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    prefer_max_smem(kern);
     attr_set = true;
   }
   int G = sm_count() * 2;
@@ -346,85 +392,103 @@ int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t
 #define CL_DISPATCH(FN)                                                                   \
   if (epi == EPI_STORE) e = norm ? FN<EPI_STORE, true>(a, st, pdl) : FN<EPI_STORE, false>(a, st, pdl);   \
   else if (epi == EPI_RESID) e = norm ? FN<EPI_RESID, true>(a, st, pdl) : FN<EPI_RESID, false>(a, st, pdl); \
-  else e = norm ? FN<EPI_GATEUP, true>(a, st, pdl) : FN<EPI_GATEUP, false>(a, st, pdl);
+  else if (epi == EPI_GATEUP) e = norm ? FN<EPI_GATEUP, true>(a, st, pdl) : FN<EPI_GATEUP, false>(a, st, pdl);   \
+  else e = norm ? FN<EPI_QKV, true>(a, st, pdl) : FN<EPI_QKV, false>(a, st, pdl);
   if (variant == 1) { CL_DISPATCH(launch_ring) } else { CL_DISPATCH(launch_ldg) }
 #undef CL_DISPATCH
   return e == cudaSuccess ? 1 : -1;
 }
 
 // ================================================================================================
-// paged GQA decode attention (split-KV), fused RoPE(q,k) + KV append + split combine.
-// grid = (n_kv, nsplit, batch), block = 256.  LPT lanes cooperate on one cached token.
+// paged GQA decode attention (split-KV) — v3.
+//   grid = (n_kv, nsplit, batch); block = 288: warp 8 streams this split's KV pages with 1-D TMA bulk
+//   copies (one (page, kv-head) block of K and of V per stage, 64 KB ring) and warps 0..7 consume them
+//   from shared memory.  RoPE and the KV append already happened in the q|k|v GEMV epilogue (EPI_QKV),
+//   so the kernel reads roped q and tokens 0..pos from the cache.
+//   PDL: everything the producer touches before griddepcontrol.wait (slots, pos, block table, K/V of
+//   EARLIER tokens) is immutable during the token step, so the KV stream of this layer overlaps the
+//   q|k|v GEMV that precedes it; only the page holding the current token is fetched after the wait.
+//   The consumers' short latency-bound phase then overlaps the o-projection's weight prefetch.
 // ================================================================================================
+constexpr int kAttnRingBytes = 64 * 1024;
+constexpr int kAttnMaxStages = 8;
+
 template <int REP, int HD>
-__global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeArgs a) {
+__global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a) {
+  constexpr int NW = 8;              // consumer warps
   constexpr int LPT = HD / 8;        // lanes per token (16-byte chunk each)
-  constexpr int TPW = 32 / LPT;      // tokens per warp iteration
-  constexpr int HALF = HD / 2;
+  constexpr int TPW = 32 / LPT;      // tokens per warp pass
   constexpr float LOG2E = 1.4426950408889634f;
-  __shared__ __align__(16) float q_s[REP][HD];
-  __shared__ __align__(16) float knew_s[HD];
-  __shared__ __align__(16) float vnew_s[HD];
-  __shared__ float red_m[8][REP], red_l[8][REP];
-  __shared__ __align__(16) float red_acc[8][REP][HD];
+  constexpr int MAXS = 64;
+  extern __shared__ __align__(128) uint8_t ring[];
+  __shared__ uint64_t full[kAttnMaxStages], empty[kAttnMaxStages];
+  __shared__ float red_m[NW][REP], red_l[NW][REP];
+  __shared__ __align__(16) float red_acc[NW][REP][HD];
+  __shared__ float cm_s[MAXS][REP], cw_s[MAXS][REP];
+  __shared__ float cL_s[REP];
   __shared__ int is_last_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
-  pdl_launch_dependents();
-  pdl_wait();
-  const int slot = a.slots ? a.slots[b] : b;
-  const int pos = a.pos[slot];
   const int P = a.page_size;
-  const int* bt = a.block_tables + (size_t)slot * a.bt_stride;
-  const float* qkv = a.qkv + (size_t)slot * a.qkv_stride;
-  const float2* rope = a.rope + (size_t)pos * HALF;
-  const float scale2 = rsqrtf((float)HD) * LOG2E;
-  const bool owns_new = (split == a.nsplit - 1);
+  const uint32_t half_bytes = (uint32_t)P * HD * 2;       // K (or V) block of one (page, kv head)
+  const uint32_t slot_bytes = 2 * half_bytes;
+  int nstg = kAttnRingBytes / (int)slot_bytes;
+  nstg = nstg > kAttnMaxStages ? kAttnMaxStages : nstg;
 
-  // ---- RoPE(q) for this kv head's REP query heads (bf16-rounded, cl-llama v1)
-  for (int t = tid; t < REP * HALF; t += 256) {
-    const int hh = t / HALF, i = t % HALF;
-    const float* qh = qkv + (size_t)(g * REP + hh) * HD;
-    const float2 cs = rope[i];
-    const float x0 = qh[i], x1 = qh[i + HALF];
-    q_s[hh][i] = bf16_round(x0 * cs.x - x1 * cs.y);
-    q_s[hh][i + HALF] = bf16_round(x1 * cs.x + x0 * cs.y);
-  }
-  // ---- RoPE(k) + KV append of the current token (one split does it)
-  if (owns_new) {
-    const int page = bt[pos / P], off = pos % P;
-    const size_t base = (((size_t)page * a.n_kv + g) * P + off) * HD;
-    const float* kr = qkv + (size_t)a.n_heads * HD + (size_t)g * HD;
-    const float* vr = qkv + (size_t)(a.n_heads + a.n_kv) * HD + (size_t)g * HD;
-    for (int i = tid; i < HALF; i += 256) {
-      const float2 cs = rope[i];
-      const float x0 = kr[i], x1 = kr[i + HALF];
-      const float k0 = bf16_round(x0 * cs.x - x1 * cs.y), k1 = bf16_round(x1 * cs.x + x0 * cs.y);
-      knew_s[i] = k0; knew_s[i + HALF] = k1;
-      a.kpool[base + i] = __float2bfloat16_rn(k0);
-      a.kpool[base + i + HALF] = __float2bfloat16_rn(k1);
-    }
-    for (int i = tid; i < HD; i += 256) {
-      const float v = bf16_round(vr[i]);
-      vnew_s[i] = v;
-      a.vpool[base + i] = __float2bfloat16_rn(v);
-    }
+  if (tid == 0) {
+    for (int i = 0; i < nstg; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NW); }
+    fence_barrier_init();
   }
   __syncthreads();
+  if (a.pdl_early) pdl_launch_dependents();
 
-  // ---- this split's cached-token range
-  int chunk = (pos + a.nsplit - 1) / a.nsplit;
-  chunk = (chunk + 15) & ~15;
-  const int t0 = split * chunk;
-  const int t1 = min(pos, t0 + chunk);
+  const int slot = a.slots ? a.slots[b] : b;
+  const int pos = a.pos[slot];                 // stable for the whole step (written by the previous step's tail)
+  const int ctx = pos + 1;
+  const int total_pages = (ctx + P - 1) / P;
+  const int pages_per_split = (total_pages + a.nsplit - 1) / a.nsplit;
+  const int pg0 = split * pages_per_split;
+  const int pg1 = min(total_pages, pg0 + pages_per_split);
+  const int npg = pg1 > pg0 ? pg1 - pg0 : 0;
+  const int* bt = a.block_tables + (size_t)slot * a.bt_stride;
 
+  if (warp == NW) {
+    // ---------------- producer
+    if (elect_one()) {
+      const uint64_t pol = policy_evict_first();
+      const int cur_page = pos / P;            // its K/V row is written by the preceding EPI_QKV kernel
+      for (int it = 0; it < npg; ++it) {
+        const int st = it % nstg;
+        const uint32_t par = (uint32_t)(it / nstg) & 1u;
+        mbar_wait(&empty[st], par ^ 1u);
+        if (pg0 + it == cur_page) pdl_wait();
+        const int page = bt[pg0 + it];
+        const size_t src = ((size_t)page * a.n_kv + g) * P * HD;
+        uint8_t* dst = ring + (size_t)st * slot_bytes;
+        mbar_arrive_expect_tx(&full[st], slot_bytes);
+        bulk_g2s(dst, a.kpool + src, half_bytes, &full[st], pol);
+        bulk_g2s(dst + half_bytes, a.vpool + src, half_bytes, &full[st], pol);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers (warps 0..7)
+  pdl_wait();
   const int sub = lane / LPT, j = lane % LPT;
+  const float scale2 = rsqrtf((float)HD) * LOG2E;
   float qr[REP][8];
+  {
+    const float* q = a.q + (size_t)slot * a.q_stride + (size_t)g * REP * HD + j * 8;
 #pragma unroll
-  for (int hh = 0; hh < REP; ++hh)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qr[hh][i] = q_s[hh][j * 8 + i];
+    for (int hh = 0; hh < REP; ++hh) {
+      const float4 q0 = *reinterpret_cast<const float4*>(q + hh * HD);
+      const float4 q1 = *reinterpret_cast<const float4*>(q + hh * HD + 4);
+      qr[hh][0] = q0.x; qr[hh][1] = q0.y; qr[hh][2] = q0.z; qr[hh][3] = q0.w;
+      qr[hh][4] = q1.x; qr[hh][5] = q1.y; qr[hh][6] = q1.z; qr[hh][7] = q1.w;
+    }
+  }
   float m[REP], l[REP], acc[REP][8];
 #pragma unroll
   for (int hh = 0; hh < REP; ++hh) {
@@ -433,58 +497,50 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeArgs a
     for (int i = 0; i < 8; ++i) acc[hh][i] = 0.f;
   }
 
-  auto consume = [&](const float (&kf)[8], const float (&vf)[8], bool active) {
-    float sc[REP];
-#pragma unroll
-    for (int hh = 0; hh < REP; ++hh) {
-      float p = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) p = fmaf(qr[hh][i], kf[i], p);
-      sc[hh] = p;
-    }
-#pragma unroll
-    for (int o = LPT / 2; o > 0; o >>= 1)
-#pragma unroll
-      for (int hh = 0; hh < REP; ++hh) sc[hh] += __shfl_xor_sync(0xffffffffu, sc[hh], o);
-    if (active) {
-#pragma unroll
-      for (int hh = 0; hh < REP; ++hh) {
-        const float s2 = sc[hh] * scale2;
-        const float mn = fmaxf(m[hh], s2);
-        const float corr = exp2f(m[hh] - mn);   // m = -inf -> 0
-        const float p = exp2f(s2 - mn);
-        l[hh] = l[hh] * corr + p;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[hh][i] = fmaf(p, vf[i], acc[hh][i] * corr);
-        m[hh] = mn;
-      }
-    }
-  };
-
-  for (int tb = t0 + warp * TPW; tb < t1; tb += 8 * TPW) {
-    const int t = tb + sub;
-    const bool active = t < t1;
-    float kf[8], vf[8];
-    if (active) {
-      const int page = bt[t / P], off = t % P;
-      const size_t base = (((size_t)page * a.n_kv + g) * P + off) * HD + j * 8;
-      const uint4 kk = ldg_stream(a.kpool + base);
-      const uint4 vv = ldg_stream(a.vpool + base);
+  for (int it = 0; it < npg; ++it) {
+    const int st = it % nstg;
+    const uint32_t par = (uint32_t)(it / nstg) & 1u;
+    mbar_wait(&full[st], par);
+    const uint8_t* kbase = ring + (size_t)st * slot_bytes;
+    const uint8_t* vbase = kbase + half_bytes;
+    const int tok0 = (pg0 + it) * P;
+    for (int tl = warp * TPW + sub; tl < P; tl += NW * TPW) {   // warp-uniform trip count (P % (NW*TPW) == 0 or all lanes step together)
+      const bool active = tok0 + tl < ctx;
+      const uint4 kk = *reinterpret_cast<const uint4*>(kbase + ((size_t)tl * HD + j * 8) * 2);
+      const uint4 vv = *reinterpret_cast<const uint4*>(vbase + ((size_t)tl * HD + j * 8) * 2);
+      float kf[8], vf[8];
       kf[0] = bf16_lo(kk.x); kf[1] = bf16_hi(kk.x); kf[2] = bf16_lo(kk.y); kf[3] = bf16_hi(kk.y);
       kf[4] = bf16_lo(kk.z); kf[5] = bf16_hi(kk.z); kf[6] = bf16_lo(kk.w); kf[7] = bf16_hi(kk.w);
       vf[0] = bf16_lo(vv.x); vf[1] = bf16_hi(vv.x); vf[2] = bf16_lo(vv.y); vf[3] = bf16_hi(vv.y);
       vf[4] = bf16_lo(vv.z); vf[5] = bf16_hi(vv.z); vf[6] = bf16_lo(vv.w); vf[7] = bf16_hi(vv.w);
-    } else {
+      float sc[REP];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+      for (int hh = 0; hh < REP; ++hh) {
+        float p = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p = fmaf(qr[hh][i], kf[i], p);
+        sc[hh] = p;
+      }
+#pragma unroll
+      for (int o = LPT / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int hh = 0; hh < REP; ++hh) sc[hh] += __shfl_xor_sync(0xffffffffu, sc[hh], o);
+      if (active) {
+#pragma unroll
+        for (int hh = 0; hh < REP; ++hh) {
+          const float s2 = sc[hh] * scale2;
+          const float mn = fmaxf(m[hh], s2);
+          const float corr = exp2f(m[hh] - mn);   // m = -inf -> 0
+          const float p = exp2f(s2 - mn);
+          l[hh] = l[hh] * corr + p;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[hh][i] = fmaf(p, vf[i], acc[hh][i] * corr);
+          m[hh] = mn;
+        }
+      }
     }
-    consume(kf, vf, active);
-  }
-  if (owns_new && warp == 0) {  // the current token, from shared memory
-    float kf[8], vf[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { kf[i] = knew_s[j * 8 + i]; vf[i] = vnew_s[j * 8 + i]; }
-    consume(kf, vf, sub == 0);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
   }
 
   // ---- merge the TPW token groups of a warp
@@ -514,18 +570,18 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeArgs a
       for (int i = 0; i < 8; ++i) red_acc[warp][hh][j * 8 + i] = acc[hh][i];
     }
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 
   // ---- CTA partial -> global
   float* part = a.part + ((((size_t)slot * a.n_kv + g) * a.nsplit + split) * REP) * (HD + 2);
-  for (int t = tid; t < REP * HD; t += 256) {
+  for (int t = tid; t < REP * HD; t += NW * 32) {
     const int hh = t / HD, i = t % HD;
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) M = fmaxf(M, red_m[w][hh]);
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, red_m[w][hh]);
     float L = 0.f, A = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < NW; ++w) {
       const float c = (red_m[w][hh] == -INFINITY) ? 0.f : exp2f(red_m[w][hh] - M);
       L = fmaf(red_l[w][hh], c, L);
       A = fmaf(red_acc[w][hh][i], c, A);
@@ -535,41 +591,71 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecodeArgs a
     ph[2 + i] = A;
   }
   __threadfence();
-  __syncthreads();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   if (tid == 0) {
     unsigned* cnt = a.counters + (size_t)slot * a.n_kv + g;
     const unsigned old = atomicAdd(cnt, 1u);
     is_last_s = (old == (unsigned)a.nsplit - 1u);
     if (is_last_s) *cnt = 0u;  // re-arm for the next launch (graph replay)
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   if (!is_last_s) return;
   __threadfence();
 
-  // ---- last split to finish combines all partials of this kv head
+  // ---- last split to finish combines all partials of this kv head: one L2 round trip brings every
+  // split's (m, l) into shared memory, then the accumulators stream with independent loads.
   const float* pall = a.part + (((size_t)slot * a.n_kv + g) * a.nsplit) * REP * (HD + 2);
-  float* out = a.out + (size_t)slot * a.out_stride;
-  for (int t = tid; t < REP * HD; t += 256) {
-    const int hh = t / HD, i = t % HD;
+  const int ns = a.nsplit;   // host guarantees nsplit <= MAXS
+  for (int t = tid; t < ns * REP; t += NW * 32) {
+    const int sidx = t / REP, hh = t % REP;
+    const float* ph = pall + ((size_t)sidx * REP + hh) * (HD + 2);
+    cm_s[sidx][hh] = __ldcg(ph);
+    cw_s[sidx][hh] = __ldcg(ph + 1);   // l for now
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (tid < REP) {
     float M = -INFINITY;
-    for (int s = 0; s < a.nsplit; ++s) M = fmaxf(M, __ldcg(pall + ((size_t)s * REP + hh) * (HD + 2)));
-    float L = 0.f, A = 0.f;
-    for (int s = 0; s < a.nsplit; ++s) {
-      const float* ph = pall + ((size_t)s * REP + hh) * (HD + 2);
-      const float ms = __ldcg(ph);
+    for (int sidx = 0; sidx < ns; ++sidx) M = fmaxf(M, cm_s[sidx][tid]);
+    float L = 0.f;
+    for (int sidx = 0; sidx < ns; ++sidx) {
+      const float ms = cm_s[sidx][tid];
       const float c = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
-      L = fmaf(__ldcg(ph + 1), c, L);
-      A = fmaf(__ldcg(ph + 2 + i), c, A);
+      L = fmaf(cw_s[sidx][tid], c, L);
+      cw_s[sidx][tid] = c;             // weight of this split
     }
-    out[(size_t)(g * REP + hh) * HD + i] = bf16_round(A / L);
+    cL_s[tid] = L;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  float* out = a.out + (size_t)slot * a.out_stride;
+  for (int t = tid; t < REP * HD; t += NW * 32) {
+    const int hh = t / HD, i = t % HD;
+    const float* pa = pall + (size_t)hh * (HD + 2) + 2 + i;
+    float A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
+    int sidx = 0;
+    for (; sidx + 4 <= ns; sidx += 4) {
+      const float v0 = __ldcg(pa + (size_t)(sidx + 0) * REP * (HD + 2));
+      const float v1 = __ldcg(pa + (size_t)(sidx + 1) * REP * (HD + 2));
+      const float v2 = __ldcg(pa + (size_t)(sidx + 2) * REP * (HD + 2));
+      const float v3 = __ldcg(pa + (size_t)(sidx + 3) * REP * (HD + 2));
+      A0 = fmaf(v0, cw_s[sidx + 0][hh], A0);
+      A1 = fmaf(v1, cw_s[sidx + 1][hh], A1);
+      A2 = fmaf(v2, cw_s[sidx + 2][hh], A2);
+      A3 = fmaf(v3, cw_s[sidx + 3][hh], A3);
+    }
+    for (; sidx < ns; ++sidx) A0 = fmaf(__ldcg(pa + (size_t)sidx * REP * (HD + 2)), cw_s[sidx][hh], A0);
+    out[(size_t)(g * REP + hh) * HD + i] = bf16_round(((A0 + A1) + (A2 + A3)) / cL_s[hh]);
   }
 }
 
 int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   const int rep = a.n_heads / a.n_kv;
-  dim3 grid(a.n_kv, a.nsplit, a.batch), block(256);
+  dim3 grid(a.n_kv, a.nsplit, a.batch), block(288);
+  if (a.nsplit > 64 || 2 * a.page_size * a.head_dim * 2 * 2 > kAttnRingBytes) return -1;
+  const size_t smem = kAttnRingBytes;
   cudaError_t e = cudaErrorInvalidValue;
-#define CL_ATT(R, D) e = launch_ex(attn_decode_kernel<R, D>, grid, block, 0, st, pdl, a)
+#define CL_ATT(R, D) do { static bool once = false; if (!once) { prefer_max_smem(attn_decode_kernel<R, D>);                 \
+      cudaFuncSetAttribute(attn_decode_kernel<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnRingBytes); once = true; } \
+    e = launch_ex(attn_decode_kernel<R, D>, grid, block, smem, st, pdl, a); } while (0)
   if (a.head_dim == 128) {
     if (rep == 1) CL_ATT(1, 128); else if (rep == 2) CL_ATT(2, 128); else if (rep == 4) CL_ATT(4, 128);
     else if (rep == 8) CL_ATT(8, 128);
@@ -605,6 +691,8 @@ int launch_embed(const __nv_bfloat16* table, int d, const int* tok, float* h, in
                  cudaStream_t st) {
   int threads = 128;
   int blocks = (d / 8 + threads - 1) / threads;
+  static bool once = false;
+  if (!once) { prefer_max_smem(embed_kernel); once = true; }
   embed_kernel<<<dim3(blocks, batch), threads, 0, st>>>(table, d, tok, h, h_stride, slots);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -645,14 +733,21 @@ __global__ void __launch_bounds__(256) step_tail_kernel(const StepTailArgs a) {
     if (is_last_s) a.counters[slot] = 0u;
   }
   __syncthreads();
-  if (!is_last_s || tid != 0) return;
+  if (!is_last_s || warp != 0) return;
   __threadfence();
   best = -INFINITY; bi = 0x7fffffff;
-  for (int i = 0; i < (int)gridDim.x; ++i) {
+  for (int i = lane; i < (int)gridDim.x; i += 32) {
     const float v = __ldcg(a.part_val + (size_t)slot * gridDim.x + i);
     const int id = __ldcg(a.part_idx + (size_t)slot * gridDim.x + i);
     if (v > best || (v == best && id < bi)) { best = v; bi = id; }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane != 0) return;
   if (bi == 0x7fffffff) bi = 0;  // all-NaN logits: stay in range
   a.tok[slot] = bi;
   a.pos[slot] += 1;
@@ -669,6 +764,8 @@ __global__ void step_bump_kernel(int* step_counter) {
 }
 
 int launch_step_tail(const StepTailArgs& a, cudaStream_t st) {
+  static bool once = false;
+  if (!once) { prefer_max_smem(step_tail_kernel); prefer_max_smem(step_bump_kernel); once = true; }
   step_tail_kernel<<<dim3(kTailBlocks, a.batch), 256, 0, st>>>(a);
   if (cudaGetLastError() != cudaSuccess) return -1;
   step_bump_kernel<<<1, 1, 0, st>>>(a.step_counter);
@@ -676,19 +773,25 @@ int launch_step_tail(const StepTailArgs& a, cudaStream_t st) {
 }
 
 __global__ void synth_bf16_kernel(__nv_bfloat16* out, int64_t n, int k_cols, int row_mult, int row_off, uint64_t seed,
-                                  int key, float scale) {
+                                  int key, float scale, int rope_hd) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / k_cols, c = i - r * k_cols;
+    int64_t r = i / k_cols;
+    const int64_t c = i - r * k_cols;
     const float v = (float)synth_int(seed, key, (uint64_t)i) * scale;
+    if (rope_hd > 0) {  // logical row (head, w) -> stored row head*hd + (w < hd/2 ? 2w : 2(w - hd/2) + 1)
+      const int64_t head = r / rope_hd;
+      const int w = (int)(r - head * rope_hd), half = rope_hd >> 1;
+      r = head * rope_hd + (w < half ? 2 * w : 2 * (w - half) + 1);
+    }
     out[(r * row_mult + row_off) * k_cols + c] = __float2bfloat16_rn(v);
   }
 }
 int launch_synth_bf16(__nv_bfloat16* out, int64_t n_logical, int k_cols, int row_mult, int row_off, uint64_t seed,
-                      int key, float scale, cudaStream_t st) {
+                      int key, float scale, cudaStream_t st, int rope_hd) {
   int blocks = (int)((n_logical + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  synth_bf16_kernel<<<blocks, 256, 0, st>>>(out, n_logical, k_cols, row_mult, row_off, seed, key, scale);
+  synth_bf16_kernel<<<blocks, 256, 0, st>>>(out, n_logical, k_cols, row_mult, row_off, seed, key, scale, rope_hd);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 __global__ void synth_gain_kernel(float* out, int n, uint64_t seed, int key, float scale) {

@@ -89,13 +89,15 @@ int Engine::init(const cl_engine_config& c) {
   if (max_seqs_ < max_batch_) max_seqs_ = max_batch_;
   use_graph_ = c.use_cuda_graph >= 0 && env_int("CL_GRAPH", 1) != 0;
   use_pdl_ = env_int("CL_PDL", 1) != 0;
+  pdl_early_ = env_int("CL_PDL_EARLY", 1);
+  skip_attn_ = env_int("CL_SKIP_ATTN", 0) != 0;   // timing experiments only (wrong results)
   gemv_variant_ = c.decode_path == 1 ? 0 : 1;
   gemv_variant_ = env_int("CL_GEMV_VARIANT", gemv_variant_);
   q_dim_ = cfg.n_heads * cfg.head_dim;
   kv_dim_ = cfg.n_kv_heads * cfg.head_dim;
   qkv_dim_ = q_dim_ + 2 * kv_dim_;
-  nsplit_ = std::max(1, std::min(32, sm_count() / cfg.n_kv_heads));
-  nsplit_ = env_int("CL_ATTN_NSPLIT", nsplit_);
+  nsplit_ = std::max(1, std::min(64, sm_count() / cfg.n_kv_heads));
+  nsplit_ = std::max(1, std::min(64, env_int("CL_ATTN_NSPLIT", nsplit_)));
   max_pages_per_seq_ = (cfg.max_seq_len + page_size_ - 1) / page_size_;
 
   const size_t kv_bytes_per_token = (size_t)2 * cfg.n_layers * kv_dim_ * 2;
@@ -170,9 +172,10 @@ int Engine::fill_synthetic(uint64_t seed) {
     const int b = l * 16;
     n += launch_synth_gain(L.attn_norm, d, seed, b + K_ATTN_NORM, kNormScale, stream_);
     n += launch_synth_gain(L.ffn_norm, d, seed, b + K_FFN_NORM, kNormScale, stream_);
-    n += launch_synth_bf16(L.wqkv, (int64_t)q_dim_ * d, d, 1, 0, seed, b + K_WQ, kLinearScale, stream_);
-    n += launch_synth_bf16(L.wqkv + (size_t)q_dim_ * d, (int64_t)kv_dim_ * d, d, 1, 0, seed, b + K_WK, kLinearScale, stream_);
-    n += launch_synth_bf16(L.wqkv + (size_t)(q_dim_ + kv_dim_) * d, (int64_t)kv_dim_ * d, d, 1, 0, seed, b + K_WV, kLinearScale, stream_);
+    // q|k|v rows are stored rope-pair-interleaved per head (kernels.h: QkvEpi)
+    n += launch_synth_bf16(L.wqkv, (int64_t)q_dim_ * d, d, 1, 0, seed, b + K_WQ, kLinearScale, stream_, cfg.head_dim);
+    n += launch_synth_bf16(L.wqkv + (size_t)q_dim_ * d, (int64_t)kv_dim_ * d, d, 1, 0, seed, b + K_WK, kLinearScale, stream_, cfg.head_dim);
+    n += launch_synth_bf16(L.wqkv + (size_t)(q_dim_ + kv_dim_) * d, (int64_t)kv_dim_ * d, d, 1, 0, seed, b + K_WV, kLinearScale, stream_, cfg.head_dim);
     n += launch_synth_bf16(L.wo, (int64_t)d * q_dim_, q_dim_, 1, 0, seed, b + K_WO, kLinearScale, stream_);
     n += launch_synth_bf16(L.wgu, (int64_t)F * d, d, 2, 0, seed, b + K_WGATE, kLinearScale, stream_);
     n += launch_synth_bf16(L.wgu, (int64_t)F * d, d, 2, 1, seed, b + K_WUP, kLinearScale, stream_);
@@ -206,9 +209,24 @@ int Engine::set_tensor(int layer, int kind, const uint16_t* data, int64_t n) {
   switch (kind) {
     case K_ATTN_NORM: return copy_gain(L.attn_norm, d);
     case K_FFN_NORM: return copy_gain(L.ffn_norm, d);
-    case K_WQ: return copy16(L.wqkv, (int64_t)q_dim_ * d);
-    case K_WK: return copy16(L.wqkv + (size_t)q_dim_ * d, (int64_t)kv_dim_ * d);
-    case K_WV: return copy16(L.wqkv + (size_t)(q_dim_ + kv_dim_) * d, (int64_t)kv_dim_ * d);
+    case K_WQ:
+    case K_WK:
+    case K_WV: {
+      const int64_t rows = kind == K_WQ ? q_dim_ : kv_dim_;
+      if (n != rows * d) { set_last_error("set_tensor: wrong element count"); return CL_ERR_INVALID_ARG; }
+      __nv_bfloat16* dst = L.wqkv + (kind == K_WQ ? 0 : kind == K_WK ? (size_t)q_dim_ * d : (size_t)(q_dim_ + kv_dim_) * d);
+      // rope-pair interleave per head: logical row (head, w) -> head*hd + (w < hd/2 ? 2w : 2(w - hd/2) + 1)
+      std::vector<uint16_t> perm((size_t)n);
+      const int hd = cfg.head_dim, half = hd / 2;
+      for (int64_t r = 0; r < rows; ++r) {
+        const int64_t head = r / hd;
+        const int w = (int)(r % hd);
+        const int64_t rr = head * hd + (w < half ? 2 * w : 2 * (w - half) + 1);
+        memcpy(&perm[(size_t)rr * d], data + (size_t)r * d, (size_t)d * 2);
+      }
+      CL_CUDA_OK(cudaMemcpy(dst, perm.data(), (size_t)n * 2, cudaMemcpyHostToDevice));
+      return CL_OK;
+    }
     case K_WO: return copy16(L.wo, d * q_dim_);
     case K_WDOWN: return copy16(L.wdown, d * F);
     case K_WGATE:
@@ -230,7 +248,7 @@ int Engine::alloc_state() {
   DMALLOC(d_bt_, S * max_pages_per_seq_ * 4);
   DMALLOC(d_slots_, (size_t)max_batch_ * 4);
   DMALLOC(d_h_, S * d * 4);
-  DMALLOC(d_qkv_, S * qkv_dim_ * 4);
+  DMALLOC(d_q_, S * q_dim_ * 4);
   DMALLOC(d_attn_, S * q_dim_ * 4);
   DMALLOC(d_act_, S * (size_t)cfg.d_ff * 4);
   DMALLOC(d_logits_, S * (size_t)cfg.vocab_size * 4);
@@ -296,39 +314,42 @@ int Engine::enqueue_step(int B, bool tail) {
   for (int l = 0; l < cfg.n_layers; ++l) {
     const auto& L = layers_[l];
     GemvArgs g;
-    g.slots = d_slots_; g.batch = B;
-    // (1) RMSNorm + fused q|k|v projection
+    g.slots = d_slots_; g.batch = B; g.pdl_early = pdl_early_;
+    // (1) RMSNorm + fused q|k|v projection; epilogue: RoPE + bf16 round + q out + KV append into the paged cache
     g.W = L.wqkv; g.N = qkv_dim_; g.K = d; g.h = d_h_; g.gain = L.attn_norm; g.eps = cfg.rms_eps;
-    g.y = d_qkv_; g.x_stride = d; g.y_stride = qkv_dim_;
-    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_STORE, true, g, stream_, use_pdl_));
-    // (2) RoPE + KV append + paged GQA attention
+    g.y = d_q_; g.x_stride = d; g.y_stride = q_dim_;
+    g.qkv.rope = rope_; g.qkv.pos = d_pos_; g.qkv.block_tables = d_bt_; g.qkv.bt_stride = max_pages_per_seq_;
+    g.qkv.kpool = kpool_ + (size_t)l * kv_layer_elems_; g.qkv.vpool = vpool_ + (size_t)l * kv_layer_elems_;
+    g.qkv.n_heads = cfg.n_heads; g.qkv.n_kv = cfg.n_kv_heads; g.qkv.head_dim = cfg.head_dim; g.qkv.page_size = page_size_;
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_QKV, true, g, stream_, use_pdl_));
+    // (2) paged GQA attention over tokens 0..pos
     AttnDecodeArgs a;
-    a.qkv = d_qkv_; a.qkv_stride = qkv_dim_; a.rope = rope_;
+    a.q = d_q_; a.q_stride = q_dim_;
     a.kpool = kpool_ + (size_t)l * kv_layer_elems_; a.vpool = vpool_ + (size_t)l * kv_layer_elems_;
     a.block_tables = d_bt_; a.bt_stride = max_pages_per_seq_; a.pos = d_pos_;
     a.out = d_attn_; a.out_stride = q_dim_; a.part = d_attn_part_; a.counters = d_attn_cnt_;
     a.slots = d_slots_; a.batch = B; a.n_heads = cfg.n_heads; a.n_kv = cfg.n_kv_heads; a.head_dim = cfg.head_dim;
-    a.page_size = page_size_; a.nsplit = nsplit_;
-    CL_LAUNCH(launch_attn_decode(a, stream_, use_pdl_));
+    a.page_size = page_size_; a.nsplit = nsplit_; a.pdl_early = pdl_early_;
+    if (!skip_attn_) CL_LAUNCH(launch_attn_decode(a, stream_, use_pdl_));
     // (3) o projection + residual
     GemvArgs o;
-    o.slots = d_slots_; o.batch = B;
+    o.slots = d_slots_; o.batch = B; o.pdl_early = pdl_early_;
     o.W = L.wo; o.N = d; o.K = q_dim_; o.x = d_attn_; o.x_stride = q_dim_; o.y = d_h_; o.resid = d_h_; o.y_stride = d;
     CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, o, stream_, use_pdl_));
     // (4) RMSNorm + gate/up + SiLU*mul
     GemvArgs u;
-    u.slots = d_slots_; u.batch = B;
+    u.slots = d_slots_; u.batch = B; u.pdl_early = pdl_early_;
     u.W = L.wgu; u.N = 2 * F; u.K = d; u.h = d_h_; u.gain = L.ffn_norm; u.eps = cfg.rms_eps; u.y = d_act_;
     u.x_stride = d; u.y_stride = F;
     CL_LAUNCH(launch_gemv(gemv_variant_, EPI_GATEUP, true, u, stream_, use_pdl_));
     // (5) down projection + residual
     GemvArgs w;
-    w.slots = d_slots_; w.batch = B;
+    w.slots = d_slots_; w.batch = B; w.pdl_early = pdl_early_;
     w.W = L.wdown; w.N = d; w.K = F; w.x = d_act_; w.x_stride = F; w.y = d_h_; w.resid = d_h_; w.y_stride = d;
     CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, w, stream_, use_pdl_));
   }
   GemvArgs lm;
-  lm.slots = d_slots_; lm.batch = B;
+  lm.slots = d_slots_; lm.batch = B; lm.pdl_early = pdl_early_;
   lm.W = lm_head_; lm.N = cfg.vocab_size; lm.K = d; lm.h = d_h_; lm.gain = final_norm_; lm.eps = cfg.rms_eps;
   lm.y = d_logits_; lm.x_stride = d; lm.y_stride = cfg.vocab_size;
   CL_LAUNCH(launch_gemv(gemv_variant_, EPI_STORE, true, lm, stream_, use_pdl_));

@@ -144,7 +144,8 @@ class Engine {
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   int page_size_ = 32, max_batch_ = 8, max_seqs_ = 8, n_pages_ = 0, max_pages_per_seq_ = 0;
   int gemv_variant_ = 1, nsplit_ = 16;
-  bool use_graph_ = true, use_pdl_ = true;
+  bool use_graph_ = true, use_pdl_ = true, skip_attn_ = false;
+  int pdl_early_ = 1;
   int qkv_dim_ = 0, q_dim_ = 0, kv_dim_ = 0;
 
   // weights
@@ -160,7 +161,7 @@ class Engine {
 
   // per-slot state
   int* d_tok_ = nullptr; int* d_pos_ = nullptr; int* d_bt_ = nullptr; int* d_slots_ = nullptr;
-  float* d_h_ = nullptr; float* d_qkv_ = nullptr; float* d_attn_ = nullptr; float* d_act_ = nullptr;
+  float* d_h_ = nullptr; float* d_q_ = nullptr; float* d_attn_ = nullptr; float* d_act_ = nullptr;
   float* d_logits_ = nullptr; float* d_attn_part_ = nullptr; unsigned* d_attn_cnt_ = nullptr;
   float* d_tail_val_ = nullptr; int* d_tail_idx_ = nullptr; unsigned* d_tail_cnt_ = nullptr;
   int* d_ids_ring_ = nullptr; int* d_step_counter_ = nullptr; int* d_prompt_ = nullptr;

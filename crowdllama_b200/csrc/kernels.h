@@ -6,7 +6,21 @@
 
 namespace cl {
 
-enum GemvEpi { EPI_STORE = 0, EPI_RESID = 1, EPI_GATEUP = 2 };
+enum GemvEpi { EPI_STORE = 0, EPI_RESID = 1, EPI_GATEUP = 2, EPI_QKV = 3 };
+
+// EPI_QKV: the q|k|v projection's rows are stored ROPE-PAIR-INTERLEAVED (within each head, row 2j holds
+// dim j and row 2j+1 holds dim j + head_dim/2), so the row pair a GEMV thread owns is exactly one RoPE
+// rotation pair: the epilogue rotates, rounds to bf16, writes q to y[slot][H*D] (natural dim order) and
+// appends k / v straight into the paged cache.  The attention kernel then needs no RoPE and no append.
+struct QkvEpi {
+  const float2* rope = nullptr;       // [max_pos][head_dim/2]
+  const int* pos = nullptr;           // [slot]
+  const int* block_tables = nullptr;  // [slot][bt_stride]
+  int bt_stride = 0;
+  __nv_bfloat16* kpool = nullptr;     // this layer
+  __nv_bfloat16* vpool = nullptr;
+  int n_heads = 0, n_kv = 0, head_dim = 0, page_size = 0;
+};
 
 // y[slot] = epi(W * x[slot]).  Row pairs (2i, 2i+1) are always processed together so the
 // gate/up interleaving (row 2i = gate_i, row 2i+1 = up_i) needs no special casing.
@@ -22,17 +36,18 @@ struct GemvArgs {
   int x_stride = 0, y_stride = 0;
   const int* slots = nullptr;        // blockIdx.y = b -> slot (nullptr => identity)
   int batch = 1;
+  int pdl_early = 1;                 // 1: trigger dependents at kernel start; 0: when this CTA has issued its last load
+  QkvEpi qkv;                        // EPI_QKV only
 };
 
 struct AttnDecodeArgs {
-  const float* qkv = nullptr;        // [slot][qkv_stride] raw q | k | v of the current token
-  int qkv_stride = 0;
-  const float2* rope = nullptr;      // [max_pos][head_dim/2] (cos, sin)
-  __nv_bfloat16* kpool = nullptr;    // this layer: [n_pages][n_kv][page][head_dim]
-  __nv_bfloat16* vpool = nullptr;
+  const float* q = nullptr;          // [slot][q_stride] roped, bf16-rounded query of the current token
+  int q_stride = 0;
+  const __nv_bfloat16* kpool = nullptr;  // this layer: [n_pages][n_kv][page][head_dim]; holds tokens 0..pos
+  const __nv_bfloat16* vpool = nullptr;
   const int* block_tables = nullptr; // [slot][bt_stride]
   int bt_stride = 0;
-  const int* pos = nullptr;          // [slot] index of the current token
+  const int* pos = nullptr;          // [slot] index of the current token (context = pos + 1 tokens)
   float* out = nullptr;              // [slot][out_stride] bf16-rounded fp32
   int out_stride = 0;
   float* part = nullptr;             // [slot][n_kv][nsplit][rep][head_dim + 2]
@@ -40,6 +55,7 @@ struct AttnDecodeArgs {
   const int* slots = nullptr;
   int batch = 1;
   int n_heads = 0, n_kv = 0, head_dim = 0, page_size = 0, nsplit = 0;
+  int pdl_early = 1;
 };
 
 struct StepTailArgs {                // argmax over logits, advance the sequence
@@ -63,8 +79,9 @@ int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 int launch_embed(const __nv_bfloat16* table, int d, const int* tok, float* h, int h_stride, const int* slots,
                  int batch, cudaStream_t st);
 int launch_step_tail(const StepTailArgs& a, cudaStream_t st);
+// rope_hd > 0: rows are written rope-pair-interleaved per head of rope_hd rows (see QkvEpi)
 int launch_synth_bf16(__nv_bfloat16* out, int64_t n_logical, int k_cols, int row_mult, int row_off, uint64_t seed,
-                      int key, float scale, cudaStream_t st);
+                      int key, float scale, cudaStream_t st, int rope_hd = 0);
 int launch_synth_gain(float* out, int n, uint64_t seed, int key, float scale, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, int64_t n, cudaStream_t st);
 int launch_fill_u16(uint16_t* p, int64_t n, uint16_t v, cudaStream_t st);
@@ -80,6 +97,7 @@ bool gemm_tcgen05_supported(int T, int N, int K);
 // xn[t] = bf16(rmsnorm(h[t]) * gain)
 int launch_rmsnorm_bf16(const float* h, const float* gain, float eps, __nv_bfloat16* out, int T, int d, cudaStream_t st);
 // rope q,k of T tokens starting at pos0; q -> bf16 [T][H][D]; k,v -> paged cache (bf16) and optional dense copies
+// qkv columns arrive rope-pair-interleaved (the GEMM uses the same permuted wqkv rows)
 struct RopeScatterArgs {
   const float* qkv; int qkv_stride; const float2* rope; int pos0; int T;
   __nv_bfloat16* q_out;              // [T][H*D]

@@ -1,6 +1,7 @@
 // ops_api.cu — cl_op_*: single-kernel entry points of the C-ABI with HOST buffers in and out.
 // Each runs exactly the kernel the token step uses (parity tests per kernel, microbenchmarks).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -110,10 +111,9 @@ int cl_op_rmsnorm_gateup(int device, int variant, const uint16_t* w_gu, const fl
   return run_gemv(device, variant, EPI_GATEUP, true, w_gu, h, gain, eps, nullptr, act, 2 * d_ff, k, d_ff, 0, nullptr);
 }
 
-int cl_op_attn_decode(int device, const float* q, const float* k_new, const float* v_new, const uint16_t* k_cache,
-                      const uint16_t* v_cache, int32_t ctx_len, int32_t n_heads, int32_t n_kv, int32_t head_dim, float rope_theta,
-                      int32_t page_size, float* out) {
-  if (!q || !k_new || !v_new || !out || ctx_len < 0 || (ctx_len > 0 && (!k_cache || !v_cache))) return CL_ERR_INVALID_ARG;
+int cl_op_attn_decode(int device, const float* q, const uint16_t* k_cache, const uint16_t* v_cache, int32_t ctx_len, int32_t n_heads,
+                      int32_t n_kv, int32_t head_dim, int32_t page_size, float* out) {
+  if (!q || !out || ctx_len <= 0 || !k_cache || !v_cache) return CL_ERR_INVALID_ARG;
   int rc = check_device(device);
   if (rc) return rc;
   const int rep = n_kv > 0 ? n_heads / n_kv : 0;
@@ -123,52 +123,96 @@ int cl_op_attn_decode(int device, const float* q, const float* k_new, const floa
     return CL_ERR_INVALID_ARG;
   }
   const int P = page_size, HD = head_dim;
-  const int n_pages = (ctx_len + 1 + P - 1) / P;
+  const int n_pages = (ctx_len + P - 1) / P;
   // scatter the dense cache into pages in a scrambled page order (exercises the block table)
   std::vector<int> bt(n_pages);
   for (int i = 0; i < n_pages; ++i) bt[i] = (int)(((long long)i * 7 + 3) % n_pages);
   if (n_pages % 7 == 0) for (int i = 0; i < n_pages; ++i) bt[i] = n_pages - 1 - i;
   const size_t pool_elems = (size_t)n_pages * n_kv * P * HD;
-  std::vector<uint16_t> kp(pool_elems, 0), vp(pool_elems, 0);
+  std::vector<uint16_t> kp(pool_elems, 0x7fc0), vp(pool_elems, 0x7fc0);   // NaN fill: slots past ctx must never be read into the result
   for (int t = 0; t < ctx_len; ++t)
     for (int g = 0; g < n_kv; ++g) {
       const size_t dst = (((size_t)bt[t / P] * n_kv + g) * P + t % P) * HD;
       memcpy(&kp[dst], k_cache + ((size_t)t * n_kv + g) * HD, (size_t)HD * 2);
       memcpy(&vp[dst], v_cache + ((size_t)t * n_kv + g) * HD, (size_t)HD * 2);
     }
-  const int half = HD / 2, qd = n_heads * HD, kvd = n_kv * HD;
-  std::vector<float2> rope((size_t)(ctx_len + 1) * half);
-  for (int p = 0; p <= ctx_len; ++p)
-    for (int i = 0; i < half; ++i) {
-      const double inv = pow((double)rope_theta, -2.0 * (double)i / (double)HD);
-      rope[(size_t)p * half + i] = make_float2((float)cos((double)p * inv), (float)sin((double)p * inv));
-    }
-  std::vector<float> qkv((size_t)qd + 2 * kvd);
-  memcpy(qkv.data(), q, (size_t)qd * 4);
-  memcpy(qkv.data() + qd, k_new, (size_t)kvd * 4);
-  memcpy(qkv.data() + qd + kvd, v_new, (size_t)kvd * 4);
-  const int nsplit = std::max(1, std::min(32, sm_count() / n_kv));
-  DevBuf dq, dr, dk, dv, dbt, dpos, dout, dpart, dcnt;
-  CL_CUDA_OK(dq.upload(qkv.data(), qkv.size() * 4));
-  CL_CUDA_OK(dr.upload(rope.data(), rope.size() * sizeof(float2)));
+  const int qd = n_heads * HD;
+  const int pos = ctx_len - 1;
+  const int nsplit = std::max(1, std::min(64, sm_count() / n_kv));
+  DevBuf dq, dk, dv, dbt, dpos, dout, dpart, dcnt;
+  CL_CUDA_OK(dq.upload(q, (size_t)qd * 4));
   CL_CUDA_OK(dk.upload(kp.data(), pool_elems * 2));
   CL_CUDA_OK(dv.upload(vp.data(), pool_elems * 2));
   CL_CUDA_OK(dbt.upload(bt.data(), bt.size() * 4));
-  CL_CUDA_OK(dpos.upload(&ctx_len, 4));
+  CL_CUDA_OK(dpos.upload(&pos, 4));
   CL_CUDA_OK(dout.alloc((size_t)qd * 4));
   CL_CUDA_OK(dpart.alloc((size_t)n_kv * nsplit * rep * (HD + 2) * 4));
   CL_CUDA_OK(dcnt.alloc((size_t)n_kv * 4));
   CL_CUDA_OK(cudaMemset(dcnt.p, 0, (size_t)n_kv * 4));
   AttnDecodeArgs a;
-  a.qkv = dq.as<float>(); a.qkv_stride = (int)qkv.size(); a.rope = dr.as<float2>();
+  a.q = dq.as<float>(); a.q_stride = qd;
   a.kpool = dk.as<__nv_bfloat16>(); a.vpool = dv.as<__nv_bfloat16>(); a.block_tables = dbt.as<int>(); a.bt_stride = n_pages;
   a.pos = dpos.as<int>(); a.out = dout.as<float>(); a.out_stride = qd; a.part = dpart.as<float>(); a.counters = dcnt.as<unsigned>();
   a.batch = 1; a.n_heads = n_heads; a.n_kv = n_kv; a.head_dim = HD; a.page_size = P; a.nsplit = nsplit;
   // run twice: the second launch checks that the split counters re-arm (graph replay safety)
   for (int i = 0; i < 2; ++i)
-    if (launch_attn_decode(a, nullptr, false) < 0) { CL_CUDA_OK(cudaGetLastError()); return CL_ERR_CUDA; }
+    if (launch_attn_decode(a, nullptr, false) < 0) { CL_CUDA_OK(cudaGetLastError()); set_last_error("launch_attn_decode failed"); return CL_ERR_CUDA; }
   CL_CUDA_OK(cudaDeviceSynchronize());
   CL_CUDA_OK(cudaMemcpy(out, dout.p, (size_t)qd * 4, cudaMemcpyDeviceToHost));
+  return CL_OK;
+}
+
+int cl_op_qkv_rope_append(int device, int variant, const uint16_t* w_qkv, const float* h, const float* gain, float eps, int32_t d_model,
+                          int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t pos, float rope_theta, float* q_out,
+                          uint16_t* k_out, uint16_t* v_out) {
+  if (!w_qkv || !h || !gain || !q_out || !k_out || !v_out || pos < 0) return CL_ERR_INVALID_ARG;
+  int rc = check_device(device);
+  if (rc) return rc;
+  const int HD = head_dim, half = HD / 2, P = 32;
+  const int qd = n_heads * HD, kvd = n_kv * HD, rows = qd + 2 * kvd;
+  if (!gemv_variant_supported(variant, rows, d_model) || (HD != 64 && HD != 128)) { set_last_error("unsupported shape"); return CL_ERR_INVALID_ARG; }
+  // the engine stores q|k|v rows rope-pair-interleaved per head
+  std::vector<uint16_t> wp((size_t)rows * d_model);
+  for (int r = 0; r < rows; ++r) {
+    const int head = r / HD, w = r % HD;
+    const int rr = head * HD + (w < half ? 2 * w : 2 * (w - half) + 1);
+    memcpy(&wp[(size_t)rr * d_model], w_qkv + (size_t)r * d_model, (size_t)d_model * 2);
+  }
+  std::vector<float2> rope((size_t)(pos + 1) * half);
+  for (int p = 0; p <= pos; ++p)
+    for (int i = 0; i < half; ++i) {
+      const double inv = pow((double)rope_theta, -2.0 * (double)i / (double)HD);
+      rope[(size_t)p * half + i] = make_float2((float)cos((double)p * inv), (float)sin((double)p * inv));
+    }
+  const int n_pages = pos / P + 1;
+  std::vector<int> bt(n_pages);
+  for (int i = 0; i < n_pages; ++i) bt[i] = n_pages - 1 - i;
+  const size_t pool_elems = (size_t)n_pages * n_kv * P * HD;
+  DevBuf dw, dh, dg, dr, dbt, dpos, dq, dk, dv;
+  CL_CUDA_OK(dw.upload(wp.data(), wp.size() * 2));
+  CL_CUDA_OK(dh.upload(h, (size_t)d_model * 4));
+  CL_CUDA_OK(dg.upload(gain, (size_t)d_model * 4));
+  CL_CUDA_OK(dr.upload(rope.data(), rope.size() * sizeof(float2)));
+  CL_CUDA_OK(dbt.upload(bt.data(), bt.size() * 4));
+  CL_CUDA_OK(dpos.upload(&pos, 4));
+  CL_CUDA_OK(dq.alloc((size_t)qd * 4));
+  CL_CUDA_OK(dk.alloc(pool_elems * 2));
+  CL_CUDA_OK(dv.alloc(pool_elems * 2));
+  GemvArgs a;
+  a.W = dw.as<__nv_bfloat16>(); a.N = rows; a.K = d_model; a.h = dh.as<float>(); a.gain = dg.as<float>(); a.eps = eps;
+  a.y = dq.as<float>(); a.x_stride = d_model; a.y_stride = qd; a.batch = 1;
+  a.qkv.rope = dr.as<float2>(); a.qkv.pos = dpos.as<int>(); a.qkv.block_tables = dbt.as<int>(); a.qkv.bt_stride = n_pages;
+  a.qkv.kpool = dk.as<__nv_bfloat16>(); a.qkv.vpool = dv.as<__nv_bfloat16>();
+  a.qkv.n_heads = n_heads; a.qkv.n_kv = n_kv; a.qkv.head_dim = HD; a.qkv.page_size = P;
+  if (launch_gemv(variant, EPI_QKV, true, a, nullptr, false) < 0) { CL_CUDA_OK(cudaGetLastError()); return CL_ERR_CUDA; }
+  CL_CUDA_OK(cudaDeviceSynchronize());
+  CL_CUDA_OK(cudaMemcpy(q_out, dq.p, (size_t)qd * 4, cudaMemcpyDeviceToHost));
+  const int page = bt[pos / P], off = pos % P;
+  for (int g = 0; g < n_kv; ++g) {
+    const size_t src = (((size_t)page * n_kv + g) * P + off) * HD;
+    CL_CUDA_OK(cudaMemcpy(k_out + (size_t)g * HD, dk.as<uint16_t>() + src, (size_t)HD * 2, cudaMemcpyDeviceToHost));
+    CL_CUDA_OK(cudaMemcpy(v_out + (size_t)g * HD, dv.as<uint16_t>() + src, (size_t)HD * 2, cudaMemcpyDeviceToHost));
+  }
   return CL_OK;
 }
 

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) rope_scatter_kernel(const RopeScatterArgs
   for (int i = threadIdx.x; i < a.n_heads * half; i += blockDim.x) {
     const int hh = i / half, j = i % half;
     const float2 cs = rope[j];
-    const float x0 = row[hh * HD + j], x1 = row[hh * HD + j + half];
+    const float x0 = row[hh * HD + 2 * j], x1 = row[hh * HD + 2 * j + 1];   // rope-pair-interleaved GEMM output
     a.q_out[(size_t)t * qd + hh * HD + j] = __float2bfloat16_rn(x0 * cs.x - x1 * cs.y);
     a.q_out[(size_t)t * qd + hh * HD + j + half] = __float2bfloat16_rn(x1 * cs.x + x0 * cs.y);
   }
@@ -80,13 +80,14 @@ __global__ void __launch_bounds__(256) rope_scatter_kernel(const RopeScatterArgs
   for (int i = threadIdx.x; i < a.n_kv * half; i += blockDim.x) {
     const int g = i / half, j = i % half;
     const float2 cs = rope[j];
-    const float x0 = row[qd + g * HD + j], x1 = row[qd + g * HD + j + half];
+    const float x0 = row[qd + g * HD + 2 * j], x1 = row[qd + g * HD + 2 * j + 1];
     const size_t base = (((size_t)page * a.n_kv + g) * a.page_size + off) * HD;
     a.kpool[base + j] = __float2bfloat16_rn(x0 * cs.x - x1 * cs.y);
     a.kpool[base + j + half] = __float2bfloat16_rn(x1 * cs.x + x0 * cs.y);
   }
   for (int i = threadIdx.x; i < kvd; i += blockDim.x) {
-    const int g = i / HD, j = i % HD;
+    const int g = i / HD, w = i % HD;                      // stored column w -> dim (w even ? w/2 : w/2 + half)
+    const int j = (w & 1) ? (w >> 1) + half : (w >> 1);
     const size_t base = (((size_t)page * a.n_kv + g) * a.page_size + off) * HD;
     a.vpool[base + j] = __float2bfloat16_rn(row[qd + kvd + i]);
   }

@@ -66,7 +66,7 @@ EXPORTS = [
     "cl_engine_stats", "cl_engine_set_tensor", "cl_generate", "cl_generate_ids", "cl_result_free",
     "cl_handle_message", "cl_buffer_free", "cl_tokenize", "cl_detokenize", "cl_seq_create", "cl_seq_free",
     "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_debug_hidden",
-    "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_attn_decode",
+    "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_qkv_rope_append", "cl_op_attn_decode",
     "cl_op_gemm_bf16", "cl_op_attn_prefill", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
     "cl_kvpool_reserve", "cl_kvpool_release", "cl_kvpool_pages_of", "cl_kvpool_free_pages", "cl_kvpool_used_pages",
 ]
@@ -116,7 +116,8 @@ def lib():
         "cl_op_gemv_residual": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp, i32, i32]),
         "cl_op_rmsnorm_gemv": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, f32, vp, i32, i32]),
         "cl_op_rmsnorm_gateup": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, f32, vp, i32, i32]),
-        "cl_op_attn_decode": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
+        "cl_op_attn_decode": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "cl_op_qkv_rope_append": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, f32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
         "cl_op_gemm_bf16": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, P(f32)]),
         "cl_op_attn_prefill": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, vp]),
         "cl_op_synth_weights": (C.c_int, [C.c_int, u64, i32, i64, f32, vp]),
@@ -394,19 +395,26 @@ def op_rmsnorm_gateup(w_gu_bf16, h, gain, eps, variant=0, device=0):
     return act
 
 
-def op_attn_decode(q, k_new, v_new, k_cache_bf16, v_cache_bf16, n_heads, n_kv, head_dim, rope_theta, page_size=32,
-                   device=0):
-    q = np.ascontiguousarray(q, dtype=np.float32)
-    kn = np.ascontiguousarray(k_new, dtype=np.float32)
-    vn = np.ascontiguousarray(v_new, dtype=np.float32)
+def op_attn_decode(q_roped, k_cache_bf16, v_cache_bf16, n_heads, n_kv, head_dim, page_size=32, device=0):
+    q = np.ascontiguousarray(q_roped, dtype=np.float32)
     kc = np.ascontiguousarray(k_cache_bf16, dtype=np.uint16)
     vc = np.ascontiguousarray(v_cache_bf16, dtype=np.uint16)
-    ctx = kc.shape[0] if kc.size else 0
     out = np.empty(n_heads * head_dim, np.float32)
-    _check(lib().cl_op_attn_decode(device, _ptr(q), _ptr(kn), _ptr(vn), _ptr(kc) if ctx else None,
-                                   _ptr(vc) if ctx else None, ctx, n_heads, n_kv, head_dim, rope_theta, page_size,
+    _check(lib().cl_op_attn_decode(device, _ptr(q), _ptr(kc), _ptr(vc), kc.shape[0], n_heads, n_kv, head_dim, page_size,
                                    _ptr(out)), "cl_op_attn_decode")
     return out
+
+
+def op_qkv_rope_append(w_qkv_bf16, h, gain, eps, n_heads, n_kv, head_dim, pos, rope_theta, variant=0, device=0):
+    w = np.ascontiguousarray(w_qkv_bf16, dtype=np.uint16)
+    h = np.ascontiguousarray(h, dtype=np.float32)
+    g = np.ascontiguousarray(gain, dtype=np.float32)
+    q = np.empty(n_heads * head_dim, np.float32)
+    k = np.empty(n_kv * head_dim, np.uint16)
+    v = np.empty(n_kv * head_dim, np.uint16)
+    _check(lib().cl_op_qkv_rope_append(device, variant, _ptr(w), _ptr(h), _ptr(g), eps, w.shape[1], n_heads, n_kv, head_dim, pos,
+                                       rope_theta, _ptr(q), _ptr(k), _ptr(v)), "cl_op_qkv_rope_append")
+    return q, k, v
 
 
 def op_gemm_bf16(x_bf16, w_bf16, iters=0, device=0):

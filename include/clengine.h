@@ -212,13 +212,19 @@ int cl_op_rmsnorm_gemv(int device, int variant, const uint16_t* w, const float* 
 /* w_gu interleaved rows (2i = gate_i, 2i+1 = up_i); act_i = bf16round(silu(g_i) * u_i) */
 int cl_op_rmsnorm_gateup(int device, int variant, const uint16_t* w_gu, const float* h,
                          const float* gain, float eps, float* act, int32_t d_ff, int32_t k);
-/* paged GQA decode attention for one sequence: q [n_heads*head_dim] fp32 (pre-RoPE),
- * k_new/v_new [n_kv*head_dim] fp32 (pre-RoPE) for position ctx_len (appended by the kernel),
- * k_cache/v_cache [ctx_len][n_kv][head_dim] bf16 (already roped), out [n_heads*head_dim]. */
-int cl_op_attn_decode(int device, const float* q, const float* k_new, const float* v_new,
-                      const uint16_t* k_cache, const uint16_t* v_cache, int32_t ctx_len,
-                      int32_t n_heads, int32_t n_kv, int32_t head_dim, float rope_theta,
-                      int32_t page_size, float* out);
+/* fused q|k|v projection of ONE token, exactly as the token step runs it: xn = bf16(rmsnorm(h)*gain);
+ * [q|k|v] = W xn (w_qkv: logical rows q | k | v in natural dim order; the wrapper applies the engine's
+ * rope-pair row interleave); RoPE at `pos`; bf16 rounding.  q_out [n_heads*head_dim] fp32 (roped),
+ * k_out / v_out [n_kv*head_dim] bf16 as appended to the paged cache. */
+int cl_op_qkv_rope_append(int device, int variant, const uint16_t* w_qkv, const float* h, const float* gain,
+                          float eps, int32_t d_model, int32_t n_heads, int32_t n_kv, int32_t head_dim,
+                          int32_t pos, float rope_theta, float* q_out, uint16_t* k_out, uint16_t* v_out);
+/* paged GQA decode attention for one sequence: q [n_heads*head_dim] fp32 (roped, bf16-rounded);
+ * k_cache/v_cache [ctx_len][n_kv][head_dim] bf16 = tokens 0..ctx_len-1 (the current token included);
+ * out [n_heads*head_dim] bf16-rounded fp32.  The wrapper scatters the cache into scrambled pages. */
+int cl_op_attn_decode(int device, const float* q, const uint16_t* k_cache, const uint16_t* v_cache,
+                      int32_t ctx_len, int32_t n_heads, int32_t n_kv, int32_t head_dim, int32_t page_size,
+                      float* out);
 /* prefill GEMM on tcgen05: Y[t][n] = sum_k X[t][k] W[n][k]; X,W bf16, Y fp32 */
 int cl_op_gemm_bf16(int device, const uint16_t* x, const uint16_t* w, float* y, int32_t t,
                     int32_t n, int32_t k, int32_t iters, float* ms);

@@ -61,34 +61,48 @@ def test_rmsnorm_gemv_and_gateup(variant, n, k):
 
 
 @pytest.mark.parametrize("n_heads,n_kv,hd", [(32, 8, 128), (32, 4, 64), (4, 2, 64), (2, 1, 64), (8, 8, 128)])
-@pytest.mark.parametrize("ctx", [0, 1, 31, 32, 33, 257, 1500])
+@pytest.mark.parametrize("ctx", [1, 2, 31, 32, 33, 257, 1500, 4100])
 def test_attn_decode_matches_oracle(n_heads, n_kv, hd, ctx):
+    """Split-KV paged attention over tokens 0..ctx-1 (TMA-staged pages, scrambled block table)."""
     rng = np.random.default_rng(ctx * 7 + n_heads + hd)
-    theta = 5e5
-    q = rng.standard_normal(n_heads * hd).astype(np.float32)
-    kn = rng.standard_normal(n_kv * hd).astype(np.float32)
-    vn = rng.standard_normal(n_kv * hd).astype(np.float32)
+    q = oc.np_bf16_round(rng.standard_normal(n_heads * hd).astype(np.float32))
     kc = _rand_bf16(rng, (ctx, n_kv, hd), 1.0)
     vc = _rand_bf16(rng, (ctx, n_kv, hd), 1.0)
-    out = eng.op_attn_decode(q, kn, vn, kc, vc, n_heads, n_kv, hd, theta, page_size=32)
-    # oracle: rope(q), rope(k_new) at position ctx, bf16-rounded; append; attention
-    q_r = oc.np_bf16_round(oc.rope(q, n_heads, hd, ctx, theta))
-    k_r = oc.np_bf16_round(oc.rope(kn, n_kv, hd, ctx, theta))
-    v_r = oc.np_bf16_round(vn)
-    kfull = np.concatenate([oc.np_f32_from_bf16(kc).reshape(ctx, n_kv, hd), k_r.reshape(1, n_kv, hd)])
-    vfull = np.concatenate([oc.np_f32_from_bf16(vc).reshape(ctx, n_kv, hd), v_r.reshape(1, n_kv, hd)])
-    ref = oc.np_bf16_round(oc.attention(q_r, kfull, vfull, n_heads, n_kv, hd))
+    out = eng.op_attn_decode(q, kc, vc, n_heads, n_kv, hd, page_size=32)
+    ref = oc.np_bf16_round(oc.attention(q, oc.np_f32_from_bf16(kc), oc.np_f32_from_bf16(vc), n_heads, n_kv, hd))
+    assert np.isfinite(out).all()      # the op NaN-fills cache slots past ctx: they must never leak into the result
     assert np.abs(out - ref).max() <= 2 ** -7 * max(1.0, np.abs(ref).max())
 
 
 def test_attn_decode_page_sizes():
     rng = np.random.default_rng(5)
     n_heads, n_kv, hd, ctx = 32, 8, 128, 700
-    q = rng.standard_normal(n_heads * hd).astype(np.float32)
-    kn = rng.standard_normal(n_kv * hd).astype(np.float32)
-    vn = rng.standard_normal(n_kv * hd).astype(np.float32)
+    q = oc.np_bf16_round(rng.standard_normal(n_heads * hd).astype(np.float32))
     kc = _rand_bf16(rng, (ctx, n_kv, hd), 1.0)
     vc = _rand_bf16(rng, (ctx, n_kv, hd), 1.0)
-    outs = [eng.op_attn_decode(q, kn, vn, kc, vc, n_heads, n_kv, hd, 1e4, page_size=p) for p in (16, 32, 64)]
-    np.testing.assert_array_equal(outs[0], outs[1])
-    np.testing.assert_array_equal(outs[1], outs[2])
+    ref = oc.np_bf16_round(oc.attention(q, oc.np_f32_from_bf16(kc), oc.np_f32_from_bf16(vc), n_heads, n_kv, hd))
+    for p in (16, 32, 64):
+        out = eng.op_attn_decode(q, kc, vc, n_heads, n_kv, hd, page_size=p)
+        assert np.abs(out - ref).max() <= 2 ** -7 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("d,n_heads,n_kv,hd,pos", [(4096, 32, 8, 128, 777), (2048, 32, 4, 64, 0), (1024, 4, 2, 64, 33)])
+def test_qkv_rope_append_matches_oracle(variant, d, n_heads, n_kv, hd, pos):
+    """Fused RMSNorm + q|k|v GEMV + RoPE + bf16 round + KV append (the EPI_QKV epilogue)."""
+    rng = np.random.default_rng(d + pos)
+    theta = 5e5
+    qd, kvd = n_heads * hd, n_kv * hd
+    w = _rand_bf16(rng, (qd + 2 * kvd, d))
+    h = (rng.standard_normal(d) * 2).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+    q, k, v = eng.op_qkv_rope_append(w, h, g, 1e-5, n_heads, n_kv, hd, pos, theta, variant=variant)
+    xn = oc.rmsnorm(h, g, 1e-5, round_bf16=True)
+    y = oc.gemv(w, xn)
+    q_ref = oc.np_bf16_round(oc.rope(y[:qd], n_heads, hd, pos, theta))
+    k_ref = oc.np_bf16_round(oc.rope(y[qd:qd + kvd], n_kv, hd, pos, theta))
+    v_ref = oc.np_bf16_round(y[qd + kvd:])
+    tol = 2 ** -6 * max(1.0, float(np.abs(y).max()))     # bf16 rounding of slightly different fp32 sums
+    assert np.abs(q - q_ref).max() <= tol
+    assert np.abs(oc.np_f32_from_bf16(k) - k_ref).max() <= tol
+    assert np.abs(oc.np_f32_from_bf16(v) - v_ref).max() <= tol

@@ -43,10 +43,15 @@ def gemv_sweep(f):
 
 def decode_sweep(f, preset="llama3-8b", ctx=4096, steps=128):
     bytes_per_tok = None
-    for env in [dict(CL_GEMV_VARIANT="0", CL_PDL="0"), dict(CL_GEMV_VARIANT="0", CL_PDL="1"),
-                dict(CL_GEMV_VARIANT="1", CL_PDL="0"), dict(CL_GEMV_VARIANT="1", CL_PDL="1"),
-                dict(CL_GEMV_VARIANT="1", CL_PDL="1", CL_GRAPH="0")]:
-        for k in ("CL_GEMV_VARIANT", "CL_PDL", "CL_GRAPH"):
+    envs = [dict(CL_GEMV_VARIANT="1", CL_PDL="1"), dict(CL_GEMV_VARIANT="1", CL_PDL="0")]
+    if "full" in sys.argv:
+        envs += [dict(CL_GEMV_VARIANT="0", CL_PDL="0"), dict(CL_GEMV_VARIANT="0", CL_PDL="1"),
+                 dict(CL_GEMV_VARIANT="1", CL_PDL="1", CL_GRAPH="0")]
+    for spec in sys.argv:
+        if "=" in spec and spec.startswith("CL_"):
+            envs = [dict(kv.split("=") for kv in spec.split(","))] + envs[:1]
+    for env in envs:
+        for k in ("CL_GEMV_VARIANT", "CL_PDL", "CL_GRAPH", "CL_ATTN_NSPLIT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         try:
@@ -63,8 +68,9 @@ def decode_sweep(f, preset="llama3-8b", ctx=4096, steps=128):
                 t0 = time.time()
                 # fill the cache cheaply: the prompt goes through the (slow, exact) token-wise path only
                 # for a short prefix; the rest of the context is decode steps on device
-                lg = e.prefill(s, prompt[:8])
-                ids, ms_fill = e.decode_greedy(s, int(lg.argmax()), ctx - 8)
+                lg = e.prefill(s, prompt[:ctx - 64])          # tcgen05 prefill
+                t_prefill = time.time() - t0
+                ids, ms_fill = e.decode_greedy(s, int(lg.argmax()), 64)
                 t_fill = time.time() - t0
                 ids, ms = e.decode_greedy(s, int(ids[-1]), steps)
                 mean_ctx = ctx + steps / 2
@@ -73,7 +79,7 @@ def decode_sweep(f, preset="llama3-8b", ctx=4096, steps=128):
                 emit(f, bench="decode", preset=preset, ctx=ctx, steps=steps, env=env, ms_per_tok=round(ms / steps, 4),
                      tok_s=round(tps, 2), gbs=round(bytes_per_tok * tps / 1e9, 1),
                      frac=round(bytes_per_tok * tps / 1e9 / HBM, 4), init_s=round(t_init, 1), fill_s=round(t_fill, 1),
-                     fill_ms_per_tok=round(ms_fill / (ctx - 8), 4), launches=e.stats()["kernel_launches"])
+                     prefill_s=round(t_prefill, 3), fill_ms_per_tok=round(ms_fill / 64, 4), launches=e.stats()["kernel_launches"])
         except Exception as ex:  # noqa: BLE001
             emit(f, bench="decode", env=env, error=str(ex))
 
