@@ -362,7 +362,11 @@ static cudaError_t launch_ring(const GemvArgs& a, cudaStream_t st, bool pdl) {
   switch (a.K) {
     case 1024: return launch_ring_inst<EPI, NORM, 2, 4, 1, 6>(a, st, pdl);
     case 2048: return launch_ring_inst<EPI, NORM, 2, 4, 2, 6>(a, st, pdl);
-    case 4096: return launch_ring_inst<EPI, NORM, 2, 4, 4, 6>(a, st, pdl);
+    case 4096:
+      // q|k|v and o-proj share the SM with the attention kernel (128 KB KV ring) under PDL: 4 stages (64 KB)
+      // (4 stages measured 2.5 us slower per kernel than 6: 64 KB in flight per SM is below the
+      //  bandwidth-latency product; see profiles/README.md)
+      return launch_ring_inst<EPI, NORM, 2, 4, 4, 6>(a, st, pdl);
     case 8192: return launch_ring_inst<EPI, NORM, 1, 8, 4, 4>(a, st, pdl);
     case 14336: return launch_ring_inst<EPI, NORM, 1, 8, 7, 3>(a, st, pdl);
     default: return cudaErrorInvalidValue;
@@ -410,7 +414,7 @@ int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t
 //   q|k|v GEMV that precedes it; only the page holding the current token is fetched after the wait.
 //   The consumers' short latency-bound phase then overlaps the o-projection's weight prefetch.
 // ================================================================================================
-constexpr int kAttnRingBytes = 64 * 1024;
+constexpr int kAttnRingBytes = 64 * 1024;    // + 96 KB GEMV ring of the neighbouring kernel = co-resident under PDL
 constexpr int kAttnMaxStages = 8;
 
 template <int REP, int HD>
@@ -626,24 +630,35 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
     cL_s[tid] = L;
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
+  // warp w accumulates splits w, w+8, ... for all REP*HD outputs: every load is independent, so the
+  // whole partial set arrives in one L2 round trip; then an 8-way shared-memory reduction.
+  {
+    constexpr int OPL = REP * HD / 32;   // outputs per lane
+    float accw[OPL];
+#pragma unroll
+    for (int k = 0; k < OPL; ++k) accw[k] = 0.f;
+    for (int sidx = warp; sidx < ns; sidx += NW) {
+      const float* ps = pall + (size_t)sidx * REP * (HD + 2);
+#pragma unroll
+      for (int k = 0; k < OPL; ++k) {
+        const int o = lane + 32 * k, hh = o / HD, i = o % HD;
+        accw[k] = fmaf(__ldcg(ps + (size_t)hh * (HD + 2) + 2 + i), cw_s[sidx][hh], accw[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < OPL; ++k) {
+      const int o = lane + 32 * k;
+      red_acc[warp][o / HD][o % HD] = accw[k];
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   float* out = a.out + (size_t)slot * a.out_stride;
   for (int t = tid; t < REP * HD; t += NW * 32) {
     const int hh = t / HD, i = t % HD;
-    const float* pa = pall + (size_t)hh * (HD + 2) + 2 + i;
-    float A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
-    int sidx = 0;
-    for (; sidx + 4 <= ns; sidx += 4) {
-      const float v0 = __ldcg(pa + (size_t)(sidx + 0) * REP * (HD + 2));
-      const float v1 = __ldcg(pa + (size_t)(sidx + 1) * REP * (HD + 2));
-      const float v2 = __ldcg(pa + (size_t)(sidx + 2) * REP * (HD + 2));
-      const float v3 = __ldcg(pa + (size_t)(sidx + 3) * REP * (HD + 2));
-      A0 = fmaf(v0, cw_s[sidx + 0][hh], A0);
-      A1 = fmaf(v1, cw_s[sidx + 1][hh], A1);
-      A2 = fmaf(v2, cw_s[sidx + 2][hh], A2);
-      A3 = fmaf(v3, cw_s[sidx + 3][hh], A3);
-    }
-    for (; sidx < ns; ++sidx) A0 = fmaf(__ldcg(pa + (size_t)sidx * REP * (HD + 2)), cw_s[sidx][hh], A0);
-    out[(size_t)(g * REP + hh) * HD + i] = bf16_round(((A0 + A1) + (A2 + A3)) / cL_s[hh]);
+    float A = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) A += red_acc[w][hh][i];
+    out[(size_t)(g * REP + hh) * HD + i] = bf16_round(A / cL_s[hh]);
   }
 }
 
