@@ -241,6 +241,11 @@ int cl_decode_greedy_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs, c
   std::lock_guard<std::mutex> lk(e->impl.mu_);
   CL_GUARD(return e->impl.decode_greedy(seqs, n_seqs, first_ids, n_steps, ids_out, device_ms);)
 }
+int cl_debug_timeline(cl_engine* e, int64_t* out, int32_t n) {
+  if (!e || !out) return CL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(e->impl.mu_);
+  return e->impl.debug_timeline(reinterpret_cast<long long*>(out), n);
+}
 int cl_debug_hidden(cl_engine* e, float* out, int32_t n) {
   if (!e || !out) return CL_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(e->impl.mu_);

@@ -68,7 +68,7 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, int slot, int r
   } else if (EPI == EPI_RESID) {
     const float* r = a.resid + (size_t)slot * a.y_stride;
     float* y = a.y + (size_t)slot * a.y_stride;
-    float r0 = r[row0], r1 = r[row0 + 1];
+    float r0 = __ldcg(r + row0), r1 = __ldcg(r + row0 + 1);
     y[row0] = r0 + v0;
     y[row0 + 1] = r1 + v1;
   } else if (EPI == EPI_GATEUP) {  // v0 = gate_i, v1 = up_i
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256, 2) gemv_ldg_kernel(const GemvArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   if (a.pdl_early) pdl_launch_dependents();
-  pdl_wait();
+  if (a.sync.wait) wait_counter_warp(a.sync.wait, a.sync.n_wait); else pdl_wait();
   const int slot = a.slots ? a.slots[b] : b;
   const int K = a.K;
 
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256, 2) gemv_ldg_kernel(const GemvArgs a) {
     const float* h = a.h + (size_t)slot * a.x_stride;
     float ss = 0.f;
     for (int i = tid * 4; i < K; i += 256 * 4) {
-      float4 v = *reinterpret_cast<const float4*>(h + i);
+      float4 v = ldcg4(h + i);
       *reinterpret_cast<float4*>(xs + i) = v;
       ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
     }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) gemv_ldg_kernel(const GemvArgs a) {
   } else {
     const float* x = a.x + (size_t)slot * a.x_stride;
     for (int i = tid * 4; i < K; i += 256 * 4)
-      *reinterpret_cast<float4*>(xs + i) = *reinterpret_cast<const float4*>(x + i);
+      *reinterpret_cast<float4*>(xs + i) = ldcg4(x + i);
   }
   __syncthreads();
 
@@ -177,6 +177,10 @@ __global__ void __launch_bounds__(256, 2) gemv_ldg_kernel(const GemvArgs a) {
     acc1 = warp_sum(acc1);
     if (lane == 0) gemv_epilogue<EPI>(a, slot, 2 * p, acc0, acc1);
     if (!a.pdl_early && p == p1 - 2) pdl_launch_dependents();   // about to start the last row pair
+  }
+  if (a.sync.signal) {
+    __syncthreads();
+    if (tid == 0) signal_counter(a.sync.signal);
   }
 }
 
@@ -214,6 +218,8 @@ __global__ void __launch_bounds__(288, 1) gemv_ring_kernel(const GemvArgs a) {
   }
   __syncthreads();
   if (a.pdl_early) pdl_launch_dependents();
+  const bool stamp = a.tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+  if (stamp) a.tl[0] = gtime_ns();
 
   if (warp == 8) {
     // ---------------- producer: weights do not depend on the previous kernel -> no pdl_wait here
@@ -236,8 +242,43 @@ __global__ void __launch_bounds__(288, 1) gemv_ring_kernel(const GemvArgs a) {
     // ---------------- consumers
     const int r = warp / S, s = warp % S;
     const int kbase = s * (K / S);
-    pdl_wait();
+    if (a.sync.wait) wait_counter_warp(a.sync.wait, a.sync.n_wait); else pdl_wait();
+    if (stamp) a.tl[1] = gtime_ns();
     const int slot = a.slots ? a.slots[b] : b;
+    if (EPI == EPI_RESID && a.comb.part != nullptr) {
+      // ---- o-projection prologue: this CTA combines its slice of the attention outputs across the KV
+      // splits (softmax-weighted), publishes it, and waits until every CTA of this kernel has done so.
+      const AttnCombine& cb = a.comb;
+      const int HD = cb.head_dim, PS = HD + 2;
+      const int o0 = (int)(((long long)K * blockIdx.x) / gridDim.x), o1 = (int)(((long long)K * (blockIdx.x + 1)) / gridDim.x);
+      const float* pbase = cb.part + (size_t)slot * cb.n_kv * cb.nsplit * cb.rep * PS;
+      float* xo = cb.x_out + (size_t)slot * a.x_stride;
+      constexpr int MAXR = 8;   // rounds of 8 outputs (one per warp): covers K / gridDim.x <= 64
+      float mv[MAXR], lv[MAXR], av[MAXR];
+#pragma unroll
+      for (int q = 0; q < MAXR; ++q) {
+        const int o = o0 + q * 8 + warp;
+        mv[q] = -INFINITY; lv[q] = 0.f; av[q] = 0.f;
+        if (o < o1 && lane < cb.nsplit) {
+          const int hg = o / HD, i = o - hg * HD;
+          const float* p = pbase + (((size_t)(hg / cb.rep) * cb.nsplit + lane) * cb.rep + (hg % cb.rep)) * PS;
+          mv[q] = __ldcg(p); lv[q] = __ldcg(p + 1); av[q] = __ldcg(p + 2 + i);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < MAXR; ++q) {
+        const int o = o0 + q * 8 + warp;
+        if (o < o1) {   // warp-uniform
+          const float M = warp_max(mv[q]);
+          const float w = (mv[q] == -INFINITY) ? 0.f : exp2f(mv[q] - M);
+          const float L = warp_sum(lv[q] * w), A = warp_sum(av[q] * w);
+          if (lane == 0) xo[o] = bf16_round(A / L);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) signal_counter(cb.phase + b);          // one barrier per batch entry
+      wait_counter_warp(cb.phase + b, gridDim.x);
+    }
     float xr[CPL][8];
     if (NORM) {
       const float* h = a.h + (size_t)slot * a.x_stride;
@@ -245,8 +286,8 @@ __global__ void __launch_bounds__(288, 1) gemv_ring_kernel(const GemvArgs a) {
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
         const int k = kbase + (c * 32 + lane) * 8;
-        float4 v0 = *reinterpret_cast<const float4*>(h + k);
-        float4 v1 = *reinterpret_cast<const float4*>(h + k + 4);
+        float4 v0 = ldcg4(h + k);
+        float4 v1 = ldcg4(h + k + 4);
         xr[c][0] = v0.x; xr[c][1] = v0.y; xr[c][2] = v0.z; xr[c][3] = v0.w;
         xr[c][4] = v1.x; xr[c][5] = v1.y; xr[c][6] = v1.z; xr[c][7] = v1.w;
 #pragma unroll
@@ -270,17 +311,18 @@ __global__ void __launch_bounds__(288, 1) gemv_ring_kernel(const GemvArgs a) {
         xr[c][6] = bf16_round(xr[c][6] * inv * g1.z); xr[c][7] = bf16_round(xr[c][7] * inv * g1.w);
       }
     } else {
-      const float* x = a.x + (size_t)slot * a.x_stride;
+      const float* x = ((EPI == EPI_RESID && a.comb.part != nullptr) ? a.comb.x_out : a.x) + (size_t)slot * a.x_stride;
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
         const int k = kbase + (c * 32 + lane) * 8;
-        float4 v0 = *reinterpret_cast<const float4*>(x + k);
-        float4 v1 = *reinterpret_cast<const float4*>(x + k + 4);
+        float4 v0 = ldcg4(x + k);
+        float4 v1 = ldcg4(x + k + 4);
         xr[c][0] = v0.x; xr[c][1] = v0.y; xr[c][2] = v0.z; xr[c][3] = v0.w;
         xr[c][4] = v1.x; xr[c][5] = v1.y; xr[c][6] = v1.z; xr[c][7] = v1.w;
       }
     }
 
+    if (stamp) a.tl[2] = gtime_ns();   // x in registers: start consuming
     const uint32_t row_off = (uint32_t)(r * K + kbase + lane * 8) * 2u;
     for (int it = 0; it < ntiles; ++it) {
       const int st = it % NST;
@@ -313,6 +355,11 @@ __global__ void __launch_bounds__(288, 1) gemv_ring_kernel(const GemvArgs a) {
       for (int i = 0; i < S; ++i) { v0 += part[(2 * p) * S + i]; v1 += part[(2 * p + 1) * S + i]; }
       gemv_epilogue<EPI>(a, slot, row_base + 2 * p, v0, v1);
     }
+    if (a.sync.signal) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) signal_counter(a.sync.signal);
+    }
+    if (stamp) a.tl[3] = gtime_ns();
   }
 }
 
@@ -337,6 +384,7 @@ bool gemv_variant_supported(int variant, int N, int K) {
   return true;
 }
 
+static int g_last_gemv_ctas = 0;
 template <int EPI, bool NORM, int TR, int S, int CPL, int NST>
 static cudaError_t launch_ring_inst(const GemvArgs& a, cudaStream_t st, bool pdl) {
   constexpr int K = S * CPL * 256;
@@ -354,6 +402,8 @@ static cudaError_t launch_ring_inst(const GemvArgs& a, cudaStream_t st, bool pdl
     attr_set = true;
   }
   if (smem > 160 * 1024) return cudaErrorInvalidValue;
+  if (a.comb.part && (a.comb.nsplit > 32 || (a.K + G - 1) / G > 64)) return cudaErrorInvalidValue;
+  g_last_gemv_ctas = G * a.batch;
   return launch_ex(kern, dim3(G, a.batch), dim3(288), smem, st, pdl, a);
 }
 
@@ -386,10 +436,12 @@ static cudaError_t launch_ldg(const GemvArgs& a, cudaStream_t st, bool pdl) {
   int G = sm_count() * 2;
   int npairs = a.N / 2;
   if (G * 8 > npairs) G = (npairs + 7) / 8;
+  if (a.comb.part) return cudaErrorInvalidValue;   // the distributed combine lives in the ring kernel only
+  g_last_gemv_ctas = G * a.batch;
   return launch_ex(kern, dim3(G, a.batch), dim3(256), smem, st, pdl, a);
 }
 
-int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t st, bool pdl) {
+int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t st, bool pdl, int* n_ctas) {
   if (variant == 1 && !gemv_variant_supported(1, a.N, a.K)) variant = 0;
   // with TR==1 configs row-pair ownership needs even tile splits; handled in launch_ring_inst
   cudaError_t e = cudaErrorInvalidValue;
@@ -400,6 +452,7 @@ int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t
   else e = norm ? FN<EPI_QKV, true>(a, st, pdl) : FN<EPI_QKV, false>(a, st, pdl);
   if (variant == 1) { CL_DISPATCH(launch_ring) } else { CL_DISPATCH(launch_ldg) }
 #undef CL_DISPATCH
+  if (n_ctas) *n_ctas = g_last_gemv_ctas;
   return e == cudaSuccess ? 1 : -1;
 }
 
@@ -414,7 +467,8 @@ int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t
 //   q|k|v GEMV that precedes it; only the page holding the current token is fetched after the wait.
 //   The consumers' short latency-bound phase then overlaps the o-projection's weight prefetch.
 // ================================================================================================
-constexpr int kAttnRingBytes = 64 * 1024;    // + 96 KB GEMV ring of the neighbouring kernel = co-resident under PDL
+static int g_attn_ring_bytes = 64 * 1024;    // + 96 KB GEMV ring of the neighbouring kernel = co-resident under PDL (env CL_ATTN_RING_KB)
+constexpr int kAttnRingBytesMax = 128 * 1024;
 constexpr int kAttnMaxStages = 8;
 
 template <int REP, int HD>
@@ -437,7 +491,7 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
   const int P = a.page_size;
   const uint32_t half_bytes = (uint32_t)P * HD * 2;       // K (or V) block of one (page, kv head)
   const uint32_t slot_bytes = 2 * half_bytes;
-  int nstg = kAttnRingBytes / (int)slot_bytes;
+  int nstg = a.ring_bytes / (int)slot_bytes;
   nstg = nstg > kAttnMaxStages ? kAttnMaxStages : nstg;
 
   if (tid == 0) {
@@ -446,6 +500,8 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
   }
   __syncthreads();
   if (a.pdl_early) pdl_launch_dependents();
+  const bool stamp = a.tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+  if (stamp) a.tl[0] = gtime_ns();
 
   const int slot = a.slots ? a.slots[b] : b;
   const int pos = a.pos[slot];                 // stable for the whole step (written by the previous step's tail)
@@ -466,7 +522,14 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
         const int st = it % nstg;
         const uint32_t par = (uint32_t)(it / nstg) & 1u;
         mbar_wait(&empty[st], par ^ 1u);
-        if (pg0 + it == cur_page) pdl_wait();
+        if (pg0 + it == cur_page) {
+          if (a.sync.wait) {   // single thread: poll directly
+            const long long t0 = clock64();
+            while (ld_acquire_u32(a.sync.wait) < a.sync.n_wait) { __nanosleep(40); if (clock64() - t0 > (1ll << 31)) __trap(); }
+          } else {
+            pdl_wait();
+          }
+        }
         const int page = bt[pg0 + it];
         const size_t src = ((size_t)page * a.n_kv + g) * P * HD;
         uint8_t* dst = ring + (size_t)st * slot_bytes;
@@ -479,7 +542,8 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
   }
 
   // ---------------- consumers (warps 0..7)
-  pdl_wait();
+  if (a.sync.wait) wait_counter_warp(a.sync.wait, a.sync.n_wait); else pdl_wait();
+  if (stamp) a.tl[1] = gtime_ns();
   const int sub = lane / LPT, j = lane % LPT;
   const float scale2 = rsqrtf((float)HD) * LOG2E;
   float qr[REP][8];
@@ -487,8 +551,8 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
     const float* q = a.q + (size_t)slot * a.q_stride + (size_t)g * REP * HD + j * 8;
 #pragma unroll
     for (int hh = 0; hh < REP; ++hh) {
-      const float4 q0 = *reinterpret_cast<const float4*>(q + hh * HD);
-      const float4 q1 = *reinterpret_cast<const float4*>(q + hh * HD + 4);
+      const float4 q0 = ldcg4(q + hh * HD);
+      const float4 q1 = ldcg4(q + hh * HD + 4);
       qr[hh][0] = q0.x; qr[hh][1] = q0.y; qr[hh][2] = q0.z; qr[hh][3] = q0.w;
       qr[hh][4] = q1.x; qr[hh][5] = q1.y; qr[hh][6] = q1.z; qr[hh][7] = q1.w;
     }
@@ -547,6 +611,7 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
     if (lane == 0) mbar_arrive(&empty[st]);
   }
 
+  if (stamp) a.tl[2] = gtime_ns();   // all pages consumed
   // ---- merge the TPW token groups of a warp
 #pragma unroll
   for (int o = LPT; o < 32; o <<= 1) {
@@ -593,6 +658,12 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
     float* ph = part + (size_t)hh * (HD + 2);
     if (i == 0) { ph[0] = M; ph[1] = L; }
     ph[2 + i] = A;
+  }
+  if (stamp) a.tl[3] = gtime_ns();   // partial written (CTA 0 is rarely the combining CTA)
+  if (a.sync.signal) {   // deferred combine: the o-projection's prologue merges the splits
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid == 0) signal_counter(a.sync.signal);
+    return;
   }
   __threadfence();
   asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -665,12 +736,16 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
 int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   const int rep = a.n_heads / a.n_kv;
   dim3 grid(a.n_kv, a.nsplit, a.batch), block(288);
-  if (a.nsplit > 64 || 2 * a.page_size * a.head_dim * 2 * 2 > kAttnRingBytes) return -1;
-  const size_t smem = kAttnRingBytes;
+  static bool env_read = false;
+  if (!env_read) { const char* v = getenv("CL_ATTN_RING_KB"); if (v && atoi(v) >= 16 && atoi(v) <= 128) g_attn_ring_bytes = atoi(v) * 1024; env_read = true; }
+  if (a.nsplit > 64 || 2 * a.page_size * a.head_dim * 2 * 2 > g_attn_ring_bytes) return -1;
+  const size_t smem = g_attn_ring_bytes;
+  AttnDecodeArgs a2 = a;
+  a2.ring_bytes = g_attn_ring_bytes;
   cudaError_t e = cudaErrorInvalidValue;
 #define CL_ATT(R, D) do { static bool once = false; if (!once) { prefer_max_smem(attn_decode_kernel<R, D>);                 \
-      cudaFuncSetAttribute(attn_decode_kernel<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnRingBytes); once = true; } \
-    e = launch_ex(attn_decode_kernel<R, D>, grid, block, smem, st, pdl, a); } while (0)
+      cudaFuncSetAttribute(attn_decode_kernel<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnRingBytesMax); once = true; } \
+    e = launch_ex(attn_decode_kernel<R, D>, grid, block, smem, st, pdl, a2); } while (0)
   if (a.head_dim == 128) {
     if (rep == 1) CL_ATT(1, 128); else if (rep == 2) CL_ATT(2, 128); else if (rep == 4) CL_ATT(4, 128);
     else if (rep == 8) CL_ATT(8, 128);
@@ -772,10 +847,18 @@ __global__ void __launch_bounds__(256) step_tail_kernel(const StepTailArgs a) {
 }
 
 // step counter bump: tiny kernel keeps the protocol obviously correct (1 thread).
-__global__ void step_bump_kernel(int* step_counter) {
+__global__ void step_bump_kernel(int* step_counter, unsigned* sync_counters, int n_sync) {
   pdl_launch_dependents();
   pdl_wait();
-  *step_counter += 1;
+  if (threadIdx.x == 0) *step_counter += 1;
+  for (int i = threadIdx.x; i < n_sync; i += blockDim.x) sync_counters[i] = 0u;   // re-arm the StepSync counters
+}
+__global__ void zero_u32_kernel(unsigned* p, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0u;
+}
+int launch_zero_u32(unsigned* p, int n, cudaStream_t st) {
+  zero_u32_kernel<<<1, 256, 0, st>>>(p, n);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_step_tail(const StepTailArgs& a, cudaStream_t st) {
@@ -783,7 +866,7 @@ int launch_step_tail(const StepTailArgs& a, cudaStream_t st) {
   if (!once) { prefer_max_smem(step_tail_kernel); prefer_max_smem(step_bump_kernel); once = true; }
   step_tail_kernel<<<dim3(kTailBlocks, a.batch), 256, 0, st>>>(a);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  step_bump_kernel<<<1, 1, 0, st>>>(a.step_counter);
+  step_bump_kernel<<<1, 256, 0, st>>>(a.step_counter, a.sync_counters, a.n_sync_counters);
   return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 

@@ -91,6 +91,10 @@ int Engine::init(const cl_engine_config& c) {
   use_pdl_ = env_int("CL_PDL", 1) != 0;
   pdl_early_ = env_int("CL_PDL_EARLY", 1);
   skip_attn_ = env_int("CL_SKIP_ATTN", 0) != 0;   // timing experiments only (wrong results)
+  use_flags_ = env_int("CL_FLAGS", 0) != 0;      // measured slower than griddepcontrol.wait (profiles/README.md)
+  want_timeline_ = env_int("CL_TIMELINE", 0) != 0;
+  use_mega_ = env_int("CL_MEGA", 1) != 0 &&
+              mega_supported(cfg.d_model, cfg.d_ff, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads, page_size_, nsplit_);
   gemv_variant_ = c.decode_path == 1 ? 0 : 1;
   gemv_variant_ = env_int("CL_GEMV_VARIANT", gemv_variant_);
   q_dim_ = cfg.n_heads * cfg.head_dim;
@@ -119,6 +123,22 @@ int Engine::init(const cl_engine_config& c) {
   if (rc) return rc;
   rc = alloc_state();
   if (rc) return rc;
+  if (use_mega_) {
+    const uint64_t rows = (uint64_t)cfg.n_layers * n_pages_ * cfg.n_kv_heads * page_size_;
+    if (rows >= (1ull << 31) || !make_tmap_2d_bf16(&kmap_, kpool_, rows, cfg.head_dim, 64, 32) ||
+        !make_tmap_2d_bf16(&vmap_, vpool_, rows, cfg.head_dim, 64, 32)) {
+      fprintf(stderr, "[clengine] KV tensor maps unavailable: using the per-op decode path\n");
+      use_mega_ = false;
+    }
+  }
+  if (use_mega_) {
+    std::vector<MegaLayer> ml(cfg.n_layers);
+    for (int l = 0; l < cfg.n_layers; ++l)
+      ml[l] = MegaLayer{layers_[l].wqkv, layers_[l].wo, layers_[l].wgu, layers_[l].wdown, layers_[l].attn_norm, layers_[l].ffn_norm,
+                        kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_};
+    DMALLOC(d_mega_layers_, ml.size() * sizeof(MegaLayer));
+    CL_CUDA_OK(cudaMemcpy(d_mega_layers_, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+  }
   pool_.reset(new KvPool(n_pages_, page_size_));
   seqs_.assign(max_seqs_, SeqState());
   tok.reset(new Tokenizer(cfg.vocab_size));
@@ -260,6 +280,13 @@ int Engine::alloc_state() {
   DMALLOC(d_tail_cnt_, S * 4);
   DMALLOC(d_ids_ring_, (size_t)ring_steps_ * max_batch_ * 4);
   DMALLOC(d_step_counter_, 4);
+  n_sync_ = std::max(cfg.n_layers * 5 + 1 + cfg.n_layers * max_batch_, cfg.n_layers * 10);   // megakernel: 6 barriers + 4 tile counters per layer
+  DMALLOC(d_sync_, (size_t)n_sync_ * 4);
+  CL_CUDA_OK(cudaMemsetAsync(d_sync_, 0, (size_t)n_sync_ * 4, stream_));
+  if (want_timeline_) {
+    DMALLOC(d_timeline_, (size_t)(cfg.n_layers * 5 + 1) * 4 * 8);   // >= n_layers * 16 stamps for the megakernel view
+    CL_CUDA_OK(cudaMemsetAsync(d_timeline_, 0, (size_t)(cfg.n_layers * 5 + 1) * 4 * 8, stream_));
+  }
   prompt_cap_ = cfg.max_seq_len;
   DMALLOC(d_prompt_, (size_t)prompt_cap_ * 4);
   CL_CUDA_OK(cudaMemsetAsync(d_tok_, 0, S * 4, stream_));
@@ -307,11 +334,30 @@ int Engine::ensure_capacity(cl_seq_t s, int n_tokens) {
 
 // ---- one token step for the sequences listed in d_slots_[0..B) -----------------------------------
 int Engine::enqueue_step(int B, bool tail) {
-  const int d = cfg.d_model, F = cfg.d_ff;
+  const int d = cfg.d_model, F = cfg.d_ff, L_ = cfg.n_layers;
   int n = 0, r;
 #define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; } while (0)
+  // StepSync: counter-based dependencies inside the step (kernels.h).  Only with PDL (the consumers must
+  // already be resident to profit) and never for the first kernel after embed / the tail (stream order).
+  const bool flags = use_flags_ && use_pdl_;
+  const bool defer_combine = flags && gemv_variant_ == 1 && gemv_variant_supported(1, d, q_dim_) && nsplit_ <= 32 &&
+                             (q_dim_ + sm_count() - 1) / sm_count() <= 64;
+  auto cnt = [&](int l, int k) -> unsigned* { return flags ? d_sync_ + (size_t)l * 5 + k : nullptr; };
+  auto tl = [&](int l, int k) -> long long* { return d_timeline_ ? d_timeline_ + ((size_t)l * 5 + k) * 4 : nullptr; };
+  const unsigned* prev_cnt = nullptr;
+  int prev_n = 0, nc = 0;
   CL_LAUNCH(launch_embed(embed_, d, d_tok_, d_h_, d, d_slots_, B, stream_));
-  for (int l = 0; l < cfg.n_layers; ++l) {
+  const bool mega = use_mega_ && B == 1 && !skip_attn_ && d_mega_layers_ != nullptr;
+  if (mega) {
+    MegaArgs m;
+    m.layers = d_mega_layers_; m.n_layers = L_; m.q_dim = q_dim_; m.qkv_dim = qkv_dim_; m.n_heads = cfg.n_heads; m.n_kv = cfg.n_kv_heads;
+    m.nsplit = nsplit_; m.eps = cfg.rms_eps; m.rope = rope_; m.pos = d_pos_; m.block_tables = d_bt_; m.bt_stride = max_pages_per_seq_;
+    m.slots = d_slots_; m.h = d_h_; m.q = d_q_; m.attn_x = d_attn_; m.act = d_act_; m.part = d_attn_part_; m.bars = d_sync_; m.tile_ctr = d_sync_ + (size_t)L_ * 6;
+    m.tl = d_timeline_; m.tl_cta = env_int("CL_TIMELINE_CTA", 0);
+    m.kv_layer_rows = (long long)n_pages_ * cfg.n_kv_heads * page_size_; m.kmap = kmap_; m.vmap = vmap_;
+    CL_LAUNCH(launch_decode_mega(m, stream_));
+  }
+  for (int l = 0; l < (mega ? 0 : L_); ++l) {
     const auto& L = layers_[l];
     GemvArgs g;
     g.slots = d_slots_; g.batch = B; g.pdl_early = pdl_early_;
@@ -321,7 +367,9 @@ int Engine::enqueue_step(int B, bool tail) {
     g.qkv.rope = rope_; g.qkv.pos = d_pos_; g.qkv.block_tables = d_bt_; g.qkv.bt_stride = max_pages_per_seq_;
     g.qkv.kpool = kpool_ + (size_t)l * kv_layer_elems_; g.qkv.vpool = vpool_ + (size_t)l * kv_layer_elems_;
     g.qkv.n_heads = cfg.n_heads; g.qkv.n_kv = cfg.n_kv_heads; g.qkv.head_dim = cfg.head_dim; g.qkv.page_size = page_size_;
-    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_QKV, true, g, stream_, use_pdl_));
+    g.sync.wait = prev_cnt; g.sync.n_wait = (unsigned)prev_n; g.sync.signal = cnt(l, 0); g.tl = tl(l, 0);
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_QKV, true, g, stream_, use_pdl_, &nc));
+    prev_cnt = cnt(l, 0); prev_n = nc;
     // (2) paged GQA attention over tokens 0..pos
     AttnDecodeArgs a;
     a.q = d_q_; a.q_stride = q_dim_;
@@ -330,34 +378,52 @@ int Engine::enqueue_step(int B, bool tail) {
     a.out = d_attn_; a.out_stride = q_dim_; a.part = d_attn_part_; a.counters = d_attn_cnt_;
     a.slots = d_slots_; a.batch = B; a.n_heads = cfg.n_heads; a.n_kv = cfg.n_kv_heads; a.head_dim = cfg.head_dim;
     a.page_size = page_size_; a.nsplit = nsplit_; a.pdl_early = pdl_early_;
+    a.sync.wait = prev_cnt; a.sync.n_wait = (unsigned)prev_n;
+    a.sync.signal = defer_combine ? cnt(l, 1) : nullptr; a.tl = tl(l, 1);
     if (!skip_attn_) CL_LAUNCH(launch_attn_decode(a, stream_, use_pdl_));
-    // (3) o projection + residual
+    // (3) o projection + residual (prologue: cross-split combine of the attention partials when deferred)
     GemvArgs o;
     o.slots = d_slots_; o.batch = B; o.pdl_early = pdl_early_;
     o.W = L.wo; o.N = d; o.K = q_dim_; o.x = d_attn_; o.x_stride = q_dim_; o.y = d_h_; o.resid = d_h_; o.y_stride = d;
-    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, o, stream_, use_pdl_));
+    if (defer_combine && !skip_attn_) {
+      o.sync.wait = cnt(l, 1); o.sync.n_wait = (unsigned)(cfg.n_kv_heads * nsplit_ * B);
+      o.comb.part = d_attn_part_; o.comb.nsplit = nsplit_; o.comb.n_kv = cfg.n_kv_heads; o.comb.rep = cfg.n_heads / cfg.n_kv_heads;
+      o.comb.head_dim = cfg.head_dim; o.comb.x_out = d_attn_; o.comb.phase = d_sync_ + (size_t)L_ * 5 + 1 + (size_t)l * max_batch_;
+    } else {
+      // the attention kernel combined in-kernel and publishes nothing: fall back to grid completion
+      o.sync.wait = nullptr;
+    }
+    o.sync.signal = cnt(l, 2); o.tl = tl(l, 2);
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, o, stream_, use_pdl_, &nc));
+    prev_cnt = cnt(l, 2); prev_n = nc;
     // (4) RMSNorm + gate/up + SiLU*mul
     GemvArgs u;
     u.slots = d_slots_; u.batch = B; u.pdl_early = pdl_early_;
     u.W = L.wgu; u.N = 2 * F; u.K = d; u.h = d_h_; u.gain = L.ffn_norm; u.eps = cfg.rms_eps; u.y = d_act_;
     u.x_stride = d; u.y_stride = F;
-    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_GATEUP, true, u, stream_, use_pdl_));
+    u.sync.wait = prev_cnt; u.sync.n_wait = (unsigned)prev_n; u.sync.signal = cnt(l, 3); u.tl = tl(l, 3);
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_GATEUP, true, u, stream_, use_pdl_, &nc));
+    prev_cnt = cnt(l, 3); prev_n = nc;
     // (5) down projection + residual
     GemvArgs w;
     w.slots = d_slots_; w.batch = B; w.pdl_early = pdl_early_;
     w.W = L.wdown; w.N = d; w.K = F; w.x = d_act_; w.x_stride = F; w.y = d_h_; w.resid = d_h_; w.y_stride = d;
-    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, w, stream_, use_pdl_));
+    w.sync.wait = prev_cnt; w.sync.n_wait = (unsigned)prev_n; w.sync.signal = cnt(l, 4); w.tl = tl(l, 4);
+    CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, w, stream_, use_pdl_, &nc));
+    prev_cnt = cnt(l, 4); prev_n = nc;
   }
   GemvArgs lm;
   lm.slots = d_slots_; lm.batch = B; lm.pdl_early = pdl_early_;
   lm.W = lm_head_; lm.N = cfg.vocab_size; lm.K = d; lm.h = d_h_; lm.gain = final_norm_; lm.eps = cfg.rms_eps;
   lm.y = d_logits_; lm.x_stride = d; lm.y_stride = cfg.vocab_size;
-  CL_LAUNCH(launch_gemv(gemv_variant_, EPI_STORE, true, lm, stream_, use_pdl_));
+  lm.sync.wait = prev_cnt; lm.sync.n_wait = (unsigned)prev_n; lm.tl = tl(L_, 0);
+  CL_LAUNCH(launch_gemv(gemv_variant_, EPI_STORE, true, lm, stream_, use_pdl_ && !mega));
   if (tail) {
     StepTailArgs t;
     t.logits = d_logits_; t.vocab = cfg.vocab_size; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
     t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
     t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = B;
+    t.sync_counters = d_sync_; t.n_sync_counters = n_sync_;
     CL_LAUNCH(launch_step_tail(t, stream_));
   }
 #undef CL_LAUNCH
@@ -527,6 +593,14 @@ int Engine::decode_greedy(const cl_seq_t* ss, int B, const int32_t* first_ids, i
   }
   if (device_ms) *device_ms = total_ms;
   return CL_OK;
+}
+
+int Engine::debug_timeline(long long* out, int n) {
+  const int want = (cfg.n_layers * 5 + 1) * 4;
+  if (!d_timeline_ || n < want) return CL_ERR_INVALID_ARG;
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  CL_CUDA_OK(cudaMemcpy(out, d_timeline_, (size_t)want * 8, cudaMemcpyDeviceToHost));
+  return want;
 }
 
 int Engine::debug_hidden(float* out, int n) {

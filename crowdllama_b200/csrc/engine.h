@@ -113,6 +113,7 @@ class Engine {
                     float* device_ms);
   int set_tensor(int layer, int kind, const uint16_t* data, int64_t n);
   int debug_hidden(float* out, int n);
+  int debug_timeline(long long* out, int n);   // CL_TIMELINE=1: globaltimer stamps of the last step (CTA 0 of every node)
   int stats(cl_stats* out);
 
   // request-level (scheduler.cpp)
@@ -146,6 +147,12 @@ class Engine {
   int gemv_variant_ = 1, nsplit_ = 16;
   bool use_graph_ = true, use_pdl_ = true, skip_attn_ = false;
   int pdl_early_ = 1;
+  bool use_flags_ = false, want_timeline_ = false, use_mega_ = false;
+  MegaLayer* d_mega_layers_ = nullptr;
+  CUtensorMap kmap_{}, vmap_{};
+  long long* d_timeline_ = nullptr;
+  unsigned* d_sync_ = nullptr;
+  int n_sync_ = 0;
   int qkv_dim_ = 0, q_dim_ = 0, kv_dim_ = 0;
 
   // weights

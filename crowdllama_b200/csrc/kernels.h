@@ -1,10 +1,26 @@
 // kernels.h — host-side launch interface of the sm_100a kernels (internal to libclengine.so).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace cl {
+
+// Dependencies inside the token step (common.cuh: wait_counter_warp / signal_counter).
+struct StepSync {
+  const unsigned* wait = nullptr;   // producer node's counter (nullptr => griddepcontrol.wait)
+  unsigned n_wait = 0;              // CTAs of the producer node
+  unsigned* signal = nullptr;       // this node's counter (nullptr => none)
+};
+// o-projection prologue: the cross-split softmax combine of the attention partials, distributed over the
+// o-projection's CTAs (each combines a slice of the H*D outputs), then a grid-wide counter barrier.
+struct AttnCombine {
+  const float* part = nullptr;      // [slot][n_kv][nsplit][rep][head_dim + 2]  (nullptr => x is read as is)
+  int nsplit = 0, n_kv = 0, rep = 0, head_dim = 0;
+  float* x_out = nullptr;           // [slot][x_stride] combined, bf16-rounded attention output
+  unsigned* phase = nullptr;        // counter: CTAs of THIS kernel that have written their slice
+};
 
 enum GemvEpi { EPI_STORE = 0, EPI_RESID = 1, EPI_GATEUP = 2, EPI_QKV = 3 };
 
@@ -38,6 +54,9 @@ struct GemvArgs {
   int batch = 1;
   int pdl_early = 1;                 // 1: trigger dependents at kernel start; 0: when this CTA has issued its last load
   QkvEpi qkv;                        // EPI_QKV only
+  StepSync sync;
+  AttnCombine comb;                  // EPI_RESID o-projection only
+  long long* tl = nullptr;           // debug timeline (CL_TIMELINE=1): 4 globaltimer stamps written by CTA 0
 };
 
 struct AttnDecodeArgs {
@@ -56,6 +75,9 @@ struct AttnDecodeArgs {
   int batch = 1;
   int n_heads = 0, n_kv = 0, head_dim = 0, page_size = 0, nsplit = 0;
   int pdl_early = 1;
+  StepSync sync;                     // sync.signal != nullptr: publish partials only, the consumer combines
+  long long* tl = nullptr;
+  int ring_bytes = 0;                // filled by the launcher
 };
 
 struct StepTailArgs {                // argmax over logits, advance the sequence
@@ -65,6 +87,8 @@ struct StepTailArgs {                // argmax over logits, advance the sequence
   int* pos = nullptr;                // [slot] incremented
   int* ids_ring = nullptr;           // [ring_steps][max_batch] generated ids
   int* step_counter = nullptr;       // device scalar, incremented once per step
+  unsigned* sync_counters = nullptr; // zeroed at the end of every step (StepSync)
+  int n_sync_counters = 0;
   int ring_steps = 0, ring_stride = 0;
   float* part_val = nullptr;         // [slot][nblk]
   int* part_idx = nullptr;
@@ -74,17 +98,51 @@ struct StepTailArgs {                // argmax over logits, advance the sequence
 };
 
 // every launcher returns the number of kernels it enqueued (for cl_stats.kernel_launches)
-int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t st, bool pdl);
+int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t st, bool pdl, int* n_ctas = nullptr);
 int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 int launch_embed(const __nv_bfloat16* table, int d, const int* tok, float* h, int h_stride, const int* slots,
                  int batch, cudaStream_t st);
 int launch_step_tail(const StepTailArgs& a, cudaStream_t st);
+// zero the step counters (run once at init; the per-step reset is part of step_bump_kernel)
+int launch_zero_u32(unsigned* p, int n, cudaStream_t st);
 // rope_hd > 0: rows are written rope-pair-interleaved per head of rope_hd rows (see QkvEpi)
 int launch_synth_bf16(__nv_bfloat16* out, int64_t n_logical, int k_cols, int row_mult, int row_off, uint64_t seed,
                       int key, float scale, cudaStream_t st, int rope_hd = 0);
 int launch_synth_gain(float* out, int n, uint64_t seed, int key, float scale, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, int64_t n, cudaStream_t st);
 int launch_fill_u16(uint16_t* p, int64_t n, uint16_t v, cudaStream_t st);
+
+// ---- persistent whole-stack decode kernel (decode_mega.cu) ----------------------------------------
+struct MegaLayer {
+  const __nv_bfloat16* wqkv; const __nv_bfloat16* wo; const __nv_bfloat16* wgu; const __nv_bfloat16* wdown;
+  const float* attn_norm; const float* ffn_norm;
+  __nv_bfloat16* kpool; __nv_bfloat16* vpool;
+};
+struct MegaArgs {
+  const MegaLayer* layers = nullptr;   // device array [n_layers]
+  int n_layers = 0, q_dim = 0, qkv_dim = 0, n_heads = 0, n_kv = 0, nsplit = 0;
+  float eps = 0.f;
+  const float2* rope = nullptr;
+  const int* pos = nullptr;
+  const int* block_tables = nullptr;
+  int bt_stride = 0;
+  const int* slots = nullptr;          // slots[0] is the sequence slot
+  float* h = nullptr;                  // [slot][d] residual stream (in: embedding, out: final hidden)
+  float* q = nullptr;                  // [slot][q_dim]
+  float* attn_x = nullptr;             // [slot][q_dim]
+  float* act = nullptr;                // [slot][d_ff]
+  float* part = nullptr;               // attention partials
+  unsigned* bars = nullptr;            // [n_layers * 6] grid-barrier counters, zero at kernel start
+  unsigned* tile_ctr = nullptr;        // [n_layers * 4] dynamic tile-scheduler counters, zero at kernel start
+  long long* tl = nullptr;             // debug: [n_layers][16] globaltimer stamps of CTA tl_cta
+  int tl_cta = 0;
+  long long kv_layer_rows = 0;         // rows of one layer in the KV tensor maps (= n_pages * n_kv * page)
+  alignas(64) CUtensorMap kmap;        // whole K pool as [L * n_pages * n_kv * page][head_dim], box {64, 32}, 128B swizzle
+  alignas(64) CUtensorMap vmap;
+};
+bool make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows);
+bool mega_supported(int d, int d_ff, int head_dim, int n_heads, int n_kv, int page_size, int nsplit);
+int launch_decode_mega(const MegaArgs& a, cudaStream_t st);
 
 bool gemv_variant_supported(int variant, int N, int K);
 int sm_count();

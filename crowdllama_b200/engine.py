@@ -65,7 +65,7 @@ EXPORTS = [
     "cl_greedy_sampling", "cl_model_preset", "cl_engine_create", "cl_engine_destroy", "cl_engine_model_config",
     "cl_engine_stats", "cl_engine_set_tensor", "cl_generate", "cl_generate_ids", "cl_result_free",
     "cl_handle_message", "cl_buffer_free", "cl_tokenize", "cl_detokenize", "cl_seq_create", "cl_seq_free",
-    "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_debug_hidden",
+    "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_debug_hidden", "cl_debug_timeline",
     "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_qkv_rope_append", "cl_op_attn_decode",
     "cl_op_gemm_bf16", "cl_op_attn_prefill", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
     "cl_kvpool_reserve", "cl_kvpool_release", "cl_kvpool_pages_of", "cl_kvpool_free_pages", "cl_kvpool_used_pages",
@@ -112,6 +112,7 @@ def lib():
         "cl_decode_greedy": (C.c_int, [vp, i32, i32, i32, vp, P(f32)]),
         "cl_decode_greedy_batch": (C.c_int, [vp, vp, i32, vp, i32, vp, P(f32)]),
         "cl_debug_hidden": (C.c_int, [vp, vp, i32]),
+        "cl_debug_timeline": (C.c_int, [vp, vp, i32]),
         "cl_op_gemv": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, i32, i32, i32, P(f32)]),
         "cl_op_gemv_residual": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp, i32, i32]),
         "cl_op_rmsnorm_gemv": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, f32, vp, i32, i32]),
@@ -300,6 +301,14 @@ class Engine:
         out = np.empty(self.cfg["d_model"], np.float32)
         _check(lib().cl_debug_hidden(self._h, _ptr(out), out.size), "cl_debug_hidden")
         return out
+
+    def debug_timeline(self) -> np.ndarray:
+        n = (self.cfg["n_layers"] * 5 + 1) * 4
+        out = np.zeros(n, np.int64)
+        rc = lib().cl_debug_timeline(self._h, _ptr(out), n)
+        if rc < 0:
+            raise EngineError(rc, "cl_debug_timeline")
+        return out.reshape(-1, 4)
 
     # ---- request level ---------------------------------------------------------------------------
     def generate_ids(self, prompt_ids, sampling: Sampling) -> GenerateResult:

@@ -196,6 +196,11 @@ int cl_decode_greedy_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs,
 /* debugging / parity: copy the residual stream after `layer` (or the final norm input when
  * layer == n_layers) of the most recent single-sequence step to host (d_model floats). */
 int cl_debug_hidden(cl_engine* e, float* out, int32_t n);
+/* profiling aid (engine created with env CL_TIMELINE=1): %globaltimer stamps [node][4] = {CTA start,
+ * dependency satisfied, inputs loaded / pages consumed, outputs written} of CTA 0 of every kernel node of
+ * the most recent token step; nodes = n_layers * {qkv, attn, o, gate|up, down} + lm_head.  Returns the
+ * number of int64 values written (or a negative status). */
+int cl_debug_timeline(cl_engine* e, int64_t* out, int32_t n);
 
 /* ---- single-op entry points (host buffers in/out; kernel parity tests and microbenches) --
  * Each runs exactly the CUDA kernel the token step uses.  bf16 data is passed as uint16_t.

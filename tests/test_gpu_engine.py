@@ -186,3 +186,27 @@ def test_llama3_8b_layer_shapes_match_oracle():
         err, mism = _compare_greedy(e, m, _prompt(8, cfg["vocab_size"]), 8)
         print(f"llama3-8b(2 layers): max logit err {err:.4g}, near-tie mismatches {mism}")
         assert mism == 0
+
+
+@pytest.mark.parametrize("mega", ["1", "0"])
+def test_megakernel_and_per_op_path_match_oracle(monkeypatch, mega):
+    """The persistent whole-stack decode kernel (decode_mega.cu, CL_MEGA=1) and the per-op kernel path
+    (CL_MEGA=0) against the oracle at Llama-3-8B layer shapes (3 layers): teacher-forced logits over a
+    context that spans several KV pages / splits and crosses page boundaries, then the device-side greedy loop."""
+    cfg = dict(oc.PRESETS["llama3-8b"])
+    cfg["n_layers"] = 3
+    cfg["max_seq_len"] = 512
+    monkeypatch.setenv("CL_MEGA", mega)
+    m = oc.Model(cfg, seed=77)
+    with eng.Engine(model=cfg, seed=77, max_batch=1) as e:
+        err, mism = _compare_greedy(e, m, _prompt(90, cfg["vocab_size"]), 44)   # crosses the 96- and 128-token boundaries
+        print(f"CL_MEGA={mega}: max logit err {err:.4g}, near-tie mismatches {mism}")
+        prompt = _prompt(61, cfg["vocab_size"])
+        so = m.new_seq()
+        first = int(so.forward(prompt).argmax())
+        ref, margins = so.greedy(first, 24)
+        s = e.seq_create()
+        assert int(e.prefill(s, prompt).argmax()) == first
+        ids, _ = e.decode_greedy(s, first, 24)
+        k = len(ref) if margins.min() > MARGIN_TOL else int(np.argmax(margins <= MARGIN_TOL))
+        np.testing.assert_array_equal(ids[:k], ref[:k])
