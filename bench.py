@@ -105,35 +105,6 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        return rank, local, world, dist
-    return rank, local, world, None
-
-
-def barrier(dist, local):
-    if dist is not None:
-        import torch
-        dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-
-def max_over_ranks(dist, x, local):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
 def cpu_baseline(steps_cap_s=25.0, max_tokens=8, warm=1):
     """The CPU oracle port on this box's host cores: Llama-3-8B shapes, synthetic weights, KV cache
     pre-filled to 4096 positions (timing only), a few greedy decode steps."""
@@ -195,7 +166,12 @@ def run_reference(args):
 def run_ours(args):
     from crowdllama_b200 import engine as eng
     hbm, tflops, peak_src = load_peaks()
-    rank, local, world, dist = dist_setup(args.gpus)
+    from crowdllama_b200.distutil import Group
+    grp = Group()
+    rank, local, world = grp.rank, grp.local_rank, grp.world
+    barrier = lambda _d, _l: grp.barrier()                      # noqa: E731
+    max_over_ranks = lambda _d, x, _l: grp.max(x)               # noqa: E731
+    dist = None
     if world != args.gpus and world > 1:
         print(f"warning: WORLD_SIZE={world} != --gpus {args.gpus}", file=sys.stderr)
     n_gpus = max(world, 1)

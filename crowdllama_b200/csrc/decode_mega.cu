@@ -274,6 +274,15 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
         ++r.git;
       }
       produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wo), T_O, SLOT, ctr + 1, CAP4, pol);
+      // The ring now holds this CTA's share of the attention + o-projection work and stays full until the
+      // consumers get through attention, the split combine and two grid barriers (~15 us) — HBM would idle.
+      // Use that window: pull the first pf_tiles * gridDim.x tiles of gate|up (the next big stream, consumed
+      // in tile order) into the 126 MB L2; the demand copies of phase P3 then hit L2.
+      for (int i = 0; i < a.pf_tiles; ++i) {
+        const int t = (int)blockIdx.x * a.pf_tiles + i;
+        if (t < T_GU)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(L.wgu) + (size_t)t * SLOT), "r"(SLOT) : "memory");
+      }
       produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wgu), T_GU, SLOT, ctr + 2, CAP4, pol);
       produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wdown), T_DN, (uint32_t)F * 2u, ctr + 3, CAP1, pol);
     }

@@ -143,6 +143,14 @@ int Engine::init(const cl_engine_config& c) {
   seqs_.assign(max_seqs_, SeqState());
   tok.reset(new Tokenizer(cfg.vocab_size));
   CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  {
+    // Advertised throughput before anything has been measured: FindBestWorker (manager.go:369-377) never
+    // selects a worker whose score is 0, so start from a model-based estimate (70 % of the HBM roofline of
+    // one decode step) and let the EWMA of real steps take over.
+    const double params = (double)cfg.n_layers * ((double)qkv_dim_ * cfg.d_model + (double)cfg.d_model * q_dim_ + 3.0 * cfg.d_ff * cfg.d_model) +
+                          (double)cfg.vocab_size * cfg.d_model;
+    tok_per_sec_ewma_ = 0.7 * 6.5e12 / (2.0 * params);
+  }
   if (c.start_scheduler) start_scheduler();
   return CL_OK;
 }
@@ -287,6 +295,18 @@ int Engine::alloc_state() {
     DMALLOC(d_timeline_, (size_t)(cfg.n_layers * 5 + 1) * 4 * 8);   // >= n_layers * 16 stamps for the megakernel view
     CL_CUDA_OK(cudaMemsetAsync(d_timeline_, 0, (size_t)(cfg.n_layers * 5 + 1) * 4 * 8, stream_));
   }
+  batch_gemm_min_ = env_int("CL_BATCH_GEMM_MIN", 3);
+  use_batch_gemm_ = env_int("CL_BATCH_GEMM", 1) != 0 && max_batch_ >= 2 && gemm_tcgen05_supported(max_batch_, cfg.d_model, cfg.d_model) &&
+                    max_batch_ <= 32;
+  if (use_batch_gemm_) {
+    bws_.reset(new BatchWs());
+    const size_t Bm = max_batch_, widest = std::max<size_t>((size_t)qkv_dim_, std::max<size_t>(2 * (size_t)cfg.d_ff, d));
+    DMALLOC(bws_->xn, Bm * d * 2);
+    DMALLOC(bws_->attn, Bm * q_dim_ * 2);
+    DMALLOC(bws_->act, Bm * (size_t)cfg.d_ff * 2);
+    DMALLOC(bws_->part, 4 * Bm * widest * 4);
+    DMALLOC(bws_->logits, Bm * (size_t)cfg.vocab_size * 4);
+  }
   prompt_cap_ = cfg.max_seq_len;
   DMALLOC(d_prompt_, (size_t)prompt_cap_ * 4);
   CL_CUDA_OK(cudaMemsetAsync(d_tok_, 0, S * 4, stream_));
@@ -334,6 +354,7 @@ int Engine::ensure_capacity(cl_seq_t s, int n_tokens) {
 
 // ---- one token step for the sequences listed in d_slots_[0..B) -----------------------------------
 int Engine::enqueue_step(int B, bool tail) {
+  if (B >= batch_gemm_min_ && tail && use_batch_gemm_ && bws_) return enqueue_step_batched(B);   // B = 2 is faster on the GEMV kernels (measured)
   const int d = cfg.d_model, F = cfg.d_ff, L_ = cfg.n_layers;
   int n = 0, r;
 #define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; } while (0)
@@ -352,7 +373,7 @@ int Engine::enqueue_step(int B, bool tail) {
     MegaArgs m;
     m.layers = d_mega_layers_; m.n_layers = L_; m.q_dim = q_dim_; m.qkv_dim = qkv_dim_; m.n_heads = cfg.n_heads; m.n_kv = cfg.n_kv_heads;
     m.nsplit = nsplit_; m.eps = cfg.rms_eps; m.rope = rope_; m.pos = d_pos_; m.block_tables = d_bt_; m.bt_stride = max_pages_per_seq_;
-    m.slots = d_slots_; m.h = d_h_; m.q = d_q_; m.attn_x = d_attn_; m.act = d_act_; m.part = d_attn_part_; m.bars = d_sync_; m.tile_ctr = d_sync_ + (size_t)L_ * 6;
+    m.slots = d_slots_; m.h = d_h_; m.q = d_q_; m.attn_x = d_attn_; m.act = d_act_; m.part = d_attn_part_; m.bars = d_sync_; m.tile_ctr = d_sync_ + (size_t)L_ * 6; m.pf_tiles = env_int("CL_MEGA_PF_TILES", 0);   // measured: no gain (profiles/README.md)
     m.tl = d_timeline_; m.tl_cta = env_int("CL_TIMELINE_CTA", 0);
     m.kv_layer_rows = (long long)n_pages_ * cfg.n_kv_heads * page_size_; m.kmap = kmap_; m.vmap = vmap_;
     CL_LAUNCH(launch_decode_mega(m, stream_));
@@ -426,6 +447,61 @@ int Engine::enqueue_step(int B, bool tail) {
     t.sync_counters = d_sync_; t.n_sync_counters = n_sync_;
     CL_LAUNCH(launch_step_tail(t, stream_));
   }
+#undef CL_LAUNCH
+  return n;
+}
+
+// ---- batched token step (B >= 2): tensor-core projections (tcgen05, split-K) + per-sequence glue -----
+static int pick_splits(int n_rows, int K) {
+  const int tiles = (n_rows + 127) / 128, nkb = (K + 63) / 64;
+  int s = std::max(1, std::min(4, sm_count() / std::max(1, tiles)));
+  while (s > 1 && ((nkb + s - 1) / s) * (s - 1) >= nkb) --s;   // every split must own >= 1 k-block
+  return s;
+}
+
+int Engine::enqueue_step_batched(int B) {
+  const int d = cfg.d_model, F = cfg.d_ff, L_ = cfg.n_layers, V = cfg.vocab_size;
+  int n = 0, r;
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; } while (0)
+  BatchWs& w = *bws_;
+  const int s_qkv = pick_splits(qkv_dim_, d), s_o = pick_splits(d, q_dim_), s_gu = pick_splits(2 * F, d), s_dn = pick_splits(d, F);
+  CL_LAUNCH(launch_embed(embed_, d, d_tok_, d_h_, d, d_slots_, B, stream_));
+  const float* pending = nullptr;   // split-K partials of the previous residual projection, folded into the next norm
+  int pending_s = 0;
+  for (int l = 0; l < L_; ++l) {
+    const auto& L = layers_[l];
+    CL_LAUNCH(launch_batch_resid_norm(d_h_, d, pending, pending_s, B, L.attn_norm, cfg.rms_eps, w.xn, d_slots_, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wqkv, w.part, nullptr, B, qkv_dim_, d, stream_, s_qkv));
+    QkvEpi e;
+    e.rope = rope_; e.pos = d_pos_; e.block_tables = d_bt_; e.bt_stride = max_pages_per_seq_;
+    e.kpool = kpool_ + (size_t)l * kv_layer_elems_; e.vpool = vpool_ + (size_t)l * kv_layer_elems_;
+    e.n_heads = cfg.n_heads; e.n_kv = cfg.n_kv_heads; e.head_dim = cfg.head_dim; e.page_size = page_size_;
+    CL_LAUNCH(launch_batch_rope_append(w.part, s_qkv, B, e, d_q_, q_dim_, d_slots_, stream_));
+    AttnDecodeArgs a;
+    a.q = d_q_; a.q_stride = q_dim_;
+    a.kpool = e.kpool; a.vpool = e.vpool; a.block_tables = d_bt_; a.bt_stride = max_pages_per_seq_; a.pos = d_pos_;
+    a.out = d_attn_; a.out_stride = q_dim_; a.part = d_attn_part_; a.counters = d_attn_cnt_;
+    a.slots = d_slots_; a.batch = B; a.n_heads = cfg.n_heads; a.n_kv = cfg.n_kv_heads; a.head_dim = cfg.head_dim;
+    // many sequences already fill the machine: fewer KV splits per sequence (cheaper combine, fewer CTAs)
+    a.page_size = page_size_; a.nsplit = std::max(1, std::min(nsplit_, 2 * sm_count() / (cfg.n_kv_heads * B))); a.pdl_early = 0;
+    CL_LAUNCH(launch_attn_decode(a, stream_, false));
+    CL_LAUNCH(launch_batch_gather_bf16(d_attn_, q_dim_, q_dim_, w.attn, d_slots_, B, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.part, nullptr, B, d, q_dim_, stream_, s_o));
+    CL_LAUNCH(launch_batch_resid_norm(d_h_, d, w.part, s_o, B, L.ffn_norm, cfg.rms_eps, w.xn, d_slots_, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.part, nullptr, B, 2 * F, d, stream_, s_gu));
+    CL_LAUNCH(launch_batch_silu(w.part, s_gu, B, F, w.act, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.act, L.wdown, w.part, nullptr, B, d, F, stream_, s_dn));
+    pending = w.part; pending_s = s_dn;
+  }
+  CL_LAUNCH(launch_batch_resid_norm(d_h_, d, pending, pending_s, B, final_norm_, cfg.rms_eps, w.xn, d_slots_, stream_));
+  CL_LAUNCH(launch_gemm_bf16(w.xn, lm_head_, w.logits, nullptr, B, V, d, stream_, 1));
+  CL_LAUNCH(launch_batch_scatter_rows(w.logits, V, d_logits_, V, d_slots_, B, stream_));
+  StepTailArgs t;
+  t.logits = d_logits_; t.vocab = V; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
+  t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
+  t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = B;
+  t.sync_counters = d_sync_; t.n_sync_counters = n_sync_;
+  CL_LAUNCH(launch_step_tail(t, stream_));
 #undef CL_LAUNCH
   return n;
 }

@@ -133,6 +133,7 @@ class Engine {
   int alloc_state();
   int ensure_capacity(cl_seq_t s, int n_tokens);  // reserve pages + upload block table row
   int enqueue_step(int B, bool tail);              // kernels of one token step for d_slots_[0..B)
+  int enqueue_step_batched(int B);                 // B >= 2: tcgen05 projections + per-sequence glue kernels
   int run_step_graph(int B);                       // graph launch (or eager enqueue)
   int read_logits(int slot, float* out);
   int prefill_tokenwise(cl_seq_t s, const int32_t* ids, int n, float* logits_out);
@@ -187,6 +188,10 @@ class Engine {
     __nv_bfloat16* act = nullptr;   // [T][F]
   };
   std::unique_ptr<PrefillWs> pws_;
+  struct BatchWs { __nv_bfloat16* xn = nullptr; __nv_bfloat16* attn = nullptr; __nv_bfloat16* act = nullptr; float* part = nullptr; float* logits = nullptr; };
+  std::unique_ptr<BatchWs> bws_;
+  bool use_batch_gemm_ = false;
+  int batch_gemm_min_ = 3;
   int prefill_chunk_tokens_ = 4096;
 
   std::unique_ptr<KvPool> pool_;

@@ -75,6 +75,7 @@ struct GemmParams {
   float* Y;
   int T, N, K, ldy;
   int accumulate_into_y;  // 1: Y += result (residual add in place)
+  int k_splits;           // > 1: split-K; split s writes its partial to Y + s * T * ldy (the consumer sums in fixed order)
 };
 
 template <int BT, int NST>
@@ -96,8 +97,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_t = (p.T + BT - 1) / BT, num_n = (p.N + BM - 1) / BM;
-  const int num_tiles = num_t * num_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int ksp = p.k_splits > 1 ? p.k_splits : 1;
+  const int num_tiles = num_t * num_n * ksp;          // split index is the slowest dimension
+  const int num_kb_all = (p.K + BK - 1) / BK;
+  const int kb_per = (num_kb_all + ksp - 1) / ksp;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_w);
@@ -120,8 +123,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile / num_t) * BM, t0 = (tile % num_t) * BT;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int bt_ = tile % (num_t * num_n), ks = tile / (num_t * num_n);
+        const int n0 = (bt_ / num_t) * BM, t0 = (bt_ % num_t) * BT;
+        const int kb0 = ks * kb_per, kb1 = min(num_kb_all, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], STAGE);
           uint8_t* sa = base + (size_t)stage * STAGE;
@@ -139,6 +144,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * BT);
+      const int ks = tile / (num_t * num_n);
+      const int kb0 = ks * kb_per, num_kb = max(0, min(num_kb_all, kb0 + kb_per) - kb0);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -162,7 +169,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n0 = (tile / num_t) * BM, t0 = (tile % num_t) * BT;
+      const int bt_ = tile % (num_t * num_n), ks = tile / (num_t * num_n);
+      const int n0 = (bt_ / num_t) * BM, t0 = (bt_ % num_t) * BT;
+      float* Yb = p.Y + (size_t)ks * p.T * p.ldy;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int n = n0 + q * 32 + lane;
@@ -176,7 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           for (int c = 0; c < 32; ++c) {
             const int t = t0 + c0 + c;
             if (t < p.T) {
-              float* dst = p.Y + (size_t)t * p.ldy + n;
+              float* dst = Yb + (size_t)t * p.ldy + n;
               const float r = __uint_as_float(v[c]);
               *dst = p.accumulate_into_y ? (*dst + r) : r;
             }
@@ -253,7 +262,7 @@ cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const Gemm
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const int tiles = ((p.T + BT - 1) / BT) * ((p.N + BM - 1) / BM);
+  const int tiles = ((p.T + BT - 1) / BT) * ((p.N + BM - 1) / BM) * (p.k_splits > 1 ? p.k_splits : 1);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, 192, smem, st>>>(mw, mx, p);
   return cudaGetLastError();
@@ -264,13 +273,15 @@ cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const Gemm
 bool gemm_tcgen05_supported(int T, int N, int K) { return T > 0 && N > 0 && K > 0 && K % 8 == 0 && get_encode() != nullptr; }
 
 int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, const float* resid, int T, int N, int K,
-                     cudaStream_t st) {
+                     cudaStream_t st, int k_splits) {
   if (!gemm_tcgen05_supported(T, N, K)) return -1;
   if (resid && resid != Y) return -1;  // residual add is in place
   const int BT = T > 128 ? 256 : T > 64 ? 128 : T > 32 ? 64 : 32;
   CUtensorMap mw, mx;
   if (!make_map(&mw, W, N, K, BM) || !make_map(&mx, X, T, K, BT)) return -1;
-  GemmParams p{Y, T, N, K, N, resid ? 1 : 0};
+  if (k_splits > 1 && (resid || (K + BK - 1) / BK < k_splits)) return -1;   // every split needs >= 1 k-block (an empty split would never signal its epilogue)
+  if (k_splits > 1 && ((K + BK - 1) / BK + k_splits - 1) / k_splits * (k_splits - 1) >= (K + BK - 1) / BK) return -1;
+  GemmParams p{Y, T, N, K, N, resid ? 1 : 0, k_splits};
   cudaError_t e;
   switch (BT) {
     case 256: e = launch_inst<256, 4>(mw, mx, p, st); break;

@@ -134,6 +134,7 @@ struct MegaArgs {
   float* part = nullptr;               // attention partials
   unsigned* bars = nullptr;            // [n_layers * 6] grid-barrier counters, zero at kernel start
   unsigned* tile_ctr = nullptr;        // [n_layers * 4] dynamic tile-scheduler counters, zero at kernel start
+  int pf_tiles = 0;                    // gate|up tiles (32 KB) each CTA prefetches into L2 during the attention window
   long long* tl = nullptr;             // debug: [n_layers][16] globaltimer stamps of CTA tl_cta
   int tl_cta = 0;
   long long kv_layer_rows = 0;         // rows of one layer in the KV tensor maps (= n_pages * n_kv * page)
@@ -149,8 +150,9 @@ int sm_count();
 
 // ---- prefill path (prefill_kernels.cu / gemm_tcgen05.cu) -----------------------------------------
 // X bf16 [T][K] row-major, W bf16 [N][K] row-major -> Y fp32 [T][N] (+= resid when resid != nullptr)
+// k_splits > 1: split-K, partial s is written to Y + s*T*N (no residual); the consumer sums the partials
 int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, const float* resid, int T, int N, int K,
-                     cudaStream_t st);
+                     cudaStream_t st, int k_splits = 1);
 bool gemm_tcgen05_supported(int T, int N, int K);
 // xn[t] = bf16(rmsnorm(h[t]) * gain)
 int launch_rmsnorm_bf16(const float* h, const float* gain, float eps, __nv_bfloat16* out, int T, int d, cudaStream_t st);
@@ -173,6 +175,14 @@ struct AttnPrefillArgs {
 int launch_attn_prefill(const AttnPrefillArgs& a, cudaStream_t st);
 // act = bf16(silu(gu[:, 2i]) * gu[:, 2i+1])
 int launch_silu_mul_bf16(const float* gu, __nv_bfloat16* act, int T, int d_ff, cudaStream_t st);
+// ---- batched decode glue (batch_kernels.cu) ------------------------------------------------------
+int launch_batch_resid_norm(float* h, int d, const float* ypart, int n_split, int B, const float* gain, float eps, __nv_bfloat16* xn,
+                            const int* slots, cudaStream_t st);
+int launch_batch_rope_append(const float* ypart, int n_split, int B, const QkvEpi& e, float* q_out, int q_stride, const int* slots,
+                             cudaStream_t st);
+int launch_batch_gather_bf16(const float* x, int n, int x_stride, __nv_bfloat16* xb, const int* slots, int B, cudaStream_t st);
+int launch_batch_silu(const float* ypart, int n_split, int B, int d_ff, __nv_bfloat16* act, cudaStream_t st);
+int launch_batch_scatter_rows(const float* y, int n, float* out, int out_stride, const int* slots, int B, cudaStream_t st);
 int launch_embed_rows(const __nv_bfloat16* table, int d, const int* ids_dev, float* h, int T, cudaStream_t st);
 
 }  // namespace cl

@@ -1,0 +1,133 @@
+"""Gateway stand-in: the reference's Ollama-compatible HTTP façade, restated for the benchmark harness.
+
+Mirrors pkg/gateway/gateway.go: POST /api/chat (handleChat :168-231 → FindBestWorker :191 → RequestInference
+:243-293) and GET /api/health (:453-461).  Worker discovery (DHT provider lookup + metadata fetch,
+internal/discovery/discovery.go:278-366) is replaced by a static address list whose metadata is polled
+over the metadata protocol — the routing rule itself (peermanager FindBestWorker) is `router.find_best_worker`.
+Quirks kept: only messages[0].content is forwarded (gateway.go:209); handler errors arrive as assistant
+text with HTTP 200 (peer.go:232-243); no worker → 503 JSON error (gateway.go:192-199).
+"""
+from __future__ import annotations
+
+import json
+import random
+import socket
+import threading
+import time
+from datetime import datetime, timezone
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+
+from . import handler as H
+from .pbwire import read_length_prefixed_pb, write_length_prefixed_pb
+from .router import Resource, find_best_worker
+from .worker import INFERENCE_PROTOCOL, METADATA_PROTOCOL, _Stream
+
+
+class PeerTable:
+    """peermanager stand-in: address -> Resource, refreshed by metadata probes."""
+
+    def __init__(self, addrs, refresh_s: float = 2.0, seed: int = 0):
+        self.addrs = list(addrs)
+        self.peers: dict[tuple, Resource] = {}
+        self.rng = random.Random(seed)
+        self.lock = threading.Lock()
+        self.refresh_s = refresh_s
+        self._stop = threading.Event()
+
+    def probe(self):
+        for a in self.addrs:
+            try:
+                with socket.create_connection(a, timeout=2) as s:
+                    s.sendall((METADATA_PROTOCOL + "\n").encode())
+                    data = b""
+                    while chunk := s.recv(65536):
+                        data += chunk
+                r = Resource.from_json(data)
+                with self.lock:
+                    self.peers[a] = r
+            except OSError:
+                with self.lock:
+                    self.peers.pop(a, None)
+
+    def start(self):
+        self.probe()
+        threading.Thread(target=self._loop, daemon=True).start()
+
+    def _loop(self):
+        while not self._stop.wait(self.refresh_s):
+            self.probe()
+
+    def stop(self):
+        self._stop.set()
+
+    def best(self, model: str):
+        with self.lock:
+            by_id = {r.peer_id: a for a, r in self.peers.items()}
+            w = find_best_worker(list(self.peers.values()), model, self.rng)
+        return (by_id[w.peer_id], w) if w else (None, None)
+
+
+def request_inference(addr, model: str, prompt: str, stream: bool):
+    """Gateway.RequestInference (gateway.go:243-293) over the TCP stand-in for a libp2p stream."""
+    with socket.create_connection(addr, timeout=600) as s:
+        s.sendall((INFERENCE_PROTOCOL + "\n").encode())
+        st = _Stream(s)
+        write_length_prefixed_pb(st, H.create_generate_request(model, prompt, stream))
+        return H.extract_generate_response(read_length_prefixed_pb(st))
+
+
+class _Handler(BaseHTTPRequestHandler):
+    protocol_version = "HTTP/1.1"
+
+    def log_message(self, *a):
+        pass
+
+    def _json(self, code, obj):
+        body = json.dumps(obj).encode()
+        self.send_response(code)
+        self.send_header("Content-Type", "application/json")
+        self.send_header("Content-Length", str(len(body)))
+        self.end_headers()
+        self.wfile.write(body)
+
+    def do_GET(self):
+        if self.path == "/api/health":
+            t: PeerTable = self.server.table
+            with t.lock:
+                peers = {r.peer_id: {"supported_models": r.supported_models, "tokens_throughput": r.tokens_throughput, "load": r.load,
+                                     "gpu_model": r.gpu_model} for r in t.peers.values()}
+            return self._json(200, {"status": "ok", "peers": peers})
+        self._json(404, {"error": "not found"})
+
+    def do_POST(self):
+        if self.path != "/api/chat":
+            return self._json(404, {"error": "not found"})
+        try:
+            req = json.loads(self.rfile.read(int(self.headers.get("Content-Length", "0"))))
+        except Exception:
+            return self._json(400, {"error": "invalid JSON"})
+        model, messages = req.get("model"), req.get("messages") or []
+        if not model or not messages:                                     # gateway.go:175-188
+            return self._json(400, {"error": "model and messages are required"})
+        addr, worker = self.server.table.best(model)
+        if worker is None:                                                # gateway.go:192-199
+            return self._json(503, {"error": f"no available worker for model {model}"})
+        with self.server.lock:
+            self.server.counts[worker.peer_id] = self.server.counts.get(worker.peer_id, 0) + 1
+        try:
+            g = request_inference(addr, model, messages[0].get("content", ""), bool(req.get("stream", False)))
+        except Exception as ex:                                           # gateway.go:210-217
+            return self._json(500, {"error": f"inference request failed: {ex}"})
+        self._json(200, {"model": g.model or model, "created_at": datetime.now(timezone.utc).isoformat(),
+                         "message": {"role": "assistant", "content": g.response}, "stream": False,
+                         "done_reason": g.done_reason, "done": g.done})
+
+
+def make_server(worker_addrs, port: int = 9001, host: str = "127.0.0.1", seed: int = 0) -> ThreadingHTTPServer:
+    srv = ThreadingHTTPServer((host, port), _Handler)
+    srv.daemon_threads = True
+    srv.request_queue_size = 256
+    srv.table = PeerTable(worker_addrs, seed=seed)
+    srv.counts, srv.lock = {}, threading.Lock()
+    srv.table.start()
+    return srv

@@ -1,0 +1,110 @@
+"""CPU tests of the request-level harness: gateway stand-in + worker protocol servers with a MOCK engine
+(mirrors /root/reference/test/integration_test.go:139-191, where the only faked piece is the model server)."""
+import json
+import socket
+import threading
+import urllib.error
+import urllib.request
+
+import pytest
+
+from crowdllama_b200 import gateway, worker
+from crowdllama_b200 import handler as H
+from crowdllama_b200.router import Resource
+
+
+class _MockEngine:
+    def __init__(self, name, tput=150.0):
+        self.model_name, self.tput = name, tput
+
+    def generate(self, model, prompt, sampling=None):
+        class R:
+            text, done_reason = f"This is a mock response. You asked: {prompt}", "stop"
+        if model != self.model_name:
+            raise RuntimeError("unknown model")
+        return R()
+
+    def stats(self):
+        return dict(tokens_per_sec=self.tput, load=0.3, vram_gb=179, gpu_model="mock B200")
+
+
+def _spawn_worker(port, name):
+    srv = worker.WorkerServer(("127.0.0.1", port), _MockEngine(name), peer_id=f"w{port}")
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    return srv
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _post(url, obj):
+    req = urllib.request.Request(url, json.dumps(obj).encode(), {"Content-Type": "application/json"})
+    with urllib.request.urlopen(req, timeout=10) as r:
+        return r.status, json.loads(r.read())
+
+
+def test_gateway_to_worker_round_trip_and_errors():
+    p1, p2, gp = _free_port(), _free_port(), _free_port()
+    w1, w2 = _spawn_worker(p1, "llama3.2"), _spawn_worker(p2, "llama3.2")
+    gw = gateway.make_server([("127.0.0.1", p1), ("127.0.0.1", p2)], port=gp)
+    threading.Thread(target=gw.serve_forever, daemon=True).start()
+    try:
+        base = f"http://127.0.0.1:{gp}"
+        # metadata protocol feeds the peer table (truthful Resource from engine stats)
+        with urllib.request.urlopen(base + "/api/health", timeout=5) as r:
+            health = json.loads(r.read())
+        assert set(health["peers"]) == {f"w{p1}", f"w{p2}"}
+        assert health["peers"][f"w{p1}"]["supported_models"] == ["llama3.2"]
+        # integration_test.go:490-553: 200, model echo, non-empty content, done
+        st, out = _post(base + "/api/chat", {"model": "llama3.2", "messages": [{"role": "user", "content": "Hello"},
+                                                                               {"role": "user", "content": "dropped"}], "stream": False})
+        assert st == 200 and out["model"] == "llama3.2" and out["done"] and out["done_reason"] == "stop"
+        assert out["message"] == {"role": "assistant", "content": "This is a mock response. You asked: Hello"}   # only messages[0]
+        # requests spread over both tied workers (random among ties)
+        for i in range(30):
+            _post(base + "/api/chat", {"model": "llama3.2", "messages": [{"role": "user", "content": str(i)}]})
+        assert len(gw.counts) == 2 and sum(gw.counts.values()) == 31
+        # unknown model -> 503; missing fields -> 400 (gateway.go:175-199)
+        for body, code in [({"model": "nope", "messages": [{"role": "user", "content": "x"}]}, 503), ({"model": "llama3.2"}, 400),
+                           ({"messages": [{"role": "user", "content": "x"}]}, 400)]:
+            with pytest.raises(urllib.error.HTTPError) as ei:
+                _post(base + "/api/chat", body)
+            assert ei.value.code == code
+    finally:
+        gw.shutdown(); w1.shutdown(); w2.shutdown()
+
+
+def test_worker_handler_error_becomes_assistant_text():
+    """A handler error travels as Response="Error: ..." (peer.go:232-243) and the gateway still answers 200."""
+    p, gp = _free_port(), _free_port()
+    srv = worker.WorkerServer(("127.0.0.1", p), _MockEngine("m"), peer_id="w")
+
+    def boom(ctx, req):
+        raise RuntimeError("engine exploded")
+    srv.api_handler = boom
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    gw = gateway.make_server([("127.0.0.1", p)], port=gp)
+    threading.Thread(target=gw.serve_forever, daemon=True).start()
+    try:
+        st, out = _post(f"http://127.0.0.1:{gp}/api/chat", {"model": "m", "messages": [{"role": "user", "content": "x"}]})
+        assert st == 200 and out["message"]["content"] == "Error: engine exploded" and out["done"]
+    finally:
+        gw.shutdown(); srv.shutdown()
+
+
+def test_metadata_protocol_returns_resource_json():
+    p = _free_port()
+    srv = _spawn_worker(p, "tinyllama")
+    try:
+        with socket.create_connection(("127.0.0.1", p), timeout=5) as s:
+            s.sendall((worker.METADATA_PROTOCOL + "\n").encode())
+            data = b""
+            while chunk := s.recv(4096):
+                data += chunk
+        r = Resource.from_json(data)
+        assert r.worker_mode and r.supported_models == ["tinyllama"] and r.tokens_throughput == 150.0 and r.gpu_model == "mock B200"
+    finally:
+        srv.shutdown()

@@ -84,9 +84,31 @@ def decode_sweep(f, preset="llama3-8b", ctx=4096, steps=128):
             emit(f, bench="decode", env=env, error=str(ex))
 
 
+def batch_sweep(f, preset="llama3-8b", ctx=1024, steps=64):
+    """Continuous-batching inner loop: B sequences advance together (cl_decode_greedy_batch)."""
+    for B in (1, 2, 4, 8):
+        try:
+            with eng.Engine(preset=preset, seed=1234, max_batch=B) as e:
+                V = e.cfg["vocab_size"]
+                seqs, firsts = [], []
+                for b in range(B):
+                    s = e.seq_create()
+                    lg = e.prefill(s, np.array([(i * 7919 + 13 + b) % V for i in range(ctx)], np.int32))
+                    seqs.append(s)
+                    firsts.append(int(lg.argmax()))
+                ids, _ = e.decode_greedy_batch(seqs, firsts, 8)
+                ids, ms = e.decode_greedy_batch(seqs, ids[-1], steps)
+                emit(f, bench="batch_decode", preset=preset, batch=B, ctx=ctx, steps=steps, ms_per_step=round(ms / steps, 4),
+                     tok_s=round(B * steps / (ms * 1e-3), 1))
+        except Exception as ex:  # noqa: BLE001
+            emit(f, bench="batch_decode", batch=B, error=str(ex))
+
+
 if __name__ == "__main__":
     with open(OUT / "microbench.jsonl", "a") as f:
         if "gemv" in sys.argv or len(sys.argv) == 1:
             gemv_sweep(f)
         if "decode" in sys.argv or len(sys.argv) == 1:
             decode_sweep(f)
+        if "batch" in sys.argv:
+            batch_sweep(f)
