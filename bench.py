@@ -238,6 +238,7 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001
             kern = {"error": str(ex)}
     e.close()
+    grp.close()
 
     if rank != 0:
         return 0
