@@ -407,13 +407,19 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
           const float corr = exp2f(mrow - mn);
           mrow = mn;
           float rs = 0.f;
-          uint32_t pf[2][4];
+          // P is split into two bf16 terms (hi + lo) so that P.V keeps ~fp32 accuracy: a single bf16 P would put a
+          // 2^-9 relative error on every attention output, which the bf16 rounding points downstream amplify
+          // (profiles/README.md, "parity vs depth")
+          uint32_t pf[2][4], pl[2][4];
 #pragma unroll
           for (int nj = 0; nj < 4; ++nj) {
             const float p0 = exp2f(sacc[nj][0] - mn), p1 = exp2f(sacc[nj][1] - mn);
             rs += p0 + p1;
-            pf[nj >> 1][(nj & 1) * 2] = pack_bf16(p0, p1);
+            const float h0 = bf16_round(p0), h1 = bf16_round(p1);
+            pf[nj >> 1][(nj & 1) * 2] = pack_bf16(h0, h1);
             pf[nj >> 1][(nj & 1) * 2 + 1] = 0u;             // rows 8..15
+            pl[nj >> 1][(nj & 1) * 2] = pack_bf16(p0 - h0, p1 - h1);
+            pl[nj >> 1][(nj & 1) * 2 + 1] = 0u;
           }
           lrow = lrow * corr + rs;
 #pragma unroll
@@ -427,6 +433,8 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
               ldsm_x4_t(vf, vb + (chunk >> 3) * 4096 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
               mma_bf16(o[nd], pf[jj], vf[0], vf[1]);
               mma_bf16(o[nd + 1], pf[jj], vf[2], vf[3]);
+              mma_bf16(o[nd], pl[jj], vf[0], vf[1]);
+              mma_bf16(o[nd + 1], pl[jj], vf[2], vf[3]);
             }
           }
         }

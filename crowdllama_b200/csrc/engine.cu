@@ -680,7 +680,18 @@ int Engine::debug_timeline(long long* out, int n) {
 }
 
 int Engine::debug_hidden(float* out, int n) {
-  if (last_single_slot_ < 0 || n != cfg.d_model) return CL_ERR_INVALID_ARG;
+  if (last_single_slot_ < 0) return CL_ERR_INVALID_ARG;
+  // negative n selects a last-layer intermediate of the most recent single-sequence step (diagnostics):
+  // -1 = q (roped), -2 = attention output, -3 = SwiGLU activation
+  if (n < 0) {
+    const float* src = n == -1 ? d_q_ + (size_t)last_single_slot_ * q_dim_ : n == -2 ? d_attn_ + (size_t)last_single_slot_ * q_dim_
+                                                                              : d_act_ + (size_t)last_single_slot_ * cfg.d_ff;
+    const int cnt = n == -3 ? cfg.d_ff : q_dim_;
+    CL_CUDA_OK(cudaMemcpyAsync(out, src, (size_t)cnt * 4, cudaMemcpyDeviceToHost, stream_));
+    CL_CUDA_OK(cudaStreamSynchronize(stream_));
+    return CL_OK;
+  }
+  if (n != cfg.d_model) return CL_ERR_INVALID_ARG;
   CL_CUDA_OK(cudaMemcpyAsync(out, d_h_ + (size_t)last_single_slot_ * cfg.d_model, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
   CL_CUDA_OK(cudaStreamSynchronize(stream_));
   return CL_OK;

@@ -445,6 +445,17 @@ int oc_debug_hidden(oc_model* m, int32_t layer, float* out) {
   return 0;
 }
 
+/* last-layer intermediates of the most recent token: 0 = q (roped, rounded), 1 = attention output (rounded),
+ * 2 = SwiGLU activation (rounded), 3 = normalised input of the last GEMV group (xn) */
+int oc_debug_vec(oc_model* m, int32_t which, float* out) {
+  const oc_config* c = &m->c;
+  const float* src = which == 0 ? m->q : which == 1 ? m->att : which == 2 ? m->act : which == 3 ? m->xn : NULL;
+  const size_t n = which == 0 || which == 1 ? (size_t)c->n_heads * c->head_dim : which == 2 ? (size_t)c->d_ff : (size_t)c->d_model;
+  if (!src) return -1;
+  memcpy(out, src, n * 4);
+  return (int)n;
+}
+
 int32_t oc_argmax(const float* logits, int32_t n) {
   int best = 0;
   for (int i = 1; i < n; ++i) if (logits[i] > logits[best]) best = i;

@@ -71,6 +71,7 @@ void oc_seq_fake_fill(oc_seq* s, int32_t len);
 int oc_forward(oc_model* m, oc_seq* s, const int32_t* ids, int32_t n, float* logits, int32_t all_logits);
 /* residual stream of the last processed token after `layer` layers (0..n_layers) */
 int oc_debug_hidden(oc_model* m, int32_t layer, float* out);
+int oc_debug_vec(oc_model* m, int32_t which, float* out);
 int32_t oc_argmax(const float* logits, int32_t n);
 /* greedy loop: feeds first_id, then each argmax; ids_out[n_steps]; margins_out (may be NULL)
  * receives top1-top2 logit gaps */

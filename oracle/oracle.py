@@ -96,6 +96,7 @@ def lib():
             "oc_forward": (C.c_int, [vp, vp, vp, i32, vp, i32]),
             "oc_debug_hidden": (C.c_int, [vp, i32, vp]),
             "oc_argmax": (i32, [vp, i32]),
+            "oc_debug_vec": (C.c_int, [vp, i32, vp]),
             "oc_greedy": (C.c_int, [vp, vp, i32, i32, vp, vp]),
             "oc_sample": (i32, [vp, i32, P(OcSampling), vp, i32, u64]),
             "oc_op_gemv": (None, [vp, vp, vp, i32, i32]),
@@ -194,6 +195,13 @@ class Model:
 
     def new_seq(self, max_len: int | None = None) -> "Seq":
         return Seq(self, max_len or self.cfg["max_seq_len"])
+
+    def debug_vec(self, which: int) -> np.ndarray:
+        n = {0: self.cfg["n_heads"] * self.cfg["head_dim"], 1: self.cfg["n_heads"] * self.cfg["head_dim"], 2: self.cfg["d_ff"],
+             3: self.cfg["d_model"]}[which]
+        out = np.empty(n, np.float32)
+        lib().oc_debug_vec(self._h, which, _ptr(out))
+        return out
 
     def hidden(self, layer: int) -> np.ndarray:
         out = np.empty(self.cfg["d_model"], np.float32)

@@ -84,6 +84,21 @@ def decode_sweep(f, preset="llama3-8b", ctx=4096, steps=128):
             emit(f, bench="decode", env=env, error=str(ex))
 
 
+def gemm_sweep(f):
+    """Prefill projections on tcgen05 (cl_op_gemm_bf16, T = 4096 tokens)."""
+    rng = np.random.default_rng(0)
+    T = 4096
+    for name, n, k in [("qkv", 6144, 4096), ("o", 4096, 4096), ("gateup", 28672, 4096), ("down", 4096, 14336)]:
+        x = (rng.integers(0, 1 << 16, size=(T, k), dtype=np.uint16) & 0xBF7F)
+        w = (rng.integers(0, 1 << 16, size=(n, k), dtype=np.uint16) & 0xBF7F)
+        try:
+            _, ms = eng.op_gemm_bf16(x, w, iters=10)
+            tf = 2.0 * T * n * k / (ms * 1e-3) / 1e12
+            emit(f, bench="gemm_tcgen05", shape=name, t=T, n=n, k=k, ms=round(ms, 4), tflops=round(tf, 1), frac_of_sustained=round(tf / 1453.9, 3))
+        except Exception as ex:  # noqa: BLE001
+            emit(f, bench="gemm_tcgen05", shape=name, error=str(ex))
+
+
 def batch_sweep(f, preset="llama3-8b", ctx=1024, steps=64):
     """Continuous-batching inner loop: B sequences advance together (cl_decode_greedy_batch)."""
     for B in (1, 2, 4, 8):
@@ -112,3 +127,5 @@ if __name__ == "__main__":
             decode_sweep(f)
         if "batch" in sys.argv:
             batch_sweep(f)
+        if "gemm" in sys.argv:
+            gemm_sweep(f)
