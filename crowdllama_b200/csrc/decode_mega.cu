@@ -39,6 +39,7 @@ struct Ring {
   uint64_t* empty;
   int* tile_id;                             // [NS] global tile index carried by each slot (-1 = end of phase)
   uint32_t git;                             // tiles issued / consumed so far by this thread's role
+  uint32_t tail;                            // producer only: oldest tile not yet known to have landed
   __device__ __forceinline__ int slot() const { return (int)(git % NS); }
   __device__ __forceinline__ uint32_t parity() const { return (git / NS) & 1u; }
 };
@@ -69,9 +70,76 @@ __device__ __forceinline__ void grid_barrier(unsigned* cnt, int tid) {
 // slowest SM.  Tiles are claimed in chunks of CH from a per-(layer, phase) counter; the claim for the next
 // chunk is issued before the current chunk's copies so its latency is hidden.  A slot with tile_id = -1 ends
 // the phase for this CTA.
-constexpr int CH = 2;
+constexpr int CH = 1;
+
+// ---- L2 lookahead.  Whenever a producer finds its ring full (the consumers sit in an epilogue, a grid barrier,
+// a norm prologue or attention: ~24 us per layer with HBM idle) it pulls weight tiles that lie AHEAD of every
+// CTA's ring into the 126 MB L2 with cp.async.bulk.prefetch.L2.  All weight tiles of the step form one sequence
+// in consumption order (per layer: q|k|v, o, gate|up, down); `ctr` is the global prefetch frontier in that
+// numbering.  The frontier is kept between (own demand position + min_ahead) and (+ budget) tiles, so the
+// lookahead never outgrows L2.  When the consumers resume, the ring refills from L2 faster than HBM could feed
+// it, the producers block again and the frontier moves on: HBM keeps streaming through the barriers.
+constexpr int PFCH = 2;
+struct Lookahead {
+  unsigned* ctr;
+  unsigned known;        // lower bound of the frontier as last seen by this CTA
+  int min_ahead, budget; // tiles
+  unsigned total;        // n_layers * tiles per layer
+  int t_qkv, tl;         // tiles in the q|k|v segment / per layer
+  unsigned n_pf, n_lim, n_jump, n_calls;   // diagnostics (CL_TIMELINE)
+};
+__device__ __forceinline__ void lookahead_step(Lookahead& la, const MegaArgs& a, unsigned mypos) {
+  if (la.budget <= 0) return;
+  ++la.n_calls;
+  const unsigned lim = mypos + (unsigned)la.budget;
+  if (la.known >= lim || la.known >= la.total) { ++la.n_lim; return; }
+  const unsigned p = atomicAdd(la.ctr, (unsigned)PFCH);
+  la.known = p + PFCH;
+  if (p < mypos + (unsigned)la.min_ahead) {      // frontier fell behind the demand stream: jump ahead
+    atomicMax(la.ctr, mypos + (unsigned)la.min_ahead);
+    la.known = mypos + (unsigned)la.min_ahead;
+    ++la.n_jump;
+    return;
+  }
+  if (p >= lim) return;
+  la.n_pf += PFCH;
+#pragma unroll
+  for (int i = 0; i < PFCH; ++i) {
+    const unsigned gidx = p + i;
+    if (gidx >= la.total) break;
+    const int l = (int)(gidx / (unsigned)la.tl);
+    int idx = (int)(gidx - (unsigned)l * (unsigned)la.tl);
+    const MegaLayer& L = a.layers[l];
+    const uint8_t* src;
+    uint32_t bytes = SLOT;
+    if (idx < la.t_qkv) src = reinterpret_cast<const uint8_t*>(L.wqkv) + (size_t)idx * SLOT;
+    else if ((idx -= la.t_qkv) < D / 4) src = reinterpret_cast<const uint8_t*>(L.wo) + (size_t)idx * SLOT;
+    else if ((idx -= D / 4) < 2 * F / 4) src = reinterpret_cast<const uint8_t*>(L.wgu) + (size_t)idx * SLOT;
+    else { idx -= 2 * F / 4; bytes = (uint32_t)F * 2u; src = reinterpret_cast<const uint8_t*>(L.wdown) + (size_t)idx * bytes; }
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+  }
+}
+// wait for a free ring slot; while blocked, run the L2 lookahead.  Then cap the number of copies IN FLIGHT:
+// tools/bench_barrier.cu shows that ~3 x 32 KB per SM already saturate HBM (7.4 TB/s), while every further tile in
+// flight only deepens the queues in front of the L2 slices — and the grid barriers' red/poll round trips wait in
+// those queues (1.2 us idle, 4.4 us with 3 tiles in flight, 12 us with 6).  The ring still fills all NS slots.
+__device__ __forceinline__ void wait_slot(Ring& r, int st, Lookahead& la, const MegaArgs& a, unsigned mypos) {
+  // (try_wait, not test_wait: a tightly polling producer warp measurably slows the two consumer warps that share
+  // its scheduler — 2.83 -> 2.86 ms/token)
+  for (uint32_t spins = 0; !mbar_try_wait(&r.empty[st], r.parity() ^ 1u); ++spins) {
+    lookahead_step(la, a, mypos);
+    if (spins > (1u << 22)) __trap();
+  }
+  for (uint32_t spins = 0; (int)(r.git - r.tail) >= a.max_flight; ++spins) {
+    const uint32_t n = r.tail;
+    if (mbar_try_wait(&r.full[n % NS], (n / NS) & 1u)) ++r.tail;
+    else lookahead_step(la, a, mypos);
+    if (spins > (1u << 22)) __trap();
+  }
+}
+
 __device__ __forceinline__ void produce_dynamic(Ring& r, const uint8_t* w, int total, uint32_t bytes, unsigned* ctr, int cap,
-                                                uint64_t pol) {
+                                                uint64_t pol, Lookahead& la, const MegaArgs& a, unsigned gbase) {
   int issued = 0;
   int cur = (int)atomicAdd(ctr, (unsigned)CH);
   while (cur < total) {
@@ -79,7 +147,7 @@ __device__ __forceinline__ void produce_dynamic(Ring& r, const uint8_t* w, int t
     const int end = min(cur + CH, total);
     for (int t = cur; t < end; ++t) {
       const int st = r.slot();
-      mbar_wait(&r.empty[st], r.parity() ^ 1u);
+      wait_slot(r, st, la, a, gbase + (unsigned)t);
       r.tile_id[st] = t;
       mbar_arrive_expect_tx(&r.full[st], bytes);
       bulk_g2s(r.base + (size_t)st * SLOT, w + (size_t)t * bytes, bytes, &r.full[st], pol);
@@ -89,7 +157,7 @@ __device__ __forceinline__ void produce_dynamic(Ring& r, const uint8_t* w, int t
     cur = nxt;
   }
   const int st = r.slot();
-  mbar_wait(&r.empty[st], r.parity() ^ 1u);
+  wait_slot(r, st, la, a, gbase + (unsigned)total);
   r.tile_id[st] = -1;
   mbar_arrive(&r.full[st]);
   ++r.git;
@@ -235,7 +303,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
   const int n_att_tiles = (npg + 1) / 2;
 
   const int T_QKV = a.qkv_dim / 4, T_O = D / 4, T_GU = 2 * F / 4, T_DN = D;   // tiles per phase
-  Ring r{ring_base, full, empty, tile_id, 0u};
+  Ring r{ring_base, full, empty, tile_id, 0u, 0u};
 
   if (warp == NW) {
     // =============================== producer ===============================
@@ -244,13 +312,16 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
     prefetch_tmap(&a.vmap);
     const uint64_t pol = policy_evict_first();
     const int cur_page = pos / P;
+    const int TL = T_QKV + T_O + T_GU + T_DN;
+    Lookahead la{a.pf_ctr, 0u, a.pf_min, a.pf_ctr ? a.pf_budget : 0, (unsigned)(a.n_layers * TL), T_QKV, TL, 0u, 0u, 0u, 0u};
     for (int l = 0; l < a.n_layers; ++l) {
       const MegaLayer& L = a.layers[l];
       unsigned* ctr = a.tile_ctr + (size_t)l * 4;
-      produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wqkv), T_QKV, SLOT, ctr + 0, CAP4, pol);
+      const unsigned g0 = (unsigned)(l * TL), g1 = g0 + T_QKV, g2 = g1 + T_O, g3 = g2 + T_GU;
+      produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wqkv), T_QKV, SLOT, ctr + 0, CAP4, pol, la, a, g0);
       for (int t = 0; t < n_att_tiles; ++t) {
         const int st = r.slot();
-        mbar_wait(&r.empty[st], r.parity() ^ 1u);
+        wait_slot(r, st, la, a, g1);
         const int pa = pg0 + 2 * t, pb = pa + 1;
         const bool two = pb < pg1;
         if (pa == cur_page || (two && pb == cur_page)) {
@@ -273,18 +344,13 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
         }
         ++r.git;
       }
-      produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wo), T_O, SLOT, ctr + 1, CAP4, pol);
-      // The ring now holds this CTA's share of the attention + o-projection work and stays full until the
-      // consumers get through attention, the split combine and two grid barriers (~15 us) — HBM would idle.
-      // Use that window: pull the first pf_tiles * gridDim.x tiles of gate|up (the next big stream, consumed
-      // in tile order) into the 126 MB L2; the demand copies of phase P3 then hit L2.
-      for (int i = 0; i < a.pf_tiles; ++i) {
-        const int t = (int)blockIdx.x * a.pf_tiles + i;
-        if (t < T_GU)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(L.wgu) + (size_t)t * SLOT), "r"(SLOT) : "memory");
-      }
-      produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wgu), T_GU, SLOT, ctr + 2, CAP4, pol);
-      produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wdown), T_DN, (uint32_t)F * 2u, ctr + 3, CAP1, pol);
+      produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wo), T_O, SLOT, ctr + 1, CAP4, pol, la, a, g1);
+      produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wgu), T_GU, SLOT, ctr + 2, CAP4, pol, la, a, g2);
+      produce_dynamic(r, reinterpret_cast<const uint8_t*>(L.wdown), T_DN, (uint32_t)F * 2u, ctr + 3, CAP1, pol, la, a, g3);
+    }
+    if (a.tl != nullptr && blockIdx.x == (unsigned)a.tl_cta) {
+      long long* dbg = a.tl + (size_t)a.n_layers * 16;
+      dbg[0] = la.n_pf; dbg[1] = la.n_lim; dbg[2] = la.n_jump; dbg[3] = la.n_calls; dbg[4] = r.git;
     }
     return;
   }

@@ -134,7 +134,9 @@ struct MegaArgs {
   float* part = nullptr;               // attention partials
   unsigned* bars = nullptr;            // [n_layers * 6] grid-barrier counters, zero at kernel start
   unsigned* tile_ctr = nullptr;        // [n_layers * 4] dynamic tile-scheduler counters, zero at kernel start
-  int pf_tiles = 0;                    // gate|up tiles (32 KB) each CTA prefetches into L2 during the attention window
+  unsigned* pf_ctr = nullptr;          // L2 lookahead frontier (one counter, zero at kernel start); nullptr = off
+  int max_flight = 6;                  // cap on bulk copies in flight per CTA (<= ring slots)
+  int pf_min = 296, pf_budget = 0;     // lookahead window in tiles ahead of a CTA's own demand position
   long long* tl = nullptr;             // debug: [n_layers][16] globaltimer stamps of CTA tl_cta
   int tl_cta = 0;
   long long kv_layer_rows = 0;         // rows of one layer in the KV tensor maps (= n_pages * n_kv * page)

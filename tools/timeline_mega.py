@@ -21,7 +21,10 @@ with eng.Engine(preset="llama3-8b", seed=1234, max_batch=1) as e:
     lg = e.prefill(s, ids)
     out, ms = e.decode_greedy(s, int(lg.argmax()), 32)
     L = e.cfg["n_layers"]
-    raw = e.debug_timeline().astype(np.float64).ravel()[: L * 16].reshape(L, 16)[:, :14]
+    full = e.debug_timeline().ravel()
+    dbg = full[L * 16: L * 16 + 5]
+    print(f"lookahead (this CTA, last step): prefetched {dbg[0]} tiles, budget-limited calls {dbg[1]}, jumps {dbg[2]}, calls {dbg[3]}, demand tiles {dbg[4]}")
+    raw = full.astype(np.float64)[: L * 16].reshape(L, 16)[:, :14]
     print(f"ms/step {ms/32:.4f}  (CTA {os.environ.get('CL_TIMELINE_CTA', '0')})")
     d = np.zeros((L - 2, 14))
     for l in range(1, L - 1):
