@@ -52,15 +52,17 @@ __device__ __forceinline__ void tile_range(int ntiles, int unit, int& t0, int& t
 }
 
 // ---- grid-wide barrier among the consumer halves of all CTAs (producer warps do not take part) ----
-__device__ __forceinline__ void grid_barrier(unsigned* cnt, int tid) {
+__device__ __forceinline__ void grid_barrier(unsigned* cnt, int tid, volatile int* pause = nullptr) {
   asm volatile("bar.sync 1, 256;" ::: "memory");
   if (tid == 0) {
+    if (pause) *pause = 1;
     // release-increment without waiting for the atomic's return value, then poll
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
     const long long t0 = clock64();
     while (ld_acquire_u32(cnt) < gridDim.x) {
       if (clock64() - t0 > (1ll << 31)) __trap();
     }
+    if (pause) *pause = 0;
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
@@ -129,6 +131,10 @@ __device__ __forceinline__ void wait_slot(Ring& r, int st, Lookahead& la, const 
   for (uint32_t spins = 0; !mbar_try_wait(&r.empty[st], r.parity() ^ 1u); ++spins) {
     lookahead_step(la, a, mypos);
     if (spins > (1u << 22)) __trap();
+  }
+  if (a.pause_in_barrier) {
+    volatile int* pause = r.tile_id + 7;
+    for (uint32_t spins = 0; *pause; ++spins) if (spins > (1u << 26)) __trap();
   }
   for (uint32_t spins = 0; (int)(r.git - r.tail) >= a.max_flight; ++spins) {
     const uint32_t n = r.tail;
@@ -282,6 +288,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
+    tile_id[7] = 0;
     for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NW); }
     fence_barrier_init();
   }
@@ -364,6 +371,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
   const int cur_pg = bt[pos / P], cur_off = pos % P;
   const float scale2 = rsqrtf((float)HD) * LOG2E;
 
+  volatile int* pz = a.pause_in_barrier ? tile_id + 7 : nullptr;
   const bool stamp = a.tl != nullptr && blockIdx.x == (unsigned)a.tl_cta && tid == 0;
 #define CL_STAMP(k) do { if (stamp) a.tl[(size_t)l * 16 + (k)] = gtime_ns(); } while (0)
   for (int l = 0; l < a.n_layers; ++l) {
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
     {
       float gr[4][8], xr[4][8];
       load_gain<4, 4>(L.attn_norm, gr, warp, lane);
-      if (l > 0) grid_barrier(a.bars + (size_t)(l - 1) * 6 + 5, tid);   // previous layer's down-proj complete (h final)
+      if (l > 0) grid_barrier(a.bars + (size_t)(l - 1) * 6 + 5, tid, pz);   // previous layer's down-proj complete (h final)
       CL_STAMP(0);
       load_x_norm<4, 4>(h, gr, a.eps, ssw, xr, warp, lane);
       CL_STAMP(1);
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
           L.vpool[base + j + HALF] = __float2bfloat16_rn(v1);
         }
       }
-      grid_barrier(bars + 0, tid);
+      grid_barrier(bars + 0, tid, pz);
       CL_STAMP(3);
     }
     // ------------------------------------------------------------------ P1: split-KV attention partials
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
       }
     }
     CL_STAMP(4);
-    grid_barrier(bars + 1, tid);
+    grid_barrier(bars + 1, tid, pz);
     CL_STAMP(5);
     // ------------------------------------------------------------------ P2: combine slice, then o-proj + residual
     {
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
           if (lane == 0) xatt[o] = bf16_round(A / Ls);
         }
       }
-      grid_barrier(bars + 2, tid);
+      grid_barrier(bars + 2, tid, pz);
       CL_STAMP(6);
       float xr[4][8];
       load_x<4, 4>(xatt, xr, warp, lane);
@@ -580,7 +588,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
         const int row = ids[p >> 2] * 4 + (p & 3);
         atomicAdd(h + row, (part[p * 4] + part[p * 4 + 1]) + (part[p * 4 + 2] + part[p * 4 + 3]));   // RED: exactly one add per row and phase
       }
-      grid_barrier(bars + 3, tid);
+      grid_barrier(bars + 3, tid, pz);
       CL_STAMP(8);
     }
     // ------------------------------------------------------------------ P3: norm + gate|up + SiLU*mul
@@ -598,7 +606,7 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
         const float up = (pp[4] + pp[5]) + (pp[6] + pp[7]);
         act[ids[p >> 1] * 2 + (p & 1)] = bf16_round(gt / (1.0f + __expf(-gt)) * up);
       }
-      grid_barrier(bars + 4, tid);
+      grid_barrier(bars + 4, tid, pz);
       CL_STAMP(11);
     }
     // ------------------------------------------------------------------ P4: down + residual

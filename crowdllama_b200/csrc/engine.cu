@@ -373,7 +373,7 @@ int Engine::enqueue_step(int B, bool tail) {
     MegaArgs m;
     m.layers = d_mega_layers_; m.n_layers = L_; m.q_dim = q_dim_; m.qkv_dim = qkv_dim_; m.n_heads = cfg.n_heads; m.n_kv = cfg.n_kv_heads;
     m.nsplit = nsplit_; m.eps = cfg.rms_eps; m.rope = rope_; m.pos = d_pos_; m.block_tables = d_bt_; m.bt_stride = max_pages_per_seq_;
-    m.slots = d_slots_; m.h = d_h_; m.q = d_q_; m.attn_x = d_attn_; m.act = d_act_; m.part = d_attn_part_; m.bars = d_sync_; m.tile_ctr = d_sync_ + (size_t)L_ * 6; m.pf_ctr = d_sync_ + (size_t)L_ * 10; m.max_flight = env_int("CL_MEGA_MAX_FLIGHT", 2); m.pf_min = env_int("CL_MEGA_PF_MIN", 900); m.pf_budget = env_int("CL_MEGA_PF_BUDGET", 4096);
+    m.slots = d_slots_; m.h = d_h_; m.q = d_q_; m.attn_x = d_attn_; m.act = d_act_; m.part = d_attn_part_; m.bars = d_sync_; m.tile_ctr = d_sync_ + (size_t)L_ * 6; m.pf_ctr = d_sync_ + (size_t)L_ * 10; m.max_flight = env_int("CL_MEGA_MAX_FLIGHT", 2); m.pause_in_barrier = env_int("CL_MEGA_PAUSE", 1); m.pf_min = env_int("CL_MEGA_PF_MIN", 900); m.pf_budget = env_int("CL_MEGA_PF_BUDGET", 4096);
     m.tl = d_timeline_; m.tl_cta = env_int("CL_TIMELINE_CTA", 0);
     m.kv_layer_rows = (long long)n_pages_ * cfg.n_kv_heads * page_size_; m.kmap = kmap_; m.vmap = vmap_;
     CL_LAUNCH(launch_decode_mega(m, stream_));

@@ -135,6 +135,7 @@ struct MegaArgs {
   unsigned* bars = nullptr;            // [n_layers * 6] grid-barrier counters, zero at kernel start
   unsigned* tile_ctr = nullptr;        // [n_layers * 4] dynamic tile-scheduler counters, zero at kernel start
   unsigned* pf_ctr = nullptr;          // L2 lookahead frontier (one counter, zero at kernel start); nullptr = off
+  int pause_in_barrier = 0;            // producer issues no new copies while the consumers sit in a grid barrier
   int max_flight = 6;                  // cap on bulk copies in flight per CTA (<= ring slots)
   int pf_min = 296, pf_budget = 0;     // lookahead window in tiles ahead of a CTA's own demand position
   long long* tl = nullptr;             // debug: [n_layers][16] globaltimer stamps of CTA tl_cta
