@@ -8,43 +8,106 @@
 namespace cl {
 
 // h[slot] += sum_s ypart[s][b]  (fixed order);  xn[b] = bf16(rmsnorm(h[slot]) * gain)
-__global__ void __launch_bounds__(256) batch_resid_norm_kernel(float* __restrict__ h, int d, const float* __restrict__ ypart, int n_split,
-                                                               int B, const float* __restrict__ gain, float eps,
-                                                               __nv_bfloat16* __restrict__ xn, const int* __restrict__ slots) {
-  __shared__ float red[8];
+// one CTA of 1024 threads per sequence: every thread owns <= 2 float4 of the row, all loads of a pass are independent
+__global__ void __launch_bounds__(1024) batch_resid_norm_kernel(float* __restrict__ h, int d, const float* __restrict__ ypart, int n_split,
+                                                                int B, const float* __restrict__ gain, float eps,
+                                                                __nv_bfloat16* __restrict__ xn, const int* __restrict__ slots) {
+  __shared__ float red[32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* hr = h + (size_t)slots[b] * d;
+  float4 v[2], g[2];
   float ss = 0.f;
-  for (int i = tid * 4; i < d; i += 1024) {
-    float4 v = *reinterpret_cast<const float4*>(hr + i);
-    for (int s = 0; s < n_split; ++s) {
-      const float4 y = *reinterpret_cast<const float4*>(ypart + ((size_t)s * B + b) * d + i);
-      v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = (tid + r * 1024) * 4;
+    v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    g[r] = v[r];
+    if (i < d) {
+      v[r] = *reinterpret_cast<const float4*>(hr + i);
+      g[r] = *reinterpret_cast<const float4*>(gain + i);
+      float4 y[8];
+      for (int s0 = 0; s0 < n_split; s0 += 8) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          y[s] = s0 + s < n_split ? __ldcg(reinterpret_cast<const float4*>(ypart + ((size_t)(s0 + s) * B + b) * d + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) { v[r].x += y[s].x; v[r].y += y[s].y; v[r].z += y[s].z; v[r].w += y[s].w; }
+      }
+      if (n_split > 0) *reinterpret_cast<float4*>(hr + i) = v[r];
     }
-    if (n_split > 0) *reinterpret_cast<float4*>(hr + i) = v;
-    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    ss = fmaf(v[r].x, v[r].x, ss); ss = fmaf(v[r].y, v[r].y, ss); ss = fmaf(v[r].z, v[r].z, ss); ss = fmaf(v[r].w, v[r].w, ss);
   }
   ss = warp_sum(ss);
   if (lane == 0) red[warp] = ss;
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) tot += red[w];
+  for (int w = 0; w < 32; ++w) tot += red[w];
   const float inv = 1.0f / sqrtf(tot / (float)d + eps);
-  __nv_bfloat16* o = xn + (size_t)b * d;
-  for (int i = tid * 4; i < d; i += 1024) {
-    const float4 v = *reinterpret_cast<const float4*>(hr + i);   // own writes: same thread, same addresses
-    const float4 g = *reinterpret_cast<const float4*>(gain + i);
-    uint2 pk;
-    pk.x = pack_bf16(v.x * inv * g.x, v.y * inv * g.y);
-    pk.y = pack_bf16(v.z * inv * g.z, v.w * inv * g.w);
-    *reinterpret_cast<uint2*>(o + i) = pk;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = (tid + r * 1024) * 4;
+    if (i < d) {
+      uint2 pk;
+      pk.x = pack_bf16(v[r].x * inv * g[r].x, v[r].y * inv * g[r].y);
+      pk.y = pack_bf16(v[r].z * inv * g[r].z, v[r].w * inv * g[r].w);
+      *reinterpret_cast<uint2*>(xn + (size_t)b * d + i) = pk;
+    }
   }
 }
 int launch_batch_resid_norm(float* h, int d, const float* ypart, int n_split, int B, const float* gain, float eps, __nv_bfloat16* xn,
                             const int* slots, cudaStream_t st) {
-  batch_resid_norm_kernel<<<B, 256, 0, st>>>(h, d, ypart, n_split, B, gain, eps, xn, slots);
+  if (d > 8192 || d % 4) return -1;
+  batch_resid_norm_kernel<<<B, 1024, 0, st>>>(h, d, ypart, n_split, B, gain, eps, xn, slots);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// xn[b] = bf16(rmsnorm(h[slots[b]]) * gain): one CTA of 1024 threads per sequence, one float4 per thread and pass
+__global__ void __launch_bounds__(1024) batch_norm_kernel(const float* __restrict__ h, int d, const float* __restrict__ gain, float eps,
+                                                          __nv_bfloat16* __restrict__ xn, const int* __restrict__ slots) {
+  __shared__ float red[32];
+  pdl_launch_dependents();
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4 g[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) { const int i = (tid + r * 1024) * 4; g[r] = i < d ? *reinterpret_cast<const float4*>(gain + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+  pdl_wait();
+  const float* hr = h + (size_t)slots[b] * d;
+  float4 v[2];
+  float ss = 0.f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = (tid + r * 1024) * 4;
+    v[r] = i < d ? ldcg4(hr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss = fmaf(v[r].x, v[r].x, ss); ss = fmaf(v[r].y, v[r].y, ss); ss = fmaf(v[r].z, v[r].z, ss); ss = fmaf(v[r].w, v[r].w, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 32; ++w) tot += red[w];
+  const float inv = 1.0f / sqrtf(tot / (float)d + eps);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = (tid + r * 1024) * 4;
+    if (i < d) {
+      uint2 pk;
+      pk.x = pack_bf16(v[r].x * inv * g[r].x, v[r].y * inv * g[r].y);
+      pk.y = pack_bf16(v[r].z * inv * g[r].z, v[r].w * inv * g[r].w);
+      *reinterpret_cast<uint2*>(xn + (size_t)b * d + i) = pk;
+    }
+  }
+}
+int launch_batch_norm(const float* h, int d, int B, const float* gain, float eps, __nv_bfloat16* xn, const int* slots, cudaStream_t st, bool pdl) {
+  if (d > 8192 || d % 4) return -1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(B); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, batch_norm_kernel, h, d, gain, eps, xn, slots) == cudaSuccess ? 1 : -1;
 }
 
 // q|k|v partials (rope-pair-interleaved columns) -> RoPE at pos[slot] -> q (fp32, bf16-rounded) and the paged cache

@@ -729,7 +729,9 @@ __global__ void __launch_bounds__(288) attn_decode_kernel(const AttnDecodeArgs a
     float A = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) A += red_acc[w][hh][i];
-    out[(size_t)(g * REP + hh) * HD + i] = bf16_round(A / cL_s[hh]);
+    const float r = bf16_round(A / cL_s[hh]);
+    out[(size_t)(g * REP + hh) * HD + i] = r;
+    if (a.out_bf16) a.out_bf16[(size_t)b * a.out_stride + (size_t)(g * REP + hh) * HD + i] = __float2bfloat16_rn(r);
   }
 }
 

@@ -101,7 +101,7 @@ def gemm_sweep(f):
 
 def batch_sweep(f, preset="llama3-8b", ctx=1024, steps=64):
     """Continuous-batching inner loop: B sequences advance together (cl_decode_greedy_batch)."""
-    for B in (1, 2, 4, 8):
+    for B in [int(x) for x in os.environ.get("CL_BATCH_LIST", "1,2,4,8").split(",")]:
         try:
             with eng.Engine(preset=preset, seed=1234, max_batch=B) as e:
                 V = e.cfg["vocab_size"]
