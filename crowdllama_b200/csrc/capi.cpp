@@ -115,8 +115,8 @@ int cl_engine_set_tensor(cl_engine* e, int32_t layer, int32_t kind, const uint16
   return e->impl.set_tensor(layer, kind, data, n);
 }
 
-#define CL_GUARD(body)                                  \
-  try { body }                                          \
+#define CL_GUARD(...)                                   \
+  try { __VA_ARGS__ }                                        \
   catch (const std::exception& ex) { set_last_error(ex.what()); return CL_ERR_INTERNAL; }
 
 int cl_generate_ids(cl_engine* e, const int32_t* prompt_ids, int32_t n_prompt, const cl_sampling* s, cl_result* out) {
@@ -126,19 +126,101 @@ int cl_generate_ids(cl_engine* e, const int32_t* prompt_ids, int32_t n_prompt, c
   CL_GUARD(return e->impl.generate_ids(prompt_ids, n_prompt, sp, out);)
 }
 
-int cl_generate(cl_engine* e, const char* model, const char* prompt, size_t prompt_len, const cl_sampling* s, cl_result* out) {
-  if (!e || !prompt || !out) return CL_ERR_INVALID_ARG;
+namespace {
+// incremental detokeniser: emits only text that later tokens cannot change (an incomplete UTF-8 tail is held back)
+struct StreamText {
+  const Tokenizer* tok;
+  std::vector<int32_t> ids;
+  size_t emitted = 0;       // bytes of sanitised text already handed out
+  std::string feed(const int32_t* fresh, int n, bool final) {
+    ids.insert(ids.end(), fresh, fresh + n);
+    std::string raw = tok->decode_bytes(ids);
+    size_t cut = raw.size();
+    if (!final) {
+      for (size_t back = 1; back <= 3 && back <= raw.size(); ++back) {
+        const unsigned char c = (unsigned char)raw[raw.size() - back];
+        if ((c >> 6) == 2) continue;                                   // continuation byte: keep looking for the lead
+        const size_t need = (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1;
+        if (need > back) cut = raw.size() - back;                      // lead byte of a sequence that is still open
+        break;
+      }
+    }
+    const std::string stable = Tokenizer::sanitize(raw.substr(0, cut));
+    std::string delta = stable.size() > emitted ? stable.substr(emitted) : std::string();
+    emitted = std::max(emitted, stable.size());
+    return delta;
+  }
+};
+struct TextSinkCtx { StreamText st; cl_token_cb cb; void* user; };
+int text_sink(void* u, const int32_t* ids, int n) {
+  auto* c = (TextSinkCtx*)u;
+  const std::string delta = c->st.feed(ids, n, false);
+  return c->cb(c->user, delta.data(), delta.size(), ids, n);
+}
+int64_t wall_ns() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+}
+std::vector<uint8_t> response_frame(const std::string& model, const std::string& text, bool done, const std::string& reason) {
+  PbGenerateResponse pr;
+  pr.model = model;
+  const int64_t ns = wall_ns();
+  pr.created_at_sec = ns / 1000000000ll;
+  pr.created_at_nanos = (int32_t)(ns % 1000000000ll);
+  pr.response = text;
+  pr.done = done;
+  pr.done_reason = reason;
+  pr.worker_id = "worker";                 // api.go:83 (literal in the reference)
+  pr.total_duration = done ? ns : 0;       // api.go:84: the reference stores time.Now().UnixNano() here
+  return pb_encode_response(pr);
+}
+struct FrameSinkCtx { StreamText st; cl_frame_cb cb; void* user; std::string model; };
+int frame_sink(void* u, const int32_t* ids, int n) {
+  auto* c = (FrameSinkCtx*)u;
+  const std::string delta = c->st.feed(ids, n, false);
+  if (delta.empty()) return 0;
+  const std::vector<uint8_t> f = response_frame(c->model, delta, false, "");
+  return c->cb(c->user, f.data(), f.size());
+}
+int check_model(cl_engine* e, const char* model) {
   // exact string match, like Resource.SupportedModels (manager.go:349-354)
   if (model && *model && e->impl.model_name != model) {
     set_last_error(std::string("model '") + model + "' is not served (serving '" + e->impl.model_name + "')");
     return CL_ERR_UNKNOWN_MODEL;
   }
+  return CL_OK;
+}
+std::vector<int32_t> prompt_ids(cl_engine* e, const char* prompt, size_t prompt_len, bool raw) {
+  const std::string user(prompt, prompt_len);
+  return e->impl.tok->encode(raw ? user : e->impl.tok->apply_chat_template(user), true);
+}
+}  // namespace
+
+int cl_generate(cl_engine* e, const char* model, const char* prompt, size_t prompt_len, const cl_sampling* s, cl_result* out) {
+  if (!e || !prompt || !out) return CL_ERR_INVALID_ARG;
+  if (int rc = check_model(e, model)) return rc;
   CL_GUARD(
-    const std::string text = e->impl.tok->apply_chat_template(std::string(prompt, prompt_len));
-    std::vector<int32_t> ids = e->impl.tok->encode(text, true);
+    std::vector<int32_t> ids = prompt_ids(e, prompt, prompt_len, false);
     cl_sampling sp;
     if (s) sp = *s; else cl_default_sampling(&sp);
     return e->impl.generate_ids(ids.data(), (int)ids.size(), sp, out);
+  )
+}
+
+int cl_generate_stream(cl_engine* e, const char* model, const char* prompt, size_t prompt_len, const cl_sampling* s, cl_token_cb cb,
+                       void* user, cl_result* out) {
+  if (!e || !prompt || !out || !cb) return CL_ERR_INVALID_ARG;
+  if (int rc = check_model(e, model)) return rc;
+  CL_GUARD(
+    std::vector<int32_t> ids = prompt_ids(e, prompt, prompt_len, false);
+    cl_sampling sp;
+    if (s) sp = *s; else cl_default_sampling(&sp);
+    TextSinkCtx ctx{StreamText{e->impl.tok.get(), {}, 0}, cb, user};
+    Engine::TokenSink sink{text_sink, &ctx};
+    const int rc = e->impl.generate_ids(ids.data(), (int)ids.size(), sp, out, &sink);
+    if (rc) return rc;
+    const std::string tail = ctx.st.feed(nullptr, 0, true);   // whatever the UTF-8 hold-back kept
+    if (!tail.empty()) cb(user, tail.data(), tail.size(), nullptr, 0);
+    return CL_OK;
   )
 }
 
@@ -150,37 +232,63 @@ void cl_result_free(cl_result* r) {
   memset(r, 0, sizeof *r);
 }
 
+static int handle_message_impl(cl_engine* e, const uint8_t* req, size_t req_len, const cl_sampling* s, cl_frame_cb cb, void* user,
+                               bool allow_stream) {
+  PbGenerateRequest gr;
+  if (!pb_decode_request(req, req_len, &gr)) {
+    set_last_error("expected GenerateRequest, got different message type");  // api.go:50
+    return CL_ERR_BAD_MESSAGE;
+  }
+  if (int rc = check_model(e, gr.model.c_str())) return rc;
+  cl_sampling sp;
+  if (s) sp = *s; else cl_default_sampling(&sp);
+  apply_options(gr.opt, &sp);                                   // request options win over the worker's defaults
+  std::vector<int32_t> ids = prompt_ids(e, gr.prompt.data(), gr.prompt.size(), gr.opt.raw);
+  cl_result r;
+  if (gr.stream && allow_stream) {
+    // streaming: Done=false frames carrying text deltas, then one Done=true frame
+    FrameSinkCtx ctx{StreamText{e->impl.tok.get(), {}, 0}, cb, user, gr.model};
+    Engine::TokenSink sink{frame_sink, &ctx};
+    const int rc = e->impl.generate_ids(ids.data(), (int)ids.size(), sp, &r, &sink);
+    if (rc) return rc;
+    const std::string tail = ctx.st.feed(nullptr, 0, true);
+    const std::vector<uint8_t> f = response_frame(gr.model, tail, true, r.done_reason);
+    cl_result_free(&r);
+    cb(user, f.data(), f.size());
+    return CL_OK;
+  }
+  const int rc = e->impl.generate_ids(ids.data(), (int)ids.size(), sp, &r);
+  if (rc) return rc;
+  const std::vector<uint8_t> f = response_frame(gr.model, std::string(r.text, r.text_len), true, r.done_reason);
+  cl_result_free(&r);
+  cb(user, f.data(), f.size());
+  return CL_OK;
+}
+
+static int collect_frame(void* user, const uint8_t* msg, size_t len) {
+  auto* v = (std::vector<uint8_t>*)user;
+  v->assign(msg, msg + len);
+  return 0;
+}
+
 int cl_handle_message(cl_engine* e, const uint8_t* req, size_t req_len, const cl_sampling* s, uint8_t** resp, size_t* resp_len) {
   if (!e || !req || !resp || !resp_len) return CL_ERR_INVALID_ARG;
   *resp = nullptr;
   *resp_len = 0;
   CL_GUARD(
-    PbGenerateRequest gr;
-    if (!pb_decode_request(req, req_len, &gr)) {
-      set_last_error("expected GenerateRequest, got different message type");  // api.go:50
-      return CL_ERR_BAD_MESSAGE;
-    }
-    cl_result r;
-    const int rc = cl_generate(e, gr.model.c_str(), gr.prompt.data(), gr.prompt.size(), s, &r);
+    std::vector<uint8_t> b;
+    const int rc = handle_message_impl(e, req, req_len, s, collect_frame, &b, false);   // one complete answer (api.go:77-92)
     if (rc) return rc;
-    PbGenerateResponse pr;
-    pr.model = gr.model;
-    const auto now = std::chrono::system_clock::now().time_since_epoch();
-    const int64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(now).count();
-    pr.created_at_sec = ns / 1000000000ll;
-    pr.created_at_nanos = (int32_t)(ns % 1000000000ll);
-    pr.response.assign(r.text, r.text_len);
-    pr.done = true;
-    pr.done_reason = r.done_reason;
-    pr.worker_id = "worker";       // api.go:83 (literal in the reference)
-    pr.total_duration = ns;        // api.go:84: the reference stores time.Now().UnixNano() here
-    cl_result_free(&r);
-    std::vector<uint8_t> b = pb_encode_response(pr);
     *resp = (uint8_t*)malloc(b.size() ? b.size() : 1);
     memcpy(*resp, b.data(), b.size());
     *resp_len = b.size();
     return CL_OK;
   )
+}
+
+int cl_handle_message_stream(cl_engine* e, const uint8_t* req, size_t req_len, const cl_sampling* s, cl_frame_cb cb, void* user) {
+  if (!e || !req || !cb) return CL_ERR_INVALID_ARG;
+  CL_GUARD(return handle_message_impl(e, req, req_len, s, cb, user, true);)
 }
 
 void cl_buffer_free(void* p) { free(p); }

@@ -55,7 +55,9 @@ class Tokenizer {
   explicit Tokenizer(int vocab_size) : vocab_(vocab_size) {}
   // ids 0..2 = <pad>, <bos>, <eos>; byte b -> 3 + b.  Needs vocab >= 259.
   std::vector<int32_t> encode(const std::string& text, bool add_bos) const;
-  std::string decode(const std::vector<int32_t>& ids) const;
+  std::string decode(const std::vector<int32_t>& ids) const;        // = sanitize(decode_bytes(ids))
+  std::string decode_bytes(const std::vector<int32_t>& ids) const;  // raw surface bytes (may cut a UTF-8 sequence)
+  static std::string sanitize(const std::string& raw);              // invalid UTF-8 / control bytes -> U+FFFD
   int bos() const { return 1; }
   int eos() const { return 2; }
   // chat framing the Ollama server applies upstream of the model (role forced to "user",
@@ -71,7 +73,17 @@ int32_t sample_token(const float* logits, int32_t vocab, const cl_sampling& sp, 
                      uint64_t step);
 
 // ---- minimal protobuf codec for llama.v1.BaseMessage (pbmsg.cpp) -------------------------------
-struct PbGenerateRequest { std::string model, prompt; bool stream = false; };
+// GenerateOptions: the proto extension SURVEY.md §8f row 3 asks for (seed / temperature / num_predict ... are
+// inexpressible on the reference's wire, api.go:193-197).  Every field has explicit presence: temperature 0
+// (greedy) must be distinguishable from "not set".
+struct PbGenerateOptions {
+  uint32_t has = 0;   // bit i set <=> field number i present
+  uint64_t seed = 0; float temperature = 0.f; int32_t top_k = 0; float top_p = 0.f; float repeat_penalty = 0.f;
+  int32_t repeat_last_n = 0; int32_t num_predict = 0; bool raw = false;
+};
+struct PbGenerateRequest { std::string model, prompt; bool stream = false; PbGenerateOptions opt; };
+// request options override the caller's default sampling field by field
+void apply_options(const PbGenerateOptions& o, cl_sampling* sp);
 struct PbGenerateResponse {
   std::string model, response, done_reason, worker_id;
   int64_t created_at_sec = 0; int32_t created_at_nanos = 0;
@@ -117,7 +129,9 @@ class Engine {
   int stats(cl_stats* out);
 
   // request-level (scheduler.cpp)
-  int generate_ids(const int32_t* prompt, int n_prompt, const cl_sampling& sp, cl_result* out);
+  // sink (optional): called on the CALLING thread with every batch of newly generated ids; nonzero return cancels
+  struct TokenSink { int (*fn)(void* user, const int32_t* ids, int n) = nullptr; void* user = nullptr; };
+  int generate_ids(const int32_t* prompt, int n_prompt, const cl_sampling& sp, cl_result* out, const TokenSink* sink = nullptr);
   void scheduler_main();
   void start_scheduler();
   void stop_scheduler();

@@ -57,7 +57,7 @@ std::vector<int32_t> Tokenizer::encode(const std::string& text, bool add_bos) co
   }
   return ids;
 }
-std::string Tokenizer::decode(const std::vector<int32_t>& ids) const {
+std::string Tokenizer::decode_bytes(const std::vector<int32_t>& ids) const {
   std::string out;
   for (int32_t id : ids) {
     if (id >= 3 && id < 259) out.push_back((char)(id - 3));
@@ -70,7 +70,10 @@ std::string Tokenizer::decode(const std::vector<int32_t>& ids) const {
       out += buf;
     }
   }
-  // bytes produced by a random-weight model are not valid UTF-8 in general: sanitise
+  return out;
+}
+// bytes produced by a random-weight model are not valid UTF-8 in general: sanitise
+std::string Tokenizer::sanitize(const std::string& out) {
   std::string clean;
   clean.reserve(out.size());
   for (size_t i = 0; i < out.size();) {
@@ -84,6 +87,7 @@ std::string Tokenizer::decode(const std::vector<int32_t>& ids) const {
   }
   return clean;
 }
+std::string Tokenizer::decode(const std::vector<int32_t>& ids) const { return sanitize(decode_bytes(ids)); }
 std::string Tokenizer::apply_chat_template(const std::string& user_prompt) const {
   return "<|user|>\n" + user_prompt + "\n<|assistant|>\n";
 }
@@ -149,11 +153,17 @@ int32_t sample_token(const float* logits, int32_t vocab, const cl_sampling& sp, 
 // kept in this one table (declaration order of the Go struct literals at api.go:77-85,193-197):
 //   BaseMessage      { oneof message { GenerateRequest generate_request = 1;
 //                                       GenerateResponse generate_response = 2; } }
-//   GenerateRequest  { string model = 1; string prompt = 2; bool stream = 3; }
+//   GenerateRequest  { string model = 1; string prompt = 2; bool stream = 3;
+//                      GenerateOptions options = 4; }                       <- EXTENSION
+//   GenerateOptions  { optional uint64 seed = 1; optional float temperature = 2; optional int32 top_k = 3;
+//                      optional float top_p = 4; optional float repeat_penalty = 5;
+//                      optional int32 repeat_last_n = 6; optional int32 num_predict = 7; optional bool raw = 8; }
 //   GenerateResponse { string model = 1; google.protobuf.Timestamp created_at = 2;
 //                      string response = 3; bool done = 4; string done_reason = 5;
 //                      string worker_id = 6; int64 total_duration = 7; }
 // ================================================================================================
+enum { kReqOptions = 4, kOptSeed = 1, kOptTemperature = 2, kOptTopK = 3, kOptTopP = 4, kOptRepeatPenalty = 5, kOptRepeatLastN = 6,
+       kOptNumPredict = 7, kOptRaw = 8 };
 enum { kBaseReq = 1, kBaseResp = 2, kReqModel = 1, kReqPrompt = 2, kReqStream = 3, kRespModel = 1, kRespCreated = 2,
        kRespResponse = 3, kRespDone = 4, kRespDoneReason = 5, kRespWorkerId = 6, kRespTotalDuration = 7 };
 
@@ -175,6 +185,40 @@ static bool skip_field(const uint8_t*& p, const uint8_t* end, int wt) {
     case 5: if (end - p < 4) return false; p += 4; return true;
     default: return false;
   }
+}
+static bool decode_options(const uint8_t* q, const uint8_t* qe, PbGenerateOptions* o) {
+  while (q < qe) {
+    uint64_t k;
+    if (!rd_varint(q, qe, &k)) return false;
+    const int f = (int)(k >> 3), wt = (int)(k & 7);
+    if (wt == 0 && (f == kOptSeed || f == kOptTopK || f == kOptRepeatLastN || f == kOptNumPredict || f == kOptRaw)) {
+      uint64_t v;
+      if (!rd_varint(q, qe, &v)) return false;
+      if (f == kOptSeed) o->seed = v;
+      else if (f == kOptTopK) o->top_k = (int32_t)(int64_t)v;
+      else if (f == kOptRepeatLastN) o->repeat_last_n = (int32_t)(int64_t)v;
+      else if (f == kOptNumPredict) o->num_predict = (int32_t)(int64_t)v;
+      else o->raw = v != 0;
+      o->has |= 1u << f;
+    } else if (wt == 5 && (f == kOptTemperature || f == kOptTopP || f == kOptRepeatPenalty)) {
+      if (qe - q < 4) return false;
+      float v;
+      memcpy(&v, q, 4);
+      q += 4;
+      if (f == kOptTemperature) o->temperature = v; else if (f == kOptTopP) o->top_p = v; else o->repeat_penalty = v;
+      o->has |= 1u << f;
+    } else if (!skip_field(q, qe, wt)) return false;
+  }
+  return true;
+}
+void apply_options(const PbGenerateOptions& o, cl_sampling* sp) {
+  if (o.has & (1u << kOptSeed)) sp->seed = o.seed;
+  if (o.has & (1u << kOptTemperature)) sp->temperature = o.temperature;
+  if (o.has & (1u << kOptTopK)) sp->top_k = o.top_k;
+  if (o.has & (1u << kOptTopP)) sp->top_p = o.top_p;
+  if (o.has & (1u << kOptRepeatPenalty)) sp->repeat_penalty = o.repeat_penalty;
+  if (o.has & (1u << kOptRepeatLastN)) sp->repeat_last_n = o.repeat_last_n;
+  if (o.has & (1u << kOptNumPredict)) sp->max_new_tokens = o.num_predict;
 }
 bool pb_decode_request(const uint8_t* data, size_t len, PbGenerateRequest* out) {
   const uint8_t* p = data; const uint8_t* end = data + len;
@@ -203,6 +247,11 @@ bool pb_decode_request(const uint8_t* data, size_t len, PbGenerateRequest* out) 
           uint64_t v;
           if (!rd_varint(q, qe, &v)) return false;
           out->stream = v != 0;
+        } else if (f2 == kReqOptions && w2 == 2) {
+          uint64_t m;
+          if (!rd_varint(q, qe, &m) || (uint64_t)(qe - q) < m) return false;
+          if (!decode_options(q, q + m, &out->opt)) return false;
+          q += m;
         } else if (!skip_field(q, qe, w2)) return false;
       }
     } else if (!skip_field(p, end, wt)) return false;

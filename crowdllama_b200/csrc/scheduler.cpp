@@ -30,6 +30,11 @@ struct Request {
   bool done = false;
   std::mutex m;
   std::condition_variable cv;
+  // streaming: ids the scheduler has published to the waiting client thread (guarded by m); `out` itself is only
+  // read by the client after `done`
+  bool streaming = false;
+  std::vector<int32_t> pub;
+  std::atomic<bool> cancel{false};
   int64_t t_arrive = 0, prefill_ns = 0, decode_ns = 0, t_done = 0;
   uint64_t arrival = 0;
   bool greedy() const { return sp.temperature <= 0.f; }
@@ -52,7 +57,15 @@ static void fill_result(const Request& r, cl_result* out, const Tokenizer* tok) 
   out->n_preempted = r.n_preempted;
 }
 
+static void publish(Request& r, int32_t id) {
+  if (!r.streaming) return;
+  std::lock_guard<std::mutex> lk(r.m);
+  r.pub.push_back(id);
+  r.cv.notify_all();
+}
+
 static bool finished(Request& r, int eos, int max_seq_len) {
+  if (r.cancel.load(std::memory_order_relaxed)) { r.done_reason = "cancelled"; return true; }
   if (!r.out.empty() && !r.sp.ignore_eos && r.out.back() == eos) { r.done_reason = "stop"; return true; }
   if ((int)r.out.size() >= r.max_new) { r.done_reason = "length"; return true; }
   if ((int)(r.prompt.size() + r.out.size()) >= max_seq_len) { r.done_reason = "length"; return true; }
@@ -60,7 +73,13 @@ static bool finished(Request& r, int eos, int max_seq_len) {
 }
 
 // ---- synchronous path (no scheduler thread): one request at a time under the engine lock --------
-static int generate_sync(Engine& e, Request& r) {
+static int generate_sync(Engine& e, Request& r, const Engine::TokenSink* sink) {
+  size_t emitted = 0;
+  auto emit = [&]() {
+    if (!sink || !sink->fn || r.out.size() <= emitted) return;
+    if (sink->fn(sink->user, r.out.data() + emitted, (int)(r.out.size() - emitted))) r.cancel = true;
+    emitted = r.out.size();
+  };
   std::lock_guard<std::mutex> lk(e.mu_);
   const int V = e.cfg.vocab_size;
   int rc = e.seq_create(&r.seq);
@@ -74,10 +93,11 @@ static int generate_sync(Engine& e, Request& r) {
   std::vector<int32_t> hist(r.prompt);
   int32_t next = sample_token(logits.data(), V, r.sp, hist.data(), (int)hist.size(), 0);
   r.out.push_back(next);
+  emit();
   while (!finished(r, e.tok->eos(), e.cfg.max_seq_len)) {
     if (r.greedy()) {
       int room = std::min(r.max_new - (int)r.out.size(), e.cfg.max_seq_len - (int)(r.prompt.size() + r.out.size()));
-      int chunk = std::min(room, 32);
+      int chunk = std::min(room, sink ? 8 : 32);
       std::vector<int32_t> ids(chunk);
       rc = e.decode_greedy(&r.seq, 1, &next, chunk, ids.data(), nullptr);
       if (rc) break;
@@ -93,6 +113,7 @@ static int generate_sync(Engine& e, Request& r) {
       next = sample_token(logits.data(), V, r.sp, hist.data(), (int)hist.size(), (uint64_t)r.out.size());
       r.out.push_back(next);
     }
+    emit();
   }
   r.decode_ns = now_ns() - t0;
   e.seq_free(r.seq);
@@ -100,7 +121,7 @@ static int generate_sync(Engine& e, Request& r) {
   return rc;
 }
 
-int Engine::generate_ids(const int32_t* prompt, int n_prompt, const cl_sampling& sp, cl_result* out) {
+int Engine::generate_ids(const int32_t* prompt, int n_prompt, const cl_sampling& sp, cl_result* out, const TokenSink* sink) {
   if (!prompt || n_prompt <= 0 || !out) { set_last_error("empty prompt"); return CL_ERR_INVALID_ARG; }
   if (n_prompt >= cfg.max_seq_len) { set_last_error("prompt longer than max_seq_len"); return CL_ERR_TOO_LONG; }
   for (int i = 0; i < n_prompt; ++i)
@@ -111,8 +132,9 @@ int Engine::generate_ids(const int32_t* prompt, int n_prompt, const cl_sampling&
   r->max_new = sp.max_new_tokens > 0 ? sp.max_new_tokens : cfg.max_seq_len - n_prompt;
   r->max_new = std::min(r->max_new, cfg.max_seq_len - n_prompt);
   r->t_arrive = now_ns();
+  r->streaming = sink && sink->fn;
   if (!sched_started_) {
-    r->status = generate_sync(*this, *r);
+    r->status = generate_sync(*this, *r, sink);
     if (r->status == CL_OK) { requests_completed_++; tokens_generated_ += (int64_t)r->out.size(); }
   } else {
     {
@@ -124,7 +146,20 @@ int Engine::generate_ids(const int32_t* prompt, int n_prompt, const cl_sampling&
     }
     q_cv_.notify_all();
     std::unique_lock<std::mutex> lk(r->m);
-    r->cv.wait(lk, [&] { return r->done; });
+    size_t seen = 0;
+    std::vector<int32_t> fresh;
+    while (true) {
+      r->cv.wait(lk, [&] { return r->done || r->pub.size() > seen; });
+      if (r->pub.size() > seen) {
+        fresh.assign(r->pub.begin() + seen, r->pub.end());
+        seen = r->pub.size();
+        lk.unlock();                       // the callback runs on this (the caller's) thread, outside every lock
+        if (sink->fn(sink->user, fresh.data(), (int)fresh.size())) r->cancel = true;
+        lk.lock();
+        continue;
+      }
+      if (r->done) break;
+    }
   }
   r->t_done = now_ns();
   if (r->status != CL_OK) {
@@ -203,6 +238,7 @@ void Engine::scheduler_main() {
       if (rc) { seq_free(r->seq); complete(r, rc, get_last_error()); continue; }
       const int32_t next = sample_token(logits.data(), V, r->sp, full.data(), (int)full.size(), (uint64_t)r->out.size());
       r->out.push_back(next);
+      publish(*r, next);
       if (!r->greedy()) cudaMemcpyAsync(d_tok_ + r->seq, &r->out.back(), 4, cudaMemcpyHostToDevice, stream_);
       if (finished(*r, tok->eos(), cfg.max_seq_len)) {
         seq_free(r->seq);
@@ -276,6 +312,7 @@ void Engine::scheduler_main() {
         cudaStreamSynchronize(stream_);
       }
       r->out.push_back(next);
+      publish(*r, next);
     }
     const int64_t dt = now_ns() - t0;
     for (auto& r : active_) r->decode_ns += dt;

@@ -63,8 +63,8 @@ class Stats(C.Structure):
 EXPORTS = [
     "cl_abi_version", "cl_strerror", "cl_last_error", "cl_default_engine_config", "cl_default_sampling",
     "cl_greedy_sampling", "cl_model_preset", "cl_engine_create", "cl_engine_destroy", "cl_engine_model_config",
-    "cl_engine_stats", "cl_engine_set_tensor", "cl_generate", "cl_generate_ids", "cl_result_free",
-    "cl_handle_message", "cl_buffer_free", "cl_tokenize", "cl_detokenize", "cl_seq_create", "cl_seq_free",
+    "cl_engine_stats", "cl_engine_set_tensor", "cl_generate", "cl_generate_ids", "cl_generate_stream", "cl_result_free",
+    "cl_handle_message", "cl_handle_message_stream", "cl_buffer_free", "cl_tokenize", "cl_detokenize", "cl_seq_create", "cl_seq_free",
     "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_debug_hidden", "cl_debug_timeline",
     "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_qkv_rope_append", "cl_op_attn_decode",
     "cl_op_gemm_bf16", "cl_op_gemm_skinny", "cl_op_attn_prefill", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
@@ -72,6 +72,11 @@ EXPORTS = [
 ]
 
 _lib = None
+
+
+# callback types of the streaming entry points (include/clengine.h: cl_token_cb, cl_frame_cb)
+TOKEN_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.c_int32)
+FRAME_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
 def lib():
@@ -99,6 +104,8 @@ def lib():
         "cl_engine_set_tensor": (C.c_int, [vp, i32, i32, vp, i64]),
         "cl_generate": (C.c_int, [vp, C.c_char_p, C.c_char_p, sz, P(Sampling), P(Result)]),
         "cl_generate_ids": (C.c_int, [vp, vp, i32, P(Sampling), P(Result)]),
+        "cl_generate_stream": (C.c_int, [vp, C.c_char_p, C.c_char_p, sz, P(Sampling), TOKEN_CB, vp, P(Result)]),
+        "cl_handle_message_stream": (C.c_int, [vp, C.c_char_p, sz, P(Sampling), FRAME_CB, vp]),
         "cl_result_free": (None, [P(Result)]),
         "cl_handle_message": (C.c_int, [vp, C.c_char_p, sz, P(Sampling), P(vp), P(sz)]),
         "cl_buffer_free": (None, [vp]),
@@ -330,6 +337,44 @@ class Engine:
             return GenerateResult(r)
         finally:
             lib().cl_result_free(C.byref(r))
+
+    def generate_stream(self, model: str, prompt: str, sampling: Sampling | None = None, on_text=None) -> GenerateResult:
+        """cl_generate_stream: on_text(text_delta: str, ids: list[int]) is called on this thread as tokens arrive;
+        a truthy return cancels the request."""
+        r = Result()
+        p = prompt.encode("utf-8")
+
+        def cb(user, text, text_len, ids, n_ids):
+            try:
+                delta = C.string_at(text, text_len).decode("utf-8", "replace") if text_len else ""
+                new = [ids[i] for i in range(n_ids)] if n_ids else []
+                return 1 if (on_text and on_text(delta, new)) else 0
+            except Exception:       # never unwind through the C frames
+                return 1
+
+        cfn = TOKEN_CB(cb)
+        _check(lib().cl_generate_stream(self._h, model.encode(), p, len(p), C.byref(sampling) if sampling else None, cfn, None,
+                                        C.byref(r)), "cl_generate_stream")
+        try:
+            return GenerateResult(r)
+        finally:
+            lib().cl_result_free(C.byref(r))
+
+    def handle_message_stream(self, req: bytes, sampling: Sampling | None = None, on_frame=None) -> int:
+        """cl_handle_message_stream: on_frame(serialised BaseMessage) per response frame; returns the frame count."""
+        n = [0]
+
+        def cb(user, msg, length):
+            try:
+                n[0] += 1
+                return 1 if (on_frame and on_frame(C.string_at(msg, length))) else 0
+            except Exception:
+                return 1
+
+        cfn = FRAME_CB(cb)
+        _check(lib().cl_handle_message_stream(self._h, req, len(req), C.byref(sampling) if sampling else None, cfn, None),
+               "cl_handle_message_stream")
+        return n[0]
 
     def handle_message(self, req: bytes, sampling: Sampling | None = None) -> bytes:
         out, n = C.c_void_p(), C.c_size_t()

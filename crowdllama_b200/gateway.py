@@ -1,7 +1,9 @@
 """Gateway stand-in: the reference's Ollama-compatible HTTP façade, restated for the benchmark harness.
 
 Mirrors pkg/gateway/gateway.go: POST /api/chat (handleChat :168-231 → FindBestWorker :191 → RequestInference
-:243-293) and GET /api/health (:453-461).  Worker discovery (DHT provider lookup + metadata fetch,
+:243-293) and GET /api/health (:453-461).  SURVEY.md §8f rows 3-4 on top: POST /api/generate (BASELINE.json names
+it, the reference gateway lacks it, gateway.go:87-88), the Ollama `options` object passed through to the worker
+(GenerateRequest.options), and `"stream": true` answered as NDJSON lines (one per worker frame).  Worker discovery (DHT provider lookup + metadata fetch,
 internal/discovery/discovery.go:278-366) is replaced by a static address list whose metadata is polled
 over the metadata protocol — the routing rule itself (peermanager FindBestWorker) is `router.find_best_worker`.
 Quirks kept: only messages[0].content is forwarded (gateway.go:209); handler errors arrive as assistant
@@ -67,13 +69,19 @@ class PeerTable:
         return (by_id[w.peer_id], w) if w else (None, None)
 
 
-def request_inference(addr, model: str, prompt: str, stream: bool):
-    """Gateway.RequestInference (gateway.go:243-293) over the TCP stand-in for a libp2p stream."""
+def request_inference(addr, model: str, prompt: str, stream: bool, options=None, on_frame=None):
+    """Gateway.RequestInference (gateway.go:243-293) over the TCP stand-in for a libp2p stream.  With stream=True the
+    worker answers with several frames; on_frame sees each one and the last (Done=true) is returned."""
     with socket.create_connection(addr, timeout=600) as s:
         s.sendall((INFERENCE_PROTOCOL + "\n").encode())
         st = _Stream(s)
-        write_length_prefixed_pb(st, H.create_generate_request(model, prompt, stream))
-        return H.extract_generate_response(read_length_prefixed_pb(st))
+        write_length_prefixed_pb(st, H.create_generate_request(model, prompt, stream, options))
+        while True:
+            g = H.extract_generate_response(read_length_prefixed_pb(st))
+            if on_frame is not None:
+                on_frame(g)
+            if g.done or not stream:
+                return g
 
 
 class _Handler(BaseHTTPRequestHandler):
@@ -99,28 +107,83 @@ class _Handler(BaseHTTPRequestHandler):
             return self._json(200, {"status": "ok", "peers": peers})
         self._json(404, {"error": "not found"})
 
+    def _ndjson_start(self):
+        self.send_response(200)
+        self.send_header("Content-Type", "application/x-ndjson")
+        self.send_header("Transfer-Encoding", "chunked")
+        self.end_headers()
+
+    def _ndjson_line(self, obj):
+        body = json.dumps(obj).encode() + b"\n"
+        self.wfile.write(f"{len(body):x}\r\n".encode() + body + b"\r\n")
+        self.wfile.flush()
+
     def do_POST(self):
-        if self.path != "/api/chat":
+        chat = self.path == "/api/chat"
+        if not chat and self.path != "/api/generate":
             return self._json(404, {"error": "not found"})
         try:
             req = json.loads(self.rfile.read(int(self.headers.get("Content-Length", "0"))))
         except Exception:
             return self._json(400, {"error": "invalid JSON"})
-        model, messages = req.get("model"), req.get("messages") or []
-        if not model or not messages:                                     # gateway.go:175-188
-            return self._json(400, {"error": "model and messages are required"})
+        model = req.get("model")
+        if chat:
+            messages = req.get("messages") or []
+            if not model or not messages:                                 # gateway.go:175-188
+                return self._json(400, {"error": "model and messages are required"})
+            prompt = messages[0].get("content", "")                       # gateway.go:209: only the first message travels
+        else:
+            prompt = req.get("prompt")
+            if not model or prompt is None:
+                return self._json(400, {"error": "model and prompt are required"})
+        from .pb import GenerateOptions
+        options = GenerateOptions.from_json(req.get("options"))
+        if not chat and req.get("raw"):
+            options = options or GenerateOptions()
+            options.raw = True
+        stream = bool(req.get("stream", False))
         addr, worker = self.server.table.best(model)
         if worker is None:                                                # gateway.go:192-199
             return self._json(503, {"error": f"no available worker for model {model}"})
         with self.server.lock:
             self.server.counts[worker.peer_id] = self.server.counts.get(worker.peer_id, 0) + 1
+
+        def shape(g):
+            now = datetime.now(timezone.utc).isoformat()
+            if chat:
+                o = {"model": g.model or model, "created_at": now, "message": {"role": "assistant", "content": g.response},
+                     "done": g.done}
+            else:
+                o = {"model": g.model or model, "created_at": now, "response": g.response, "done": g.done}
+            if g.done:
+                o["done_reason"] = g.done_reason
+            return o
+
+        if stream:
+            started = [False]
+
+            def on_frame(g):
+                if not started[0]:
+                    self._ndjson_start()
+                    started[0] = True
+                self._ndjson_line(shape(g))
+
+            try:
+                request_inference(addr, model, prompt, True, options, on_frame)
+            except Exception as ex:
+                if not started[0]:
+                    return self._json(500, {"error": f"inference request failed: {ex}"})
+                self._ndjson_line({"error": f"inference request failed: {ex}", "done": True})
+            self.wfile.write(b"0\r\n\r\n")
+            return
         try:
-            g = request_inference(addr, model, messages[0].get("content", ""), bool(req.get("stream", False)))
+            g = request_inference(addr, model, prompt, False, options)
         except Exception as ex:                                           # gateway.go:210-217
             return self._json(500, {"error": f"inference request failed: {ex}"})
-        self._json(200, {"model": g.model or model, "created_at": datetime.now(timezone.utc).isoformat(),
-                         "message": {"role": "assistant", "content": g.response}, "stream": False,
-                         "done_reason": g.done_reason, "done": g.done})
+        o = shape(g)
+        o["stream"] = False
+        o.setdefault("done_reason", g.done_reason)
+        self._json(200, o)
 
 
 def make_server(worker_addrs, port: int = 9001, host: str = "127.0.0.1", seed: int = 0) -> ThreadingHTTPServer:

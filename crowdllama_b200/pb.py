@@ -11,7 +11,11 @@ from dataclasses import dataclass, field
 
 FIELDS = {
     "BaseMessage": {"generate_request": 1, "generate_response": 2},
-    "GenerateRequest": {"model": 1, "prompt": 2, "stream": 3},
+    "GenerateRequest": {"model": 1, "prompt": 2, "stream": 3, "options": 4},
+    # EXTENSION: request options the reference's wire cannot express (api.go:193-197);
+    # every field has explicit presence (proto3 `optional`): temperature 0 = greedy is not "unset"
+    "GenerateOptions": {"seed": 1, "temperature": 2, "top_k": 3, "top_p": 4, "repeat_penalty": 5, "repeat_last_n": 6,
+                        "num_predict": 7, "raw": 8},
     "GenerateResponse": {"model": 1, "created_at": 2, "response": 3, "done": 4, "done_reason": 5, "worker_id": 6,
                          "total_duration": 7},
     "Timestamp": {"seconds": 1, "nanos": 2},
@@ -66,11 +70,78 @@ def _fields(b: bytes):
         yield f, wt, v
 
 
+import struct
+
+_OPT_FLOAT = ("temperature", "top_p", "repeat_penalty")
+
+
+@dataclass
+class GenerateOptions:
+    """Ollama `options` subset (api/types.go Options upstream): None = not set (the worker's default applies)."""
+    seed: int | None = None
+    temperature: float | None = None
+    top_k: int | None = None
+    top_p: float | None = None
+    repeat_penalty: float | None = None
+    repeat_last_n: int | None = None
+    num_predict: int | None = None
+    raw: bool | None = None
+
+    def encode(self) -> bytes:
+        F, out = FIELDS["GenerateOptions"], b""
+        for name, fno in F.items():
+            v = getattr(self, name)
+            if v is None:
+                continue
+            if name in _OPT_FLOAT:
+                out += _varint(fno << 3 | 5) + struct.pack("<f", float(v))
+            else:
+                out += _varint(fno << 3) + _varint(int(v))
+        return out
+
+    @classmethod
+    def decode(cls, b: bytes) -> "GenerateOptions":
+        F, m = FIELDS["GenerateOptions"], cls()
+        by_no = {v: k for k, v in F.items()}
+        for f, wt, v in _fields(b):
+            name = by_no.get(f)
+            if name is None:
+                continue
+            if name in _OPT_FLOAT and wt == 5:
+                setattr(m, name, struct.unpack("<f", v)[0])
+            elif name not in _OPT_FLOAT and wt == 0:
+                if name == "raw":
+                    m.raw = bool(v)
+                elif name == "seed":
+                    m.seed = v
+                else:
+                    setattr(m, name, v if v < 1 << 63 else v - (1 << 64))
+        return m
+
+    @classmethod
+    def from_json(cls, d: dict | None) -> "GenerateOptions | None":
+        """Ollama request JSON `options` object -> GenerateOptions (unknown keys are ignored, as Ollama does)."""
+        if not d:
+            return None
+        m = cls()
+        for k in ("seed", "top_k", "repeat_last_n", "num_predict"):
+            if d.get(k) is not None:
+                setattr(m, k, int(d[k]))
+        for k in _OPT_FLOAT:
+            if d.get(k) is not None:
+                setattr(m, k, float(d[k]))
+        return m
+
+    def is_empty(self) -> bool:
+        return all(getattr(self, k) is None for k in FIELDS["GenerateOptions"])
+
+
 @dataclass
 class GenerateRequest:
     model: str = ""
     prompt: str = ""
     stream: bool = False
+    options: GenerateOptions | None = None
 
     def encode(self) -> bytes:
         F = FIELDS["GenerateRequest"]
@@ -81,6 +152,8 @@ class GenerateRequest:
             out += _ld(F["prompt"], self.prompt.encode())
         if self.stream:
             out += _varint(F["stream"] << 3) + b"\x01"
+        if self.options is not None and not self.options.is_empty():
+            out += _ld(F["options"], self.options.encode())
         return out
 
     @classmethod
@@ -93,6 +166,8 @@ class GenerateRequest:
                 m.prompt = v.decode("utf-8", "replace")
             elif f == F["stream"] and wt == 0:
                 m.stream = bool(v)
+            elif f == F["options"] and wt == 2:
+                m.options = GenerateOptions.decode(v)
         return m
 
 

@@ -14,15 +14,18 @@ package b200handler
 #cgo LDFLAGS: -L${SRCDIR}/../../crowdllama_b200/lib -lclengine -Wl,-rpath,${SRCDIR}/../../crowdllama_b200/lib
 #include <stdlib.h>
 #include "clengine.h"
+extern int goFrameCallback(void* user, uint8_t* msg, size_t len);   // //export in callbacks.go
 */
 import "C"
 
 import (
 	"context"
 	"fmt"
+	"runtime/cgo"
 	"time"
 	"unsafe"
 
+	"google.golang.org/protobuf/proto"
 	"google.golang.org/protobuf/types/known/timestamppb"
 
 	llamav1 "github.com/crowdllama/crowdllama-pb/llama/v1"
@@ -97,6 +100,33 @@ func (e *Engine) Handler() crowdllama.UnifiedAPIHandler {
 	}
 }
 
+// HandleStream is the streaming form (SURVEY.md §8f row 4; the reference rejects stream:true, api.go:155): the
+// request is handed to libclengine as bytes, every response frame (Done=false text deltas, then Done=true) comes
+// back through emit on the calling goroutine.  GenerateRequest.Options (field 4, the §8f-row-3 extension) is
+// applied inside the library.  The frame callback is exported to C as goFrameCallback (see callbacks.go in a real
+// build: //export goFrameCallback, cgo.Handle carries `emit`).
+func (e *Engine) HandleStream(req *llamav1.BaseMessage, emit func(*llamav1.BaseMessage) error) error {
+	raw, err := proto.Marshal(req)
+	if err != nil {
+		return err
+	}
+	h := cgo.NewHandle(func(frame []byte) error {
+		var m llamav1.BaseMessage
+		if err := proto.Unmarshal(frame, &m); err != nil {
+			return err
+		}
+		return emit(&m)
+	})
+	defer h.Delete()
+	buf := C.CBytes(raw) // copied: C never retains Go memory
+	defer C.free(buf)
+	if rc := C.cl_handle_message_stream(e.h, (*C.uint8_t)(buf), C.size_t(len(raw)), nil,
+		C.cl_frame_cb(C.goFrameCallback), unsafe.Pointer(&h)); rc != C.CL_OK {
+		return fmt.Errorf("failed to call B200 engine: %w", lastErr(rc))
+	}
+	return nil
+}
+
 // Stats feeds truthful routing metadata into crowdllama.Resource (pkg/crowdllama/types.go:30-40),
 // replacing the constants at pkg/peer/peer.go:319-358.
 func (e *Engine) Stats(r *crowdllama.Resource) error {
@@ -108,3 +138,14 @@ func (e *Engine) Stats(r *crowdllama.Resource) error {
 	r.VRAMGB, r.GPUModel = int(s.vram_gb), C.GoString(&s.gpu_model[0])
 	return nil
 }
+
+// callbacks.go (same package; cgo requires //export functions to live in a file without C definitions):
+//
+//	//export goFrameCallback
+//	func goFrameCallback(user unsafe.Pointer, msg *C.uint8_t, n C.size_t) C.int {
+//		emit := (*cgo.Handle)(user).Value().(func([]byte) error)
+//		if err := emit(C.GoBytes(unsafe.Pointer(msg), C.int(n))); err != nil {
+//			return 1 // cancels the request: done_reason "cancelled"
+//		}
+//		return 0
+//	}

@@ -161,6 +161,22 @@ int cl_generate_ids(cl_engine* e, const int32_t* prompt_ids, int32_t n_prompt,
                     const cl_sampling* s, cl_result* out);
 void cl_result_free(cl_result* r);
 
+/* Streaming variant of cl_generate (the reference rejects stream:true, api.go:155).
+ * cb runs on the CALLING thread (cgo-safe) with each batch of new tokens: text = UTF-8 delta that later tokens
+ * cannot change (an incomplete multi-byte tail is held back), ids/n_ids = the new token ids (NULL/0 for the final
+ * flush).  A nonzero return cancels the request (done_reason "cancelled").  out receives the whole result. */
+typedef int (*cl_token_cb)(void* user, const char* text, size_t text_len, const int32_t* ids, int32_t n_ids);
+int cl_generate_stream(cl_engine* e, const char* model, const char* prompt, size_t prompt_len,
+                       const cl_sampling* s, cl_token_cb cb, void* user, cl_result* out);
+/* Byte-level streaming handler: like cl_handle_message, but when GenerateRequest.stream is set the answer is a
+ * sequence of serialised BaseMessage{GenerateResponse} frames — Done=false frames carrying text deltas, then one
+ * Done=true frame with done_reason — each handed to cb (the host writes them length-prefixed to the stream,
+ * pbwire.go:14-33).  Without stream: exactly one Done=true frame.  GenerateRequest.options (field 4, the proto
+ * extension of §8f row 3: seed, temperature, top_k, top_p, repeat_penalty, repeat_last_n, num_predict, raw)
+ * override `s` field by field in both entry points. */
+typedef int (*cl_frame_cb)(void* user, const uint8_t* msg, size_t len);
+int cl_handle_message_stream(cl_engine* e, const uint8_t* req, size_t req_len, const cl_sampling* s,
+                             cl_frame_cb cb, void* user);
 /* replaces: WorkerAPIHandler, api.go:45-96, at the byte level.  `req`/`req_len` is a serialised
  * llama.v1.BaseMessage (the payload pbwire.go:14-41 length-prefixes); on success *resp is a
  * malloc'd serialised BaseMessage{GenerateResponse} (free with cl_buffer_free).  A request that

@@ -209,6 +209,40 @@ def test_generate_ids_greedy_and_sampled_match_oracle_sampler():
             hist.append(t)
 
 
+@pytest.mark.parametrize("scheduler", [False, True])
+def test_streaming_options_and_cancel_through_the_c_abi(scheduler):
+    """SURVEY.md §8f rows 3-4 at the C-ABI: cl_generate_stream / cl_handle_message_stream deliver exactly the text and
+    ids of the one-shot calls; GenerateRequest.options override the worker's sampling; a callback can cancel."""
+    from crowdllama_b200 import handler as H
+    from crowdllama_b200.pb import BaseMessage, GenerateOptions
+    with eng.Engine(preset="tiny-test", seed=33, model_name="tiny", start_scheduler=scheduler) as e:
+        g = eng.greedy(24, ignore_eos=True)
+        whole = e.generate("tiny", "why is the sky blue? ☃", g)
+        deltas, ids = [], []
+        r = e.generate_stream("tiny", "why is the sky blue? ☃", g, lambda d, new: (deltas.append(d), ids.extend(new)) and False)
+        assert r.text == whole.text and list(r.token_ids) == list(whole.token_ids) and r.done_reason == "length"
+        assert "".join(deltas) == whole.text and ids == list(whole.token_ids)
+        assert len([d for d in deltas if d]) > 1                                # really incremental
+        # byte-level handler: frames
+        req = H.create_generate_request("tiny", "hello", True, GenerateOptions(temperature=0.0, num_predict=12, seed=1))
+        frames = []
+        n = e.handle_message_stream(req.encode(), None, lambda f: frames.append(BaseMessage.decode(f).generate_response) and False)
+        assert n == len(frames) >= 2 and [f.done for f in frames] == [False] * (n - 1) + [True]
+        assert frames[-1].done_reason == "length" and all(f.model == "tiny" and f.worker_id == "worker" for f in frames)
+        one = BaseMessage.decode(e.handle_message(req.encode(), None)).generate_response       # cl_handle_message ignores stream
+        assert one.done and one.response == "".join(f.response for f in frames)
+        # options decide: without them the default sampler is stochastic and unbounded; with them greedy and 12 tokens
+        again = BaseMessage.decode(e.handle_message(req.encode(), eng.ollama_default_sampling(seed=99, max_new_tokens=5))).generate_response
+        assert again.response == one.response
+        raw = H.create_generate_request("tiny", "hello", False, GenerateOptions(temperature=0.0, num_predict=12, raw=True))
+        assert BaseMessage.decode(e.handle_message(raw.encode(), None)).generate_response.response != one.response  # no chat framing
+        # cancel after the third callback
+        calls = []
+        r = e.generate_stream("tiny", "x", eng.greedy(200, ignore_eos=True), lambda d, new: (calls.append(1), len(calls) >= 3)[1])
+        assert r.done_reason == "cancelled" and 3 <= r.n_generated < 200
+        assert e.generate("tiny", "why is the sky blue? ☃", g).text == whole.text   # the engine is healthy afterwards
+
+
 @pytest.mark.parametrize("preset", ["tinyllama-1.1b"])
 def test_tinyllama_shapes_match_oracle(preset):
     cfg = dict(oc.PRESETS[preset])

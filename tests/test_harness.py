@@ -24,6 +24,13 @@ class _MockEngine:
             raise RuntimeError("unknown model")
         return R()
 
+    def generate_stream(self, model, prompt, sampling=None, on_text=None):
+        r = self.generate(model, prompt, sampling)
+        self.last_sampling = sampling
+        for w in r.text.split(" "):
+            on_text(w + " ", [0])
+        return r
+
     def stats(self):
         return dict(tokens_per_sec=self.tput, load=0.3, vram_gb=179, gpu_model="mock B200")
 
@@ -108,3 +115,48 @@ def test_metadata_protocol_returns_resource_json():
         assert r.worker_mode and r.supported_models == ["tinyllama"] and r.tokens_throughput == 150.0 and r.gpu_model == "mock B200"
     finally:
         srv.shutdown()
+
+
+def test_generate_endpoint_options_and_streaming():
+    """POST /api/generate, `options` passed through to the worker, NDJSON streaming."""
+    wp, gp = _free_port(), _free_port()
+    w = _spawn_worker(wp, "tinyllama")
+    seen = {}
+    orig = w.engine.generate
+
+    def rec(model, prompt, sampling=None):
+        seen["sampling"] = sampling
+        return orig(model, prompt, sampling)
+    w.engine.generate = rec
+    g = gateway.make_server([("127.0.0.1", wp)], port=gp)
+    threading.Thread(target=g.serve_forever, daemon=True).start()
+    try:
+        base = f"http://127.0.0.1:{gp}"
+        _, r = _post(base + "/api/generate", {"model": "tinyllama", "prompt": "why?", "stream": False,
+                                              "options": {"temperature": 0, "seed": 42, "num_predict": 32, "mirostat": 2}})
+        assert r["response"] == "This is a mock response. You asked: why?" and r["done"] and r["done_reason"] == "stop"
+        assert "message" not in r and r["stream"] is False
+        s = seen["sampling"]
+        assert (s.temperature, s.seed, s.max_new_tokens) == (0.0, 42, 32) and s.top_k == 40      # unset fields: Ollama defaults
+        _, r = _post(base + "/api/chat", {"model": "tinyllama", "messages": [{"role": "user", "content": "hi"}],
+                                          "options": {"top_k": 1}})
+        assert r["message"]["content"].endswith("You asked: hi") and seen["sampling"].top_k == 1
+        with pytest.raises(urllib.error.HTTPError) as ei:
+            _post(base + "/api/generate", {"model": "tinyllama"})
+        assert ei.value.code == 400
+        # streaming: one NDJSON line per worker frame, done only on the last
+        req = urllib.request.Request(base + "/api/generate", data=json.dumps({"model": "tinyllama", "prompt": "a b", "stream": True}).encode(),
+                                     headers={"Content-Type": "application/json"})
+        with urllib.request.urlopen(req, timeout=10) as resp:
+            assert resp.headers["Content-Type"] == "application/x-ndjson"
+            lines = [json.loads(x) for x in resp.read().decode().splitlines() if x.strip()]
+        assert len(lines) >= 3 and [x["done"] for x in lines] == [False] * (len(lines) - 1) + [True]
+        assert "".join(x["response"] for x in lines).strip() == "This is a mock response. You asked: a b"
+        assert lines[-1]["done_reason"] == "stop"
+        req = urllib.request.Request(base + "/api/chat", data=json.dumps({"model": "tinyllama", "stream": True,
+                                     "messages": [{"role": "user", "content": "x"}]}).encode(), headers={"Content-Type": "application/json"})
+        with urllib.request.urlopen(req, timeout=10) as resp:
+            lines = [json.loads(x) for x in resp.read().decode().splitlines() if x.strip()]
+        assert "".join(x["message"]["content"] for x in lines).strip().endswith("You asked: x") and lines[-1]["done"]
+    finally:
+        g.shutdown(); g.server_close(); w.shutdown(); w.server_close()

@@ -140,6 +140,13 @@ def test_codec_is_wire_compatible_with_google_protobuf():
     gr.field.add(name="model", number=1, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
     gr.field.add(name="prompt", number=2, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
     gr.field.add(name="stream", number=3, type=T.TYPE_BOOL, label=T.LABEL_OPTIONAL)
+    gr.field.add(name="options", number=4, type=T.TYPE_MESSAGE, type_name=".llama.v1t.GenerateOptions", label=T.LABEL_OPTIONAL)
+    go = fd.message_type.add(name="GenerateOptions")          # the §8f-row-3 extension: proto3 `optional` scalars
+    for i, (nm, ty) in enumerate([("seed", T.TYPE_UINT64), ("temperature", T.TYPE_FLOAT), ("top_k", T.TYPE_INT32),
+                                  ("top_p", T.TYPE_FLOAT), ("repeat_penalty", T.TYPE_FLOAT), ("repeat_last_n", T.TYPE_INT32),
+                                  ("num_predict", T.TYPE_INT32), ("raw", T.TYPE_BOOL)]):
+        go.oneof_decl.add(name=f"_{nm}")
+        go.field.add(name=nm, number=i + 1, type=ty, label=T.LABEL_OPTIONAL, oneof_index=i, proto3_optional=True)
     gp = fd.message_type.add(name="GenerateResponse")
     gp.field.add(name="model", number=1, type=T.TYPE_STRING, label=T.LABEL_OPTIONAL)
     gp.field.add(name="created_at", number=2, type=T.TYPE_MESSAGE, type_name=".google.protobuf.Timestamp", label=T.LABEL_OPTIONAL)
@@ -164,6 +171,22 @@ def test_codec_is_wire_compatible_with_google_protobuf():
     g = Base.FromString(ours)
     assert g.WhichOneof("message") == "generate_request"
     assert (g.generate_request.model, g.generate_request.prompt, g.generate_request.stream) == ("tinyllama", "why is the sky blue? ☃", True)
+    # request options: explicit presence both ways (temperature 0.0 and num_predict -1 must survive)
+    from crowdllama_b200.pb import GenerateOptions
+    opts = GenerateOptions(seed=(1 << 63) + 5, temperature=0.0, top_k=40, top_p=0.5, num_predict=-1, raw=True)
+    g = Base.FromString(H.create_generate_request("m", "p", True, opts).encode())
+    o = g.generate_request.options
+    assert o.HasField("temperature") and o.temperature == 0.0 and o.seed == (1 << 63) + 5 and o.top_k == 40
+    assert o.num_predict == -1 and o.raw and abs(o.top_p - 0.5) < 1e-7
+    assert not o.HasField("repeat_penalty") and not o.HasField("repeat_last_n")
+    g3 = Base()
+    g3.generate_request.model = "m"
+    g3.generate_request.options.temperature = 0.0
+    g3.generate_request.options.repeat_last_n = 64
+    g3.generate_request.options.num_predict = -2
+    back_o = BaseMessage.decode(g3.SerializeToString()).generate_request.options
+    assert back_o == GenerateOptions(temperature=0.0, repeat_last_n=64, num_predict=-2)
+    assert BaseMessage.decode(H.create_generate_request("m", "p", False).encode()).generate_request.options is None
     g2 = Base()
     g2.generate_response.model = "m"
     g2.generate_response.response = "text"
@@ -198,6 +221,70 @@ def test_worker_handler_envelope():
     assert g.worker_id == "worker" and g.total_duration > 0 and g.created_at_seconds > 0
     with pytest.raises(H.HandlerError, match="expected GenerateRequest, got different message type"):
         h(None, BaseMessage(generate_response=GenerateResponse()))
+
+
+def test_request_options_override_worker_defaults_field_by_field():
+    from crowdllama_b200.pb import GenerateOptions
+    seen = {}
+
+    class Rec(_MockEngine):
+        def generate(self, model, prompt, sampling=None):
+            seen["s"] = sampling
+            return super().generate(model, prompt, sampling)
+
+    base = eng.Sampling()
+    base.temperature, base.top_k, base.top_p, base.repeat_penalty, base.repeat_last_n, base.seed, base.max_new_tokens = 0.8, 40, 0.9, 1.1, 64, 11, 128
+    h = H.worker_api_handler(Rec(), base)
+    h(None, H.create_generate_request("test-model", "x", False))
+    assert seen["s"] is base                                           # no options: the worker's defaults, untouched
+    h(None, H.create_generate_request("test-model", "x", False, GenerateOptions(temperature=0.0, seed=5, num_predict=7)))
+    s = seen["s"]
+    assert (s.temperature, s.seed, s.max_new_tokens) == (0.0, 5, 7)
+    assert (s.top_k, s.repeat_last_n) == (40, 64) and abs(s.top_p - 0.9) < 1e-6 and abs(s.repeat_penalty - 1.1) < 1e-6
+    assert base.temperature == pytest.approx(0.8) and base.seed == 11  # the default object is not mutated
+
+
+def test_streaming_frames_on_the_inference_stream():
+    """stream=true -> several length-prefixed GenerateResponse frames, Done only on the last."""
+    class Duplex(io.BytesIO):
+        def __init__(self, data):
+            super().__init__(data)
+            self.out = io.BytesIO()
+
+        def write(self, b):
+            return self.out.write(b)
+
+    class Streaming(_MockEngine):
+        def generate_stream(self, model, prompt, sampling=None, on_text=None):
+            for piece in ("PB ", "Hello, ", "", prompt):
+                on_text(piece, [1])
+            return self.generate(model, prompt, sampling)
+
+    def frames(handler, stream_flag):
+        wire = io.BytesIO()
+        pbwire.write_length_prefixed_pb(wire, H.create_generate_request("test-model", "world", stream_flag))
+        s = Duplex(wire.getvalue())
+        assert H.handle_inference_stream(handler, s)
+        rd, out = io.BytesIO(s.out.getvalue()), []
+        while rd.tell() < len(rd.getvalue()):
+            out.append(pbwire.read_length_prefixed_pb(rd).generate_response)
+        return out
+
+    fs = frames(H.worker_api_handler(Streaming()), True)
+    assert [f.response for f in fs] == ["PB ", "Hello, ", "world", ""]  # empty deltas are not sent; the last frame closes
+    assert [f.done for f in fs] == [False, False, False, True] and fs[-1].done_reason == "stop"
+    assert all(f.model == "test-model" and f.worker_id == "worker" for f in fs) and fs[0].total_duration == 0
+    assert len(frames(H.worker_api_handler(Streaming()), False)) == 1   # stream=false: the reference's single answer
+    one = frames(H.worker_api_handler(_MockEngine()), True)             # an engine without streaming: one complete frame
+    assert len(one) == 1 and one[0].done and one[0].response == "PB Hello, world"
+
+    def failing_stream(ctx, req, emit):
+        emit(H._response("test-model", "partial", False))
+        raise RuntimeError("boom")
+    h = H.worker_api_handler(Streaming())
+    h.stream = failing_stream
+    fs = frames(h, True)
+    assert fs[-1].response == "Error: boom" and fs[-1].done            # peer.go:232-243 semantics, mid-stream
 
 
 def test_handle_inference_stream_error_becomes_text():
