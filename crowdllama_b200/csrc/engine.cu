@@ -144,12 +144,15 @@ int Engine::init(const cl_engine_config& c) {
   tok.reset(new Tokenizer(cfg.vocab_size));
   CL_CUDA_OK(cudaStreamSynchronize(stream_));
   {
-    // Advertised throughput before anything has been measured: FindBestWorker (manager.go:369-377) never
-    // selects a worker whose score is 0, so start from a model-based estimate (70 % of the HBM roofline of
-    // one decode step) and let the EWMA of real steps take over.
+    // Advertised throughput = CAPACITY: decode steps per second x max_batch, i.e. what this worker delivers with a
+    // full batch at its current step time.  (Advertising the achieved tokens/s instead made FindBestWorker's
+    // score T/(1+L) a positive feedback: the busy worker's T grows with its batch, idle workers keep a
+    // single-stream T, and one worker of four took all 256 requests — profiles/README.md.)  Before anything has
+    // been measured: a model-based estimate (70 % of the HBM roofline of one decode step); FindBestWorker
+    // (manager.go:369-377) never selects a worker whose score is 0.
     const double params = (double)cfg.n_layers * ((double)qkv_dim_ * cfg.d_model + (double)cfg.d_model * q_dim_ + 3.0 * cfg.d_ff * cfg.d_model) +
                           (double)cfg.vocab_size * cfg.d_model;
-    tok_per_sec_ewma_ = 0.7 * 6.5e12 / (2.0 * params);
+    tok_per_sec_ewma_ = 0.7 * 6.5e12 / (2.0 * params) * (double)max_batch_;
   }
   if (c.start_scheduler) start_scheduler();
   return CL_OK;
@@ -741,7 +744,7 @@ int Engine::decode_greedy(const cl_seq_t* ss, int B, const int32_t* first_ids, i
   }
   tokens_generated_ += (int64_t)n_steps * B;
   if (total_ms > 0.f) {
-    const double tps = (double)n_steps * B / (total_ms * 1e-3);
+    const double tps = (double)n_steps * max_batch_ / (total_ms * 1e-3);   // capacity: steps/s x max_batch
     tok_per_sec_ewma_ = tok_per_sec_ewma_ == 0.0 ? tps : 0.8 * tok_per_sec_ewma_ + 0.2 * tps;
   }
   if (device_ms) *device_ms = total_ms;
@@ -780,11 +783,11 @@ int Engine::stats(cl_stats* out) {
   int active = 0;
   for (auto& s : seqs_) active += s.live ? 1 : 0;
   out->active_seqs = active;
-  out->load = std::min(1.0, (double)active / (double)max_batch_);
   {
     std::lock_guard<std::mutex> lk(q_mu_);
     out->queue_depth = (int)queue_.size();
   }
+  out->load = std::min(1.0, (double)(active + out->queue_depth) / (double)max_batch_);   // queued requests count as load
   out->kv_pages_total = n_pages_;
   out->kv_pages_used = pool_ ? pool_->used_pages() : 0;
   out->tokens_generated = tokens_generated_;

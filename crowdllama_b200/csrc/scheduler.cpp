@@ -317,7 +317,7 @@ void Engine::scheduler_main() {
     const int64_t dt = now_ns() - t0;
     for (auto& r : active_) r->decode_ns += dt;
     tokens_generated_ += B;
-    const double tps = (double)B / ((double)dt * 1e-9);
+    const double tps = (double)max_batch_ / ((double)dt * 1e-9);   // capacity at the current step time (engine.cu, init)
     tok_per_sec_ewma_ = tok_per_sec_ewma_ == 0.0 ? tps : 0.9 * tok_per_sec_ewma_ + 0.1 * tps;
     // ---- retire finished requests
     for (size_t i = 0; i < active_.size();) {

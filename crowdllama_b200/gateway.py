@@ -186,10 +186,13 @@ class _Handler(BaseHTTPRequestHandler):
         self._json(200, o)
 
 
+class _Server(ThreadingHTTPServer):
+    daemon_threads = True
+    request_queue_size = 256        # listen() backlog: must be a class attribute, the constructor already listens
+
+
 def make_server(worker_addrs, port: int = 9001, host: str = "127.0.0.1", seed: int = 0) -> ThreadingHTTPServer:
-    srv = ThreadingHTTPServer((host, port), _Handler)
-    srv.daemon_threads = True
-    srv.request_queue_size = 256
+    srv = _Server((host, port), _Handler)
     srv.table = PeerTable(worker_addrs, seed=seed)
     srv.counts, srv.lock = {}, threading.Lock()
     srv.table.start()

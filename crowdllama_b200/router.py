@@ -37,10 +37,30 @@ class Resource:
         return "/ipns/" + self.peer_id
 
 
+def advertised_throughput(tokens_per_sec: float) -> float:
+    """Quantise the measured capacity to half-octave buckets.  FindBestWorker compares scores with a strict '>' and
+    breaks exact ties at random (Go map order, manager.go:369-377); the reference's workers all advertise the constant
+    150, so identical machines tie and share the load.  Raw measured EWMAs never tie: between two metadata refreshes
+    every request would go to the one worker whose EWMA happens to be 1 % higher."""
+    if tokens_per_sec <= 0:
+        return 0.0
+    import math
+    return float(round(2.0 ** (round(math.log2(tokens_per_sec) * 2.0) / 2.0), 1))
+
+
+def advertised_load(load: float) -> float:
+    """Two levels only: 0 while the worker has a free batch slot, 1 once it is saturated (every slot busy or requests
+    queued).  The gateway sees metadata that is 2-30 s old (DiscoveryInterval 10 s, MetadataUpdateInterval 30 s,
+    manager.go:99-101); a fine-grained load makes the momentarily least loaded worker win EVERY request until the next
+    refresh (measured: 36 / 100 / 42 / 78 requests over four identical workers).  With two levels all unsaturated
+    workers tie and FindBestWorker's random tie-break spreads the requests, as it does with the reference's constants."""
+    return 1.0 if load >= 1.0 else 0.0
+
+
 def resource_from_engine(peer_id: str, engine, version: str = "b200") -> Resource:
     st = engine.stats()
-    return Resource(peer_id=peer_id, supported_models=[engine.model_name], tokens_throughput=float(st["tokens_per_sec"]),
-                    vram_gb=int(st["vram_gb"]), load=float(st["load"]), gpu_model=st["gpu_model"],
+    return Resource(peer_id=peer_id, supported_models=[engine.model_name], tokens_throughput=advertised_throughput(float(st["tokens_per_sec"])),
+                    vram_gb=int(st["vram_gb"]), load=advertised_load(float(st["load"])), gpu_model=st["gpu_model"],
                     last_updated=datetime.now(timezone.utc).isoformat(), version=version, worker_mode=True)
 
 

@@ -112,8 +112,8 @@ typedef struct cl_result {
 } cl_result;
 
 typedef struct cl_stats {
-  double tokens_per_sec;     /* EWMA decode throughput -> Resource.TokensThroughput (types.go:33) */
-  double load;               /* active / max_batch in [0,1] -> Resource.Load (types.go:35) */
+  double tokens_per_sec;     /* capacity: EWMA of decode steps/s x max_batch -> Resource.TokensThroughput (types.go:33) */
+  double load;               /* (active + queued) / max_batch, capped at 1 -> Resource.Load (types.go:35) */
   int32_t queue_depth;
   int32_t active_seqs;
   int32_t kv_pages_total;

@@ -2,6 +2,7 @@
 framing / protobuf codec (mirrors /root/reference/pkg/crowdllama/pbwire_test.go), the handler
 envelope with a mock engine (mirrors /root/reference/pkg/ipc/ipc_test.go:44-146), routing
 (manager.go:338-387) and Resource JSON (types_test.go)."""
+import collections
 import io
 import json
 import random
@@ -335,6 +336,17 @@ def test_ties_are_uniform_random():
         p = find_best_worker(ws, "m", rng).peer_id
         counts[p] = counts.get(p, 0) + 1
     assert len(counts) == 8 and min(counts.values()) > 350
+
+
+def test_advertised_throughput_buckets_make_identical_workers_tie():
+    from crowdllama_b200.router import advertised_throughput
+    assert advertised_throughput(0.0) == 0.0
+    a, b = advertised_throughput(3190.0), advertised_throughput(3260.0)       # two B200s, EWMAs 2 % apart
+    assert a == b and 2700 < a < 3900
+    assert advertised_throughput(5700.0) > a                                  # an idle worker (short steps) still ranks higher
+    ws = [_w(f"w{i}", ["m"], advertised_throughput(3200.0 + 13 * i), 0.0) for i in range(4)]
+    picks = collections.Counter(find_best_worker(ws, "m", random.Random(s)).peer_id for s in range(400))
+    assert len(picks) == 4 and min(picks.values()) > 60                       # ties -> uniform random, as with the constant 150
 
 
 def test_resource_json_round_trip():

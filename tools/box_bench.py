@@ -64,7 +64,12 @@ def main():
         except Exception as ex:  # noqa: BLE001
             errs.append(str(ex))
 
-    one(-1)   # warm-up request (graph capture, prefill workspace)
+    # warm EVERY worker directly (graph capture, prefill workspace), then one request through the gateway
+    for addr in addrs:
+        for _ in range(2):
+            gateway.request_inference(addr, a.model_name, "warm-up " + prompt, False)
+    one(-1)
+    errs.clear()
     lat.clear()
     gw.counts.clear()
     sem = threading.Semaphore(a.concurrency)
