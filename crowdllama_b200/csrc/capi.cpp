@@ -293,6 +293,66 @@ int cl_handle_message_stream(cl_engine* e, const uint8_t* req, size_t req_len, c
 
 void cl_buffer_free(void* p) { free(p); }
 
+// ---- tokenizer (tokenizer.cpp) ---------------------------------------------------------------------------------
+struct cl_tokenizer { std::unique_ptr<Tokenizer> t; };
+
+int cl_tokenizer_load(const char* tokenizer_json_path, const char* chat_family, cl_tokenizer** out) {
+  if (!tokenizer_json_path || !out) return CL_ERR_INVALID_ARG;
+  *out = nullptr;
+  CL_GUARD(
+    std::string err;
+    std::unique_ptr<Tokenizer> t = load_hf_tokenizer(tokenizer_json_path, chat_family ? chat_family : "", &err);
+    if (!t) { set_last_error(err); return CL_ERR_IO; }
+    *out = new cl_tokenizer{std::move(t)};
+    return CL_OK;
+  )
+}
+void cl_tokenizer_free(cl_tokenizer* t) { delete t; }
+int cl_tokenizer_encode(const cl_tokenizer* t, const char* text, size_t len, int32_t add_bos, int32_t chat, int32_t* ids, int32_t cap,
+                        int32_t* n_out) {
+  if (!t || !text || !n_out) return CL_ERR_INVALID_ARG;
+  CL_GUARD(
+    const std::string s(text, len);
+    const std::vector<int32_t> v = t->t->encode(chat ? t->t->apply_chat_template(s) : s, add_bos != 0);
+    *n_out = (int32_t)v.size();
+    if (ids && cap >= (int32_t)v.size()) { if (!v.empty()) memcpy(ids, v.data(), v.size() * 4); }
+    else if (ids) return CL_ERR_INVALID_ARG;
+    return CL_OK;
+  )
+}
+int cl_tokenizer_decode(const cl_tokenizer* t, const int32_t* ids, int32_t n, char* buf, size_t cap, size_t* len_out) {
+  if (!t || (!ids && n > 0) || !len_out) return CL_ERR_INVALID_ARG;
+  CL_GUARD(
+    const std::string s = t->t->decode_bytes(std::vector<int32_t>(ids, ids + n));   // raw bytes: the caller decides about UTF-8
+    *len_out = s.size();
+    if (buf && cap >= s.size()) { if (!s.empty()) memcpy(buf, s.data(), s.size()); }
+    else if (buf) return CL_ERR_INVALID_ARG;
+    return CL_OK;
+  )
+}
+int cl_tokenizer_info(const cl_tokenizer* t, int32_t* vocab_size, int32_t* bos, int32_t* eos) {
+  if (!t) return CL_ERR_INVALID_ARG;
+  if (vocab_size) *vocab_size = t->t->vocab_size();
+  if (bos) *bos = t->t->bos();
+  if (eos) *eos = t->t->eos();
+  return CL_OK;
+}
+int cl_engine_load_tokenizer(cl_engine* e, const char* tokenizer_json_path, const char* chat_family) {
+  if (!e || !tokenizer_json_path) return CL_ERR_INVALID_ARG;
+  CL_GUARD(
+    std::string err;
+    std::unique_ptr<Tokenizer> t = load_hf_tokenizer(tokenizer_json_path, chat_family ? chat_family : "", &err);
+    if (!t) { set_last_error(err); return CL_ERR_IO; }
+    if (t->vocab_size() > e->impl.cfg.vocab_size) {
+      set_last_error("tokenizer has more ids than the model's vocabulary");
+      return CL_ERR_INVALID_ARG;
+    }
+    std::lock_guard<std::mutex> lk(e->impl.mu_);
+    e->impl.tok = std::move(t);
+    return CL_OK;
+  )
+}
+
 int cl_tokenize(cl_engine* e, const char* text, size_t len, int32_t* ids, int32_t cap, int32_t* n_out) {
   if (!e || !text || !n_out) return CL_ERR_INVALID_ARG;
   std::vector<int32_t> v = e->impl.tok->encode(std::string(text, len), false);

@@ -141,7 +141,7 @@ int Engine::init(const cl_engine_config& c) {
   }
   pool_.reset(new KvPool(n_pages_, page_size_));
   seqs_.assign(max_seqs_, SeqState());
-  tok.reset(new Tokenizer(cfg.vocab_size));
+  tok.reset(new ByteTokenizer(cfg.vocab_size));
   CL_CUDA_OK(cudaStreamSynchronize(stream_));
   {
     // Advertised throughput = CAPACITY: decode steps per second x max_batch, i.e. what this worker delivers with a

@@ -49,24 +49,41 @@ class KvPool {
   std::vector<int> empty_;
 };
 
-// ---- tokenizer: byte-level fallback (no vocab files exist offline) --------
+// ---- tokenizers ---------------------------------------------------------------------------------
 class Tokenizer {
  public:
-  explicit Tokenizer(int vocab_size) : vocab_(vocab_size) {}
-  // ids 0..2 = <pad>, <bos>, <eos>; byte b -> 3 + b.  Needs vocab >= 259.
-  std::vector<int32_t> encode(const std::string& text, bool add_bos) const;
-  std::string decode(const std::vector<int32_t>& ids) const;        // = sanitize(decode_bytes(ids))
-  std::string decode_bytes(const std::vector<int32_t>& ids) const;  // raw surface bytes (may cut a UTF-8 sequence)
+  virtual ~Tokenizer() {}
+  virtual std::vector<int32_t> encode(const std::string& text, bool add_bos) const = 0;
+  virtual std::string decode_bytes(const std::vector<int32_t>& ids) const = 0;   // raw surface bytes (may cut a UTF-8 sequence)
+  std::string decode(const std::vector<int32_t>& ids) const { return sanitize(decode_bytes(ids)); }
   static std::string sanitize(const std::string& raw);              // invalid UTF-8 / control bytes -> U+FFFD
-  int bos() const { return 1; }
-  int eos() const { return 2; }
-  // chat framing the Ollama server applies upstream of the model (role forced to "user",
-  // api.go:111-116).  A neutral, documented framing is used because template files are absent.
-  std::string apply_chat_template(const std::string& user_prompt) const;
+  virtual int bos() const = 0;
+  virtual int eos() const = 0;
+  virtual bool is_stop(int id) const { return id == eos(); }        // Llama-3 also stops on <|eot_id|>
+  // chat framing the Ollama server applies upstream of the model (role forced to "user", api.go:111-116)
+  virtual std::string apply_chat_template(const std::string& user_prompt) const = 0;
+  virtual int vocab_size() const = 0;
+};
+
+// byte-level fallback (no vocab files exist offline): ids 0..2 = <pad>, <bos>, <eos>;
+// byte b -> 3 + b.  Needs vocab >= 259.  A neutral, documented chat framing is used.
+class ByteTokenizer : public Tokenizer {
+ public:
+  explicit ByteTokenizer(int vocab_size) : vocab_(vocab_size) {}
+  std::vector<int32_t> encode(const std::string& text, bool add_bos) const override;
+  std::string decode_bytes(const std::vector<int32_t>& ids) const override;
+  int bos() const override { return 1; }
+  int eos() const override { return 2; }
+  std::string apply_chat_template(const std::string& user_prompt) const override;
+  int vocab_size() const override { return vocab_; }
 
  private:
   int vocab_;
 };
+
+// HF tokenizer.json (BPE: SentencePiece-style and byte-level) — tokenizer.cpp.  chat_family: "llama3" | "mistral" |
+// "zephyr" | "chatml" | "" (auto-detect from the added tokens).  nullptr + *err on failure.
+std::unique_ptr<Tokenizer> load_hf_tokenizer(const std::string& path, const std::string& chat_family, std::string* err);
 
 // ---- sampler (host; mirrors oracle oc_sample) ---------------------------------------------------
 int32_t sample_token(const float* logits, int32_t vocab, const cl_sampling& sp, const int32_t* history, int32_t n_history,

@@ -46,7 +46,7 @@ const std::vector<int>& KvPool::pages_of(int owner) {
 // ================================================================================================
 // Tokenizer (byte-level fallback)
 // ================================================================================================
-std::vector<int32_t> Tokenizer::encode(const std::string& text, bool add_bos) const {
+std::vector<int32_t> ByteTokenizer::encode(const std::string& text, bool add_bos) const {
   std::vector<int32_t> ids;
   ids.reserve(text.size() + 1);
   if (add_bos) ids.push_back(bos());
@@ -57,7 +57,7 @@ std::vector<int32_t> Tokenizer::encode(const std::string& text, bool add_bos) co
   }
   return ids;
 }
-std::string Tokenizer::decode_bytes(const std::vector<int32_t>& ids) const {
+std::string ByteTokenizer::decode_bytes(const std::vector<int32_t>& ids) const {
   std::string out;
   for (int32_t id : ids) {
     if (id >= 3 && id < 259) out.push_back((char)(id - 3));
@@ -81,14 +81,13 @@ std::string Tokenizer::sanitize(const std::string& out) {
     int n = c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 0;
     bool ok = n > 0 && i + n <= out.size();
     for (int k = 1; ok && k < n; ++k) ok = (((unsigned char)out[i + k]) >> 6) == 2;
-    if (ok && n == 1 && c < 0x20 && c != '\n' && c != '\t') ok = false;
+    if (ok && n == 1 && c < 0x20 && c != '\n' && c != '\t' && c != '\r') ok = false;
     if (ok) { clean.append(out, i, n); i += n; }
     else { clean += "\xEF\xBF\xBD"; i += 1; }
   }
   return clean;
 }
-std::string Tokenizer::decode(const std::vector<int32_t>& ids) const { return sanitize(decode_bytes(ids)); }
-std::string Tokenizer::apply_chat_template(const std::string& user_prompt) const {
+std::string ByteTokenizer::apply_chat_template(const std::string& user_prompt) const {
   return "<|user|>\n" + user_prompt + "\n<|assistant|>\n";
 }
 

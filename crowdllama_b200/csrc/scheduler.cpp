@@ -64,9 +64,9 @@ static void publish(Request& r, int32_t id) {
   r.cv.notify_all();
 }
 
-static bool finished(Request& r, int eos, int max_seq_len) {
+static bool finished(Request& r, const Tokenizer& tok, int max_seq_len) {
   if (r.cancel.load(std::memory_order_relaxed)) { r.done_reason = "cancelled"; return true; }
-  if (!r.out.empty() && !r.sp.ignore_eos && r.out.back() == eos) { r.done_reason = "stop"; return true; }
+  if (!r.out.empty() && !r.sp.ignore_eos && tok.is_stop(r.out.back())) { r.done_reason = "stop"; return true; }
   if ((int)r.out.size() >= r.max_new) { r.done_reason = "length"; return true; }
   if ((int)(r.prompt.size() + r.out.size()) >= max_seq_len) { r.done_reason = "length"; return true; }
   return false;
@@ -94,7 +94,7 @@ static int generate_sync(Engine& e, Request& r, const Engine::TokenSink* sink) {
   int32_t next = sample_token(logits.data(), V, r.sp, hist.data(), (int)hist.size(), 0);
   r.out.push_back(next);
   emit();
-  while (!finished(r, e.tok->eos(), e.cfg.max_seq_len)) {
+  while (!finished(r, *e.tok, e.cfg.max_seq_len)) {
     if (r.greedy()) {
       int room = std::min(r.max_new - (int)r.out.size(), e.cfg.max_seq_len - (int)(r.prompt.size() + r.out.size()));
       int chunk = std::min(room, sink ? 8 : 32);
@@ -103,7 +103,7 @@ static int generate_sync(Engine& e, Request& r, const Engine::TokenSink* sink) {
       if (rc) break;
       for (int i = 0; i < chunk; ++i) {
         r.out.push_back(ids[i]);
-        if (finished(r, e.tok->eos(), e.cfg.max_seq_len)) break;
+        if (finished(r, *e.tok, e.cfg.max_seq_len)) break;
       }
       next = r.out.back();
     } else {
@@ -240,7 +240,7 @@ void Engine::scheduler_main() {
       r->out.push_back(next);
       publish(*r, next);
       if (!r->greedy()) cudaMemcpyAsync(d_tok_ + r->seq, &r->out.back(), 4, cudaMemcpyHostToDevice, stream_);
-      if (finished(*r, tok->eos(), cfg.max_seq_len)) {
+      if (finished(*r, *tok, cfg.max_seq_len)) {
         seq_free(r->seq);
         requests_completed_++;
         tokens_generated_ += 1;
@@ -322,7 +322,7 @@ void Engine::scheduler_main() {
     // ---- retire finished requests
     for (size_t i = 0; i < active_.size();) {
       auto r = active_[i];
-      if (finished(*r, tok->eos(), cfg.max_seq_len)) {
+      if (finished(*r, *tok, cfg.max_seq_len)) {
         seq_free(r->seq);
         active_.erase(active_.begin() + i);
         requests_completed_++;

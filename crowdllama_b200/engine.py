@@ -69,6 +69,7 @@ EXPORTS = [
     "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_qkv_rope_append", "cl_op_attn_decode",
     "cl_op_gemm_bf16", "cl_op_gemm_skinny", "cl_op_attn_prefill", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
     "cl_kvpool_reserve", "cl_kvpool_release", "cl_kvpool_pages_of", "cl_kvpool_free_pages", "cl_kvpool_used_pages",
+    "cl_tokenizer_load", "cl_tokenizer_free", "cl_tokenizer_encode", "cl_tokenizer_decode", "cl_tokenizer_info", "cl_engine_load_tokenizer",
 ]
 
 _lib = None
@@ -130,6 +131,12 @@ def lib():
         "cl_op_gemm_skinny": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, P(f32), vp]),
         "cl_op_attn_prefill": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, vp]),
         "cl_op_synth_weights": (C.c_int, [C.c_int, u64, i32, i64, f32, vp]),
+        "cl_tokenizer_load": (C.c_int, [C.c_char_p, C.c_char_p, P(vp)]),
+        "cl_tokenizer_free": (None, [vp]),
+        "cl_tokenizer_encode": (C.c_int, [vp, C.c_char_p, sz, i32, i32, vp, i32, P(i32)]),
+        "cl_tokenizer_decode": (C.c_int, [vp, vp, i32, vp, sz, P(sz)]),
+        "cl_tokenizer_info": (C.c_int, [vp, P(i32), P(i32), P(i32)]),
+        "cl_engine_load_tokenizer": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
         "cl_kvpool_create": (C.c_int, [i32, i32, P(vp)]),
         "cl_kvpool_destroy": (None, [vp]),
         "cl_kvpool_reserve": (C.c_int, [vp, i32, i32]),
@@ -385,6 +392,11 @@ class Engine:
         finally:
             lib().cl_buffer_free(out)
 
+    def load_tokenizer(self, tokenizer_json_path: str, chat_family: str | None = None) -> None:
+        """Replace the byte-level fallback by an HF tokenizer.json (cl_engine_load_tokenizer)."""
+        _check(lib().cl_engine_load_tokenizer(self._h, str(tokenizer_json_path).encode(), chat_family.encode() if chat_family else None),
+               "cl_engine_load_tokenizer")
+
     def tokenize(self, text: str) -> np.ndarray:
         b = text.encode("utf-8")
         n = C.c_int32()
@@ -511,6 +523,46 @@ def op_synth_weights(seed, key, n, scale, device=0):
     out = np.empty(n, np.uint16)
     _check(lib().cl_op_synth_weights(device, seed, key, n, scale, _ptr(out)), "cl_op_synth_weights")
     return out
+
+
+class HfTokenizer:
+    """Native tokenizer.json loader (csrc/tokenizer.cpp) — host logic, works without a GPU."""
+
+    def __init__(self, tokenizer_json_path, chat_family: str | None = None):
+        h = C.c_void_p()
+        _check(lib().cl_tokenizer_load(str(tokenizer_json_path).encode(), chat_family.encode() if chat_family else None, C.byref(h)),
+               "cl_tokenizer_load")
+        self._h = h
+        v, b, e = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().cl_tokenizer_info(self._h, C.byref(v), C.byref(b), C.byref(e)), "cl_tokenizer_info")
+        self.vocab_size, self.bos, self.eos = v.value, b.value, e.value
+
+    def encode(self, text: str, add_bos: bool = False, chat: bool = False) -> list:
+        b = text.encode("utf-8")
+        n = C.c_int32()
+        _check(lib().cl_tokenizer_encode(self._h, b, len(b), int(add_bos), int(chat), None, 0, C.byref(n)), "cl_tokenizer_encode")
+        ids = np.zeros(max(n.value, 1), np.int32)
+        _check(lib().cl_tokenizer_encode(self._h, b, len(b), int(add_bos), int(chat), _ptr(ids), n.value, C.byref(n)), "cl_tokenizer_encode")
+        return ids[:n.value].tolist()
+
+    def decode(self, ids) -> str:
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        n = C.c_size_t()
+        _check(lib().cl_tokenizer_decode(self._h, _ptr(a), len(a), None, 0, C.byref(n)), "cl_tokenizer_decode")
+        buf = C.create_string_buffer(n.value + 1)
+        _check(lib().cl_tokenizer_decode(self._h, _ptr(a), len(a), buf, n.value, C.byref(n)), "cl_tokenizer_decode")
+        return buf.raw[:n.value].decode("utf-8", errors="replace")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cl_tokenizer_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class KvPool:

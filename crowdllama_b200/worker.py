@@ -65,8 +65,10 @@ class _Conn(socketserver.BaseRequestHandler):
 
 
 def serve(device: int, port: int, preset: str, model_name: str, max_batch: int = 8, greedy_tokens: int = 0, host="127.0.0.1",
-          ready_event=None, seed: int = 1234):
+          ready_event=None, seed: int = 1234, tokenizer: str | None = None, chat_family: str | None = None):
     e = eng.Engine(preset=preset, model_name=model_name, device=device, seed=seed, max_batch=max_batch, start_scheduler=True)
+    if tokenizer:
+        e.load_tokenizer(tokenizer, chat_family)      # HF tokenizer.json instead of the byte-level fallback
     sampling = eng.greedy(greedy_tokens, ignore_eos=True) if greedy_tokens > 0 else None   # None = Ollama defaults
     srv = WorkerServer((host, port), e, peer_id=f"b200-worker-{device}", sampling=sampling)
     if ready_event is not None:
@@ -86,9 +88,11 @@ def main():
     ap.add_argument("--model-name", default="llama3:8b")
     ap.add_argument("--max-batch", type=int, default=8)
     ap.add_argument("--greedy-tokens", type=int, default=0, help="> 0: force greedy with this num_predict (benchmarks)")
+    ap.add_argument("--tokenizer", default=None, help="path of an HF tokenizer.json (default: byte-level fallback)")
+    ap.add_argument("--chat-family", default=None, help="llama3 | mistral | zephyr | chatml (default: auto-detect)")
     a = ap.parse_args()
     print(f"worker on cuda:{a.device} port {a.port} serving {a.model_name}", flush=True)
-    serve(a.device, a.port, a.preset, a.model_name, a.max_batch, a.greedy_tokens)
+    serve(a.device, a.port, a.preset, a.model_name, a.max_batch, a.greedy_tokens, tokenizer=a.tokenizer, chat_family=a.chat_family)
 
 
 if __name__ == "__main__":

@@ -262,6 +262,22 @@ int cl_op_attn_prefill(int device, const uint16_t* q, const uint16_t* k, const u
 int cl_op_synth_weights(int device, uint64_t seed, int32_t tensor_key, int64_t n, float scale,
                         uint16_t* out_bf16);
 
+/* ---- tokenizer (host logic; usable without a GPU) --------------------------------------------
+ * Loader for HF `tokenizer.json` BPE tokenizers — SentencePiece-style (Llama-2 / Mistral / TinyLlama) and byte-level
+ * (Llama-3) — replacing what the Ollama server does upstream of the reference's handler (api.go:108-160; SURVEY.md
+ * §8f row 2).  chat_family: "llama3" | "mistral" | "zephyr" | "chatml" | NULL (auto from the added tokens). */
+typedef struct cl_tokenizer cl_tokenizer;
+int cl_tokenizer_load(const char* tokenizer_json_path, const char* chat_family, cl_tokenizer** out);
+void cl_tokenizer_free(cl_tokenizer* t);
+/* chat != 0: wrap text as one user turn + generation prompt first.  ids may be NULL to query *n_out. */
+int cl_tokenizer_encode(const cl_tokenizer* t, const char* text, size_t len, int32_t add_bos, int32_t chat,
+                        int32_t* ids, int32_t cap, int32_t* n_out);
+/* raw surface bytes, special tokens skipped (may end inside a UTF-8 sequence); buf may be NULL to query *len_out */
+int cl_tokenizer_decode(const cl_tokenizer* t, const int32_t* ids, int32_t n, char* buf, size_t cap, size_t* len_out);
+int cl_tokenizer_info(const cl_tokenizer* t, int32_t* vocab_size, int32_t* bos, int32_t* eos);
+/* install a tokenizer.json into a running engine (replaces the byte-level fallback behind cl_generate*, cl_tokenize) */
+int cl_engine_load_tokenizer(cl_engine* e, const char* tokenizer_json_path, const char* chat_family);
+
 /* ---- paged-KV allocator (host logic; usable without a GPU) ------------------------------ */
 typedef struct cl_kvpool cl_kvpool;
 int cl_kvpool_create(int32_t n_pages, int32_t page_size, cl_kvpool** out);

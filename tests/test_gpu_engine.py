@@ -243,6 +243,31 @@ def test_streaming_options_and_cancel_through_the_c_abi(scheduler):
         assert e.generate("tiny", "why is the sky blue? ☃", g).text == whole.text   # the engine is healthy afterwards
 
 
+@pytest.mark.parametrize("name", ["spm_legacy", "llama3"])
+def test_engine_with_a_tokenizer_json(name):
+    """an HF tokenizer.json replaces the byte-level fallback behind cl_generate / cl_tokenize."""
+    from pathlib import Path
+    gold = Path(__file__).resolve().parent / "golden" / "tokenizers" / f"{name}.tokenizer.json"
+    cfg = dict(oc.PRESETS["tiny-test"])
+    cfg["vocab_size"] = 1024
+    ref = eng.HfTokenizer(gold)
+    with eng.Engine(model=cfg, seed=3, model_name="tiny") as e:
+        with pytest.raises(eng.EngineError):
+            e.load_tokenizer(gold.parent / "does-not-exist.json")
+        e.load_tokenizer(gold)
+        text = "Why is the sky blue? It's 12:45 ☃"
+        assert list(e.tokenize(text)) == ref.encode(text)
+        r = e.generate("tiny", text, eng.greedy(12, ignore_eos=True))
+        assert r.n_prompt == len(ref.encode(text, add_bos=True, chat=True)) and r.n_generated == 12
+        assert r.text == e.detokenize(r.token_ids)
+        deltas = []
+        r2 = e.generate_stream("tiny", text, eng.greedy(12, ignore_eos=True), lambda d, ids: deltas.append(d) and False)
+        assert list(r2.token_ids) == list(r.token_ids) and "".join(deltas) == r.text
+    with eng.Engine(preset="tiny-test", seed=3) as e:                  # 512-entry model vocabulary < 702 tokenizer ids
+        with pytest.raises(eng.EngineError):
+            e.load_tokenizer(gold)
+
+
 @pytest.mark.parametrize("preset", ["tinyllama-1.1b"])
 def test_tinyllama_shapes_match_oracle(preset):
     cfg = dict(oc.PRESETS[preset])
