@@ -367,7 +367,11 @@ __global__ void __launch_bounds__(288, 1) decode_mega_kernel(const __grid_consta
   float* qbuf = a.q + (size_t)slot * a.q_dim;
   float* xatt = a.attn_x + (size_t)slot * a.q_dim;
   float* act = a.act + (size_t)slot * F;
-  const float2* rope = a.rope + (size_t)pos * HALF;
+  // RoPE row of the current position: one row serves all 32 layers, so it is staged in shared memory once — the P0
+  // epilogue sits between the q|k|v GEMV and barrier B0, where a global load costs a loaded L2 round trip per layer
+  float2* rope = reinterpret_cast<float2*>(red_acc + NW * REP * HD);   // [HALF]
+  for (int i = tid; i < HALF; i += 256) rope[i] = __ldg(a.rope + (size_t)pos * HALF + i);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   const int cur_pg = bt[pos / P], cur_off = pos % P;
   const float scale2 = rsqrtf((float)HD) * LOG2E;
 
@@ -640,7 +644,7 @@ bool mega_supported(int d, int d_ff, int head_dim, int n_heads, int n_kv, int pa
 
 int launch_decode_mega(const MegaArgs& a, cudaStream_t st) {
   static bool attr = false;
-  constexpr size_t smem = (size_t)NS * SLOT + 2 * NS * 8 + (8 + CAP4 + 8 + CAP4 * 16 + 2 * NW * REP + NW * REP * HD) * 4 + 128 + 1024;
+  constexpr size_t smem = (size_t)NS * SLOT + 2 * NS * 8 + (8 + CAP4 + 8 + CAP4 * 16 + 2 * NW * REP + NW * REP * HD + 2 * HALF) * 4 + 128 + 1024;
   if (!attr) {
     if (cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
