@@ -7,12 +7,26 @@
 
 namespace cl {
 
+// launch with or without the programmatic-dependent-launch attribute (the kernels call griddepcontrol.* either way)
+template <typename Kern, typename... Args>
+static int launch_k(Kern kern, dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...) == cudaSuccess ? 1 : -1;
+}
+
 // h[slot] += sum_s ypart[s][b]  (fixed order);  xn[b] = bf16(rmsnorm(h[slot]) * gain)
 // one CTA of 1024 threads per sequence: every thread owns <= 2 float4 of the row, all loads of a pass are independent
 __global__ void __launch_bounds__(1024) batch_resid_norm_kernel(float* __restrict__ h, int d, const float* __restrict__ ypart, int n_split,
                                                                 int B, const float* __restrict__ gain, float eps,
                                                                 __nv_bfloat16* __restrict__ xn, const int* __restrict__ slots) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* hr = h + (size_t)slots[b] * d;
   float4 v[2], g[2];
@@ -56,10 +70,9 @@ __global__ void __launch_bounds__(1024) batch_resid_norm_kernel(float* __restric
   }
 }
 int launch_batch_resid_norm(float* h, int d, const float* ypart, int n_split, int B, const float* gain, float eps, __nv_bfloat16* xn,
-                            const int* slots, cudaStream_t st) {
+                            const int* slots, cudaStream_t st, bool pdl) {
   if (d > 8192 || d % 4) return -1;
-  batch_resid_norm_kernel<<<B, 1024, 0, st>>>(h, d, ypart, n_split, B, gain, eps, xn, slots);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_k(batch_resid_norm_kernel, dim3(B), dim3(1024), st, pdl, h, d, ypart, n_split, B, gain, eps, xn, slots);
 }
 
 // xn[b] = bf16(rmsnorm(h[slots[b]]) * gain): one CTA of 1024 threads per sequence, one float4 per thread and pass
@@ -113,6 +126,8 @@ int launch_batch_norm(const float* h, int d, int B, const float* gain, float eps
 // q|k|v partials (rope-pair-interleaved columns) -> RoPE at pos[slot] -> q (fp32, bf16-rounded) and the paged cache
 __global__ void __launch_bounds__(256) batch_rope_append_kernel(const float* __restrict__ ypart, int n_split, int B, QkvEpi e,
                                                                 float* __restrict__ q_out, int q_stride, const int* __restrict__ slots) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y, slot = slots[b];
   const int HD = e.head_dim, half = HD >> 1;
   const int qkv_dim = (e.n_heads + 2 * e.n_kv) * HD;
@@ -144,10 +159,9 @@ __global__ void __launch_bounds__(256) batch_rope_append_kernel(const float* __r
   }
 }
 int launch_batch_rope_append(const float* ypart, int n_split, int B, const QkvEpi& e, float* q_out, int q_stride, const int* slots,
-                             cudaStream_t st) {
+                             cudaStream_t st, bool pdl) {
   const int pairs = (e.n_heads + 2 * e.n_kv) * e.head_dim / 2;
-  batch_rope_append_kernel<<<dim3((pairs + 255) / 256, B), 256, 0, st>>>(ypart, n_split, B, e, q_out, q_stride, slots);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_k(batch_rope_append_kernel, dim3((pairs + 255) / 256, B), dim3(256), st, pdl, ypart, n_split, B, e, q_out, q_stride, slots);
 }
 
 // x[slot][n] (fp32, already bf16-rounded) -> xb[b][n] bf16
@@ -170,6 +184,8 @@ int launch_batch_gather_bf16(const float* x, int n, int x_stride, __nv_bfloat16*
 
 // gate|up partials (interleaved pairs) -> act[b][i] = bf16(silu(g) * u)
 __global__ void batch_silu_kernel(const float* __restrict__ ypart, int n_split, int B, int d_ff, __nv_bfloat16* __restrict__ act) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d_ff; i += gridDim.x * blockDim.x) {
     float g = 0.f, u = 0.f;
@@ -180,9 +196,8 @@ __global__ void batch_silu_kernel(const float* __restrict__ ypart, int n_split, 
     act[(size_t)b * d_ff + i] = __float2bfloat16_rn(g / (1.0f + __expf(-g)) * u);
   }
 }
-int launch_batch_silu(const float* ypart, int n_split, int B, int d_ff, __nv_bfloat16* act, cudaStream_t st) {
-  batch_silu_kernel<<<dim3((d_ff + 255) / 256, B), 256, 0, st>>>(ypart, n_split, B, d_ff, act);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+int launch_batch_silu(const float* ypart, int n_split, int B, int d_ff, __nv_bfloat16* act, cudaStream_t st, bool pdl) {
+  return launch_k(batch_silu_kernel, dim3((d_ff + 255) / 256, B), dim3(256), st, pdl, ypart, n_split, B, d_ff, act);
 }
 
 // logits partial/tmp [b][vocab] -> logits[slot][vocab]

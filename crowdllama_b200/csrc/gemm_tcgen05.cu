@@ -75,10 +75,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // no-ops unless launched with the programmatic-serialization attribute (batched decode step)
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
+      // X is the previous kernel's output.  (Filling the ring with W tiles BEFORE the wait was tried and lost:
+      // B = 16 step 4.81 -> 5.12 ms — the early bulk stream slows the latency-bound glue kernel it overlaps with.)
+      pdl_wait();
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int bt_ = tile % (num_t * num_n), ks = tile / (num_t * num_n);
@@ -124,6 +128,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     }
   } else {
     // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+    pdl_wait();              // Y / the split-K workspace may still be read by the previous kernel
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -211,7 +216,7 @@ bool make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 namespace {
 
 template <int BT, int NST>
-cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st) {
+cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st, bool pdl) {
   auto kern = gemm_tcgen05_kernel<BT, NST>;
   constexpr size_t smem = (size_t)NST * (BM * BK * 2 + BT * BK * 2) + 1024 + 256;
   static bool attr = false;
@@ -222,8 +227,13 @@ cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const Gemm
   }
   const int tiles = ((p.T + BT - 1) / BT) * ((p.N + BM - 1) / BM) * (p.k_splits > 1 ? p.k_splits : 1);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, 192, smem, st>>>(mw, mx, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = la; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, mw, mx, p);
 }
 
 }  // namespace
@@ -231,7 +241,7 @@ cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const Gemm
 bool gemm_tcgen05_supported(int T, int N, int K) { return T > 0 && N > 0 && K > 0 && K % 8 == 0 && get_encode() != nullptr; }
 
 int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, const float* resid, int T, int N, int K,
-                     cudaStream_t st, int k_splits) {
+                     cudaStream_t st, int k_splits, bool pdl) {
   if (!gemm_tcgen05_supported(T, N, K)) return -1;
   if (resid && resid != Y) return -1;  // residual add is in place
   const int BT = T > 128 ? 256 : T > 64 ? 128 : T > 32 ? 64 : 32;
@@ -242,10 +252,10 @@ int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, c
   GemmParams p{Y, T, N, K, N, resid ? 1 : 0, k_splits};
   cudaError_t e;
   switch (BT) {
-    case 256: e = launch_inst<256, 4>(mw, mx, p, st); break;
-    case 128: e = launch_inst<128, 6>(mw, mx, p, st); break;
-    case 64: e = launch_inst<64, 8>(mw, mx, p, st); break;
-    default: e = launch_inst<32, 8>(mw, mx, p, st); break;
+    case 256: e = launch_inst<256, 4>(mw, mx, p, st, pdl); break;
+    case 128: e = launch_inst<128, 6>(mw, mx, p, st, pdl); break;
+    case 64: e = launch_inst<64, 8>(mw, mx, p, st, pdl); break;
+    default: e = launch_inst<32, 8>(mw, mx, p, st, pdl); break;
   }
   return e == cudaSuccess ? 1 : -1;
 }

@@ -156,7 +156,7 @@ int sm_count();
 // X bf16 [T][K] row-major, W bf16 [N][K] row-major -> Y fp32 [T][N] (+= resid when resid != nullptr)
 // k_splits > 1: split-K, partial s is written to Y + s*T*N (no residual); the consumer sums the partials
 int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, const float* resid, int T, int N, int K,
-                     cudaStream_t st, int k_splits = 1);
+                     cudaStream_t st, int k_splits = 1, bool pdl = false);
 bool gemm_tcgen05_supported(int T, int N, int K);
 // xn[t] = bf16(rmsnorm(h[t]) * gain)
 int launch_rmsnorm_bf16(const float* h, const float* gain, float eps, __nv_bfloat16* out, int T, int d, cudaStream_t st);
@@ -203,13 +203,13 @@ int launch_gemm_skinny(const SkinnyArgs& a, cudaStream_t st, bool pdl);
 
 // ---- batched decode glue (batch_kernels.cu) ------------------------------------------------------
 int launch_batch_resid_norm(float* h, int d, const float* ypart, int n_split, int B, const float* gain, float eps, __nv_bfloat16* xn,
-                            const int* slots, cudaStream_t st);
+                            const int* slots, cudaStream_t st, bool pdl = false);
 // xn[b] = bf16(rmsnorm(h[slots[b]]) * gain)   (PDL-aware)
 int launch_batch_norm(const float* h, int d, int B, const float* gain, float eps, __nv_bfloat16* xn, const int* slots, cudaStream_t st, bool pdl);
 int launch_batch_rope_append(const float* ypart, int n_split, int B, const QkvEpi& e, float* q_out, int q_stride, const int* slots,
-                             cudaStream_t st);
+                             cudaStream_t st, bool pdl = false);
 int launch_batch_gather_bf16(const float* x, int n, int x_stride, __nv_bfloat16* xb, const int* slots, int B, cudaStream_t st);
-int launch_batch_silu(const float* ypart, int n_split, int B, int d_ff, __nv_bfloat16* act, cudaStream_t st);
+int launch_batch_silu(const float* ypart, int n_split, int B, int d_ff, __nv_bfloat16* act, cudaStream_t st, bool pdl = false);
 int launch_batch_scatter_rows(const float* y, int n, float* out, int out_stride, const int* slots, int B, cudaStream_t st);
 int launch_embed_rows(const __nv_bfloat16* table, int d, const int* ids_dev, float* h, int T, cudaStream_t st);
 
