@@ -123,13 +123,14 @@ int Engine::init(const cl_engine_config& c) {
   if (rc) return rc;
   rc = alloc_state();
   if (rc) return rc;
-  if (use_mega_) {
+  if (cfg.head_dim == 128 && page_size_ == 32) {   // pool-wide KV tensor maps: persistent kernel + tensor-core batched attention
     const uint64_t rows = (uint64_t)cfg.n_layers * n_pages_ * cfg.n_kv_heads * page_size_;
-    if (rows >= (1ull << 31) || !make_tmap_2d_bf16(&kmap_, kpool_, rows, cfg.head_dim, 64, 32) ||
-        !make_tmap_2d_bf16(&vmap_, vpool_, rows, cfg.head_dim, 64, 32)) {
-      fprintf(stderr, "[clengine] KV tensor maps unavailable: using the per-op decode path\n");
-      use_mega_ = false;
-    }
+    have_kv_maps_ = rows < (1ull << 31) && make_tmap_2d_bf16(&kmap_, kpool_, rows, cfg.head_dim, 64, 32) &&
+                    make_tmap_2d_bf16(&vmap_, vpool_, rows, cfg.head_dim, 64, 32);
+  }
+  if (use_mega_ && !have_kv_maps_) {
+    fprintf(stderr, "[clengine] KV tensor maps unavailable: using the per-op decode path\n");
+    use_mega_ = false;
   }
   if (use_mega_) {
     std::vector<MegaLayer> ml(cfg.n_layers);
@@ -567,7 +568,11 @@ int Engine::enqueue_step_batched(int B) {
     a.slots = d_slots_; a.batch = B; a.n_heads = cfg.n_heads; a.n_kv = cfg.n_kv_heads; a.head_dim = cfg.head_dim;
     // many sequences already fill the machine: fewer KV splits per sequence (cheaper combine, fewer CTAs)
     a.page_size = page_size_; a.nsplit = std::max(1, std::min(nsplit_, batch_attn_ctas / (cfg.n_kv_heads * B))); a.pdl_early = bp ? 1 : 0;
-    CL_LAUNCH(launch_attn_decode(a, stream_, bp));
+    static const bool attn_tc = env_int("CL_BATCH_ATTN_TC", 1) != 0;
+    if (attn_tc && have_kv_maps_ && attn_decode_tc_supported(cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, page_size_, a.nsplit))
+      CL_LAUNCH(launch_attn_decode_tc(a, kmap_, vmap_, (long long)l * n_pages_ * cfg.n_kv_heads * page_size_, stream_, bp));
+    else
+      CL_LAUNCH(launch_attn_decode(a, stream_, bp));
     CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.part, nullptr, B, d, q_dim_, stream_, s_o, bp));
     CL_LAUNCH(launch_batch_resid_norm(d_h_, d, w.part, s_o, B, L.ffn_norm, cfg.rms_eps, w.xn, d_slots_, stream_, bp));
     CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.part, nullptr, B, 2 * F, d, stream_, s_gu, bp));

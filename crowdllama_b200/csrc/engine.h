@@ -182,6 +182,7 @@ class Engine {
   bool use_flags_ = false, want_timeline_ = false, use_mega_ = false;
   MegaLayer* d_mega_layers_ = nullptr;
   CUtensorMap kmap_{}, vmap_{};
+  bool have_kv_maps_ = false;
   long long* d_timeline_ = nullptr;
   unsigned* d_sync_ = nullptr;
   int n_sync_ = 0;

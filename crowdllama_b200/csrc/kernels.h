@@ -101,6 +101,11 @@ struct StepTailArgs {                // argmax over logits, advance the sequence
 // every launcher returns the number of kernels it enqueued (for cl_stats.kernel_launches)
 int launch_gemv(int variant, int epi, bool norm, const GemvArgs& a, cudaStream_t st, bool pdl, int* n_ctas = nullptr);
 int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
+// tensor-core variant for the batched step (attn_decode_tc.cu): head_dim 128, 4 q heads per kv head, page 32;
+// kmap / vmap = pool-wide 2-D tensor maps (make_tmap_2d_bf16, box {64, 32}), layer_row0 = first row of this layer
+bool attn_decode_tc_supported(int n_heads, int n_kv, int head_dim, int page_size, int nsplit);
+int launch_attn_decode_tc(const AttnDecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, long long layer_row0, cudaStream_t st,
+                          bool pdl);
 int launch_embed(const __nv_bfloat16* table, int d, const int* tok, float* h, int h_stride, const int* slots,
                  int batch, cudaStream_t st);
 int launch_step_tail(const StepTailArgs& a, cudaStream_t st);
