@@ -14,6 +14,8 @@
 
 namespace cl {
 
+static int pick_splits(int n_rows, int K);   // batched-decode split-K rule (defined with the batched step)
+
 enum { K_EMBED = 0, K_LM_HEAD = 1, K_FINAL_NORM = 2, K_ATTN_NORM = 3, K_WQ = 4, K_WK = 5, K_WV = 6, K_WO = 7,
        K_FFN_NORM = 8, K_WGATE = 9, K_WUP = 10, K_WDOWN = 11 };
 static constexpr float kLinearScale = 1.35e-4f;
@@ -311,6 +313,10 @@ int Engine::alloc_state() {
     use_skinny_ = env_int("CL_BATCH_SKINNY", 0) != 0;   // fused-epilogue variant: measured 5.8-6.2 ms vs 4.7 ms per B=8 step (profiles/README.md)
     // split-K partial workspace: the old path uses <= 4 splits; the skinny path up to K/64/kb splits of [B][N]
     size_t part_floats = 4 * Bm * widest;
+    for (int nk : {0, 1, 2, 3}) {   // split-K partials of the four projections (pick_splits)
+      const int N = nk == 0 ? qkv_dim_ : nk == 2 ? 2 * cfg.d_ff : d, K = nk == 1 ? q_dim_ : nk == 3 ? cfg.d_ff : d;
+      part_floats = std::max(part_floats, (size_t)pick_splits(N, K) * Bm * (size_t)N);
+    }
     if (use_skinny_) {
       const int kb_small = env_int("CL_SKINNY_KB", 4), kb_gu = env_int("CL_SKINNY_KB_GU", 8), kb_lm = env_int("CL_SKINNY_KB_LM", 16);
       part_floats = std::max(part_floats, (size_t)skinny_splits(d, kb_small) * Bm * qkv_dim_);
@@ -471,11 +477,24 @@ int Engine::enqueue_step(int B, bool tail) {
 }
 
 // ---- batched token step (B >= 2): tensor-core projections (tcgen05, split-K) + per-sequence glue -----
+// split-K count of a batched-decode projection: the launch is as slow as its busiest CTA, i.e.
+// rounds(= ceil(tiles * s / SMs)) x k-blocks per unit.  224 gate|up tiles on 148 SMs cost 2 x 64 k-blocks unsplit but
+// 8 x 13 with 5 splits (ideal 96.9); down 56 -> 50 with 9.  Among the counts within 10 % of the best the smallest wins
+// (fewer partials for the consumer kernel to sum).
 static int pick_splits(int n_rows, int K) {
-  const int tiles = (n_rows + 127) / 128, nkb = (K + 63) / 64;
-  int s = std::max(1, std::min(4, sm_count() / std::max(1, tiles)));
-  while (s > 1 && ((nkb + s - 1) / s) * (s - 1) >= nkb) --s;   // every split must own >= 1 k-block
-  return s;
+  const int tiles = (n_rows + 127) / 128, nkb = (K + 63) / 64, sms = sm_count();
+  int best_cost = 1 << 30;
+  int cost_of[17];
+  for (int s = 1; s <= 16; ++s) {
+    const int kbp = (nkb + s - 1) / s;
+    cost_of[s] = -1;
+    if ((nkb + kbp - 1) / kbp != s) continue;                 // every split must own >= 1 k-block
+    cost_of[s] = ((tiles * s + sms - 1) / sms) * kbp;
+    best_cost = std::min(best_cost, cost_of[s]);
+  }
+  for (int s = 1; s <= 16; ++s)
+    if (cost_of[s] >= 0 && cost_of[s] * 10 <= best_cost * 11) return s;
+  return 1;
 }
 
 // ---- batched token step, v2: skinny tensor-core projections with fused epilogues (gemm_skinny.cu), 7 kernels per

@@ -134,7 +134,7 @@ def test_batched_decode_matches_single_and_oracle(monkeypatch, batch_gemm):
 
 @pytest.mark.parametrize("skinny", ["0", "1"])
 def test_batched_decode_llama_shapes(monkeypatch, skinny):
-    """Batched tensor-core step at Llama-3-8B layer shapes (2 layers, split-K 3/4/1/4) vs the oracle, teacher-forced.
+    """Batched tensor-core step at Llama-3-8B layer shapes (2 layers, split-K 3/4/5/9) vs the oracle, teacher-forced.
     skinny=1: the fused-epilogue projections of gemm_skinny.cu (dynamic split-K units, owner reduction)."""
     monkeypatch.setenv("CL_BATCH_SKINNY", skinny)
     cfg = dict(oc.PRESETS["llama3-8b"])
