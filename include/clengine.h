@@ -275,7 +275,8 @@ int cl_tokenizer_encode(const cl_tokenizer* t, const char* text, size_t len, int
 /* raw surface bytes, special tokens skipped (may end inside a UTF-8 sequence); buf may be NULL to query *len_out */
 int cl_tokenizer_decode(const cl_tokenizer* t, const int32_t* ids, int32_t n, char* buf, size_t cap, size_t* len_out);
 int cl_tokenizer_info(const cl_tokenizer* t, int32_t* vocab_size, int32_t* bos, int32_t* eos);
-/* install a tokenizer.json into a running engine (replaces the byte-level fallback behind cl_generate*, cl_tokenize) */
+/* install a tokenizer.json into an engine (replaces the byte-level fallback behind cl_generate*, cl_tokenize).
+ * Call it before the engine serves requests: in-flight cl_generate calls tokenise without a lock. */
 int cl_engine_load_tokenizer(cl_engine* e, const char* tokenizer_json_path, const char* chat_family);
 
 /* ---- paged-KV allocator (host logic; usable without a GPU) ------------------------------ */

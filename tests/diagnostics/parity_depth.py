@@ -5,7 +5,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from crowdllama_b200 import engine as eng  # noqa: E402
 from oracle import oracle as oc  # noqa: E402
