@@ -9,8 +9,8 @@
 //   added tokens       leftmost-longest match on the raw text (chat markers, <s>, </s>, ...)
 //   normalizer         null | Prepend | Replace(String) | Sequence of those
 //   pre_tokenizer      null | Metaspace | ByteLevel | Split(regex) + ByteLevel   (GPT-2 and Llama-3 regex flavours,
-//                      implemented as hand-written scanners; Unicode classes \p{L} \p{N} \s from range tables that
-//                      cover the major scripts — exotic code points fall into "other")
+//                      implemented as hand-written scanners; Unicode classes \p{L} \p{N} from generated range tables
+//                      (unicode_tables.inc), \s = the White_Space property)
 //   model              BPE: vocab, merges ("a b" or [a, b]), byte_fallback, ignore_merges, unk_token
 //   decoder            ByteLevel | SentencePiece chain (Replace ▁, ByteFallback, Fuse, Strip)
 #include <algorithm>
@@ -177,20 +177,7 @@ bool in_ranges(uint32_t cp, const Range* r, size_t n) {
   }
   return false;
 }
-// \p{L}: the letter blocks of the major scripts (sorted, disjoint)
-const Range kLetters[] = {
-    {0x41, 0x5A}, {0x61, 0x7A}, {0xAA, 0xAA}, {0xB5, 0xB5}, {0xBA, 0xBA}, {0xC0, 0xD6}, {0xD8, 0xF6}, {0xF8, 0x2C1}, {0x2C6, 0x2D1},
-    {0x2E0, 0x2E4}, {0x370, 0x374}, {0x376, 0x377}, {0x37A, 0x37D}, {0x37F, 0x37F}, {0x386, 0x386}, {0x388, 0x3FF}, {0x400, 0x481},
-    {0x48A, 0x52F}, {0x531, 0x556}, {0x561, 0x587}, {0x5D0, 0x5EA}, {0x620, 0x64A}, {0x66E, 0x66F}, {0x671, 0x6D3}, {0x6FA, 0x6FC},
-    {0x904, 0x939}, {0x958, 0x961}, {0x985, 0x9B9}, {0xE01, 0xE30}, {0xE40, 0xE46}, {0x10A0, 0x10FF}, {0x1100, 0x11FF}, {0x1E00, 0x1FBC},
-    {0x1FC2, 0x1FFC}, {0x2C00, 0x2CE4}, {0x3005, 0x3006}, {0x3041, 0x3096}, {0x309D, 0x309F}, {0x30A1, 0x30FA}, {0x30FC, 0x30FF},
-    {0x3105, 0x312F}, {0x3131, 0x318E}, {0x3400, 0x4DBF}, {0x4E00, 0x9FFF}, {0xA000, 0xA48C}, {0xAC00, 0xD7A3}, {0xF900, 0xFAFF},
-    {0xFB00, 0xFB06}, {0xFB1D, 0xFDFB}, {0xFE70, 0xFEFC}, {0xFF21, 0xFF3A}, {0xFF41, 0xFF5A}, {0xFF66, 0xFFDC}, {0x10000, 0x100FA},
-    {0x1D400, 0x1D7CB}, {0x20000, 0x2FA1F}, {0x30000, 0x3134A}};
-const Range kNumbers[] = {
-    {0x30, 0x39}, {0xB2, 0xB3}, {0xB9, 0xB9}, {0xBC, 0xBE}, {0x660, 0x669}, {0x6F0, 0x6F9}, {0x966, 0x96F}, {0x9E6, 0x9EF}, {0xE50, 0xE59},
-    {0x2070, 0x2070}, {0x2074, 0x2079}, {0x2080, 0x2089}, {0x2150, 0x2189}, {0x2460, 0x249B}, {0x24EA, 0x24FF}, {0x2776, 0x2793},
-    {0x3007, 0x3007}, {0x3021, 0x3029}, {0x3220, 0x3229}, {0x3280, 0x3289}, {0xFF10, 0xFF19}, {0x1D7CE, 0x1D7FF}};
+#include "unicode_tables.inc"   // kLetters / kNumbers: exact \\p{L} and \\p{N} ranges (tools/gen_unicode_tables.py)
 bool is_letter(uint32_t cp) { return in_ranges(cp, kLetters, sizeof kLetters / sizeof *kLetters); }
 bool is_number(uint32_t cp) { return in_ranges(cp, kNumbers, sizeof kNumbers / sizeof *kNumbers); }
 bool is_space(uint32_t cp) {

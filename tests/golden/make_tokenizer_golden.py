@@ -7,6 +7,7 @@ components the target model families ship in their tokenizer.json:
   metaspace    newer SentencePiece conversions: Metaspace pre-tokenizer (prepend_scheme "first", split False)
   llama3       Llama-3: Split(<tiktoken cl100k-style regex>) + ByteLevel, BPE with ignore_merges, ByteLevel decoder,
                "<|begin_of_text|>" ... "<|eot_id|>" added tokens
+  gpt2         GPT-2 / Qwen-style: ByteLevel pre-tokenizer with its built-in regex, "<|endoftext|>", "<|im_start|>"
 and every case string is encoded / decoded by the library.  The C++ implementation must reproduce ids and text.
 
     python tests/golden/make_tokenizer_golden.py      # rewrites tests/golden/tokenizers/*.json
@@ -71,9 +72,19 @@ def llama3() -> Tokenizer:
     return tok
 
 
+def gpt2() -> Tokenizer:
+    tok = Tokenizer(models.BPE())
+    tok.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False, trim_offsets=True, use_regex=True)
+    tok.decoder = decoders.ByteLevel(add_prefix_space=True, trim_offsets=True, use_regex=True)
+    tr = trainers.BpeTrainer(vocab_size=900, special_tokens=[], initial_alphabet=pre_tokenizers.ByteLevel.alphabet(), show_progress=False)
+    tok.train_from_iterator(CORPUS, tr)
+    tok.add_special_tokens([AddedToken(t, special=True, normalized=False) for t in ["<|endoftext|>", "<|im_start|>", "<|im_end|>"]])
+    return tok
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
-    for name, tok in (("spm_legacy", spm(False)), ("metaspace", spm(True)), ("llama3", llama3())):
+    for name, tok in (("spm_legacy", spm(False)), ("metaspace", spm(True)), ("llama3", llama3()), ("gpt2", gpt2())):
         tok.save(str(OUT / f"{name}.tokenizer.json"))
         cases = []
         for text in CASES:
