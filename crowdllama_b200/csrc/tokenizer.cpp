@@ -308,6 +308,8 @@ class HfBpeTokenizer : public Tokenizer {
   std::unordered_map<std::string, int> vocab_;
   std::vector<std::string> id_to_tok_;
   std::vector<char> special_;                         // id -> skipped on decode
+  std::vector<char> is_added_;                        // id -> added token (surface form = content, not byte-level mapped)
+  bool added_first_[256] = {};                        // bytes that can start an added token
   std::unordered_map<uint64_t, std::pair<int, int>> merges_;   // (a << 32 | b) -> (rank, merged id)
   std::vector<std::pair<std::string, int>> added_;    // content, id (sorted by length desc)
   int unk_ = -1, bos_ = -1, eos_ = -1, eot_ = -1, byte_tok_[256];
@@ -354,6 +356,8 @@ bool HfBpeTokenizer::load(const std::string& path, const std::string& chat_famil
     std::sort(added_.begin(), added_.end(), [](auto& x, auto& y) { return x.first.size() > y.first.size(); });
   }
   special_.resize(id_to_tok_.size(), 0);
+  is_added_.assign(id_to_tok_.size(), 0);
+  for (auto& at : added_) { is_added_[at.second] = 1; added_first_[(unsigned char)at.first[0]] = true; }
   // merges
   if (const JVal* mg = model->get("merges")) {
     int rank = 0;
@@ -535,6 +539,7 @@ std::vector<int32_t> HfBpeTokenizer::encode(const std::string& text, bool add_bo
   bool first = true;
   for (size_t i = 0; i < text.size();) {
     int hit = -1; size_t hit_len = 0;
+    if (!added_first_[(unsigned char)text[i]]) { ++i; continue; }
     for (auto& at : added_)   // sorted by length: the first hit is the longest
       if (at.first.size() <= text.size() - i && text.compare(i, at.first.size(), at.first) == 0) { hit = at.second; hit_len = at.first.size(); break; }
     if (hit < 0) { ++i; continue; }
@@ -555,9 +560,7 @@ std::string HfBpeTokenizer::decode_bytes(const std::vector<int32_t>& ids) const 
     if (id < 0 || id >= (int)id_to_tok_.size() || special_[id]) continue;
     const std::string& t = id_to_tok_[id];
     if (!spm_decoder_ && byte_level_) {
-      bool is_added = false;
-      for (auto& at : added_) if (at.second == id) { is_added = true; break; }
-      if (is_added) { out += t; continue; }
+      if (is_added_[id]) { out += t; continue; }
       for (size_t i = 0; i < t.size();) {
         int n;
         const uint32_t cp = next_cp(t, i, &n);
