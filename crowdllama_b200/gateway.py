@@ -197,3 +197,28 @@ def make_server(worker_addrs, port: int = 9001, host: str = "127.0.0.1", seed: i
     srv.counts, srv.lock = {}, threading.Lock()
     srv.table.start()
     return srv
+
+
+def main():
+    """python -m crowdllama_b200.gateway --port 9001 --worker 127.0.0.1:9101 --worker 127.0.0.1:9102 ..."""
+    import argparse
+    ap = argparse.ArgumentParser(description="Ollama-compatible gateway stand-in in front of B200 worker peers")
+    ap.add_argument("--host", default="127.0.0.1")
+    ap.add_argument("--port", type=int, default=9001)                      # the reference gateway's default port
+    ap.add_argument("--worker", action="append", default=[], help="host:port of a worker peer (repeatable)")
+    ap.add_argument("--seed", type=int, default=0, help="seed of the random tie-break in FindBestWorker")
+    a = ap.parse_args()
+    addrs = []
+    for w in a.worker or ["127.0.0.1:9101"]:
+        h, _, p = w.rpartition(":")
+        addrs.append((h or "127.0.0.1", int(p)))
+    srv = make_server(addrs, port=a.port, host=a.host, seed=a.seed)
+    print(f"gateway on http://{a.host}:{a.port} -> workers {addrs}", flush=True)
+    try:
+        srv.serve_forever(poll_interval=0.2)
+    finally:
+        srv.server_close()
+
+
+if __name__ == "__main__":
+    main()
