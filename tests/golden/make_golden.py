@@ -7,7 +7,7 @@ architecture that IS importable here: HF transformers' LlamaForCausalLM / Mistra
 run on CPU in float32 over bf16-representable seeded weights.
 
   python tests/golden/make_golden.py      -> tests/golden/hf_tiny_llama.npz, hf_tiny_mistral.npz,
-                                              synth_kat.npz
+                                              hf_tiny_llama3geom.npz, synth_kat.npz
 
 Fixtures are small (< 1 MB each) and committed; tests never import transformers.
 """
@@ -31,6 +31,11 @@ def hf_fixture(kind: str, path: Path, seed: int):
     if kind == "llama":
         cfg = dict(n_layers=2, d_model=128, n_heads=2, n_kv_heads=1, head_dim=64, d_ff=256, vocab_size=256,
                    max_seq_len=64, rope_theta=10000.0, rms_eps=1e-5)
+    elif kind == "llama3geom":
+        # the head geometry of Llama-3-8B / Mistral-7B (head_dim 128, 4 query heads per kv head, rope theta 5e5)
+        # on a small residual width: pins the oracle's RoPE pairing and GQA grouping for exactly that geometry
+        cfg = dict(n_layers=2, d_model=128, n_heads=4, n_kv_heads=1, head_dim=128, d_ff=256, vocab_size=256,
+                   max_seq_len=64, rope_theta=500000.0, rms_eps=1e-5)
     else:
         cfg = dict(n_layers=2, d_model=128, n_heads=4, n_kv_heads=1, head_dim=64, d_ff=192, vocab_size=320,
                    max_seq_len=64, rope_theta=1e6, rms_eps=1e-5)
@@ -41,7 +46,7 @@ def hf_fixture(kind: str, path: Path, seed: int):
                   head_dim=cfg["head_dim"],
                   attention_bias=False, hidden_act="silu")
     torch.manual_seed(seed)
-    if kind == "llama":
+    if kind in ("llama", "llama3geom"):
         model = LlamaForCausalLM(LlamaConfig(mlp_bias=False, **common))
     else:
         model = MistralForCausalLM(MistralConfig(sliding_window=None, **common))
@@ -93,6 +98,12 @@ def synth_kat(path: Path):
 
 
 if __name__ == "__main__":
-    hf_fixture("llama", OUT / "hf_tiny_llama.npz", 0)
-    hf_fixture("mistral", OUT / "hf_tiny_mistral.npz", 1)
-    synth_kat(OUT / "synth_kat.npz")
+    only = sys.argv[1] if len(sys.argv) > 1 else None     # e.g. `make_golden.py llama3geom` regenerates one fixture
+    if only in (None, "llama"):
+        hf_fixture("llama", OUT / "hf_tiny_llama.npz", 0)
+    if only in (None, "mistral"):
+        hf_fixture("mistral", OUT / "hf_tiny_mistral.npz", 1)
+    if only in (None, "llama3geom"):
+        hf_fixture("llama3geom", OUT / "hf_tiny_llama3geom.npz", 2)
+    if only in (None, "synth"):
+        synth_kat(OUT / "synth_kat.npz")

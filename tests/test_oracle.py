@@ -23,7 +23,7 @@ def _load_hf(name):
     return z, cfg, m
 
 
-@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz"])
+@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz", "hf_tiny_llama3geom.npz"])
 def test_oracle_matches_hf_fp32(fixture):
     """act_rounding=0 (pure fp32 activations) must reproduce HF float32 logits: pins RoPE pairing,
     GQA head mapping, norm placement, SwiGLU and the untied LM head."""
@@ -38,7 +38,7 @@ def test_oracle_matches_hf_fp32(fixture):
     assert (logits.argmax(-1) == ref.argmax(-1)).all()
 
 
-@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz"])
+@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz", "hf_tiny_llama3geom.npz"])
 def test_oracle_v1_rounding_close_to_hf(fixture):
     """cl-llama v1 numerics (bf16 rounding points) stay within a bf16-sized band of HF fp32."""
     z, cfg, m = _load_hf(fixture)
