@@ -70,8 +70,14 @@ def worker_api_handler(engine: "eng.Engine", sampling: "eng.Sampling | None" = N
             raise HandlerError("expected GenerateRequest, got different message type")
         return generate_req
 
+    def _raw(generate_req) -> bool:
+        # raw = "do not apply the chat template": only the byte-level entry points of libclengine know how
+        return bool(generate_req.options and generate_req.options.raw and hasattr(engine, "handle_message_stream"))
+
     def handler(ctx, req: BaseMessage) -> BaseMessage:
         generate_req = _request(req)
+        if _raw(generate_req):
+            return worker_api_handler_bytes(engine, sampling)(ctx, req)
         try:
             r = engine.generate(generate_req.model, generate_req.prompt, merge_sampling(sampling, generate_req.options))
         except eng.EngineError as ex:                                # api.go:63-68 wraps the backend error
@@ -80,6 +86,8 @@ def worker_api_handler(engine: "eng.Engine", sampling: "eng.Sampling | None" = N
 
     def stream(ctx, req: BaseMessage, emit) -> None:
         generate_req = _request(req)
+        if _raw(generate_req):
+            return worker_api_handler_bytes(engine, sampling).stream(ctx, req, emit)
         if not hasattr(engine, "generate_stream"):                   # engines without streaming answer in one frame
             return emit(handler(ctx, req))
 

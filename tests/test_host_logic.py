@@ -245,6 +245,30 @@ def test_request_options_override_worker_defaults_field_by_field():
     assert base.temperature == pytest.approx(0.8) and base.seed == 11  # the default object is not mutated
 
 
+def test_raw_requests_take_the_byte_level_entry_point():
+    """options.raw (no chat template) is implemented inside libclengine: the closure hands such requests over as bytes."""
+    from crowdllama_b200.pb import GenerateOptions
+    seen = []
+
+    class Bytes(_MockEngine):
+        def handle_message(self, req, sampling=None):
+            seen.append(BaseMessage.decode(req).generate_request)
+            return H._response("test-model", "raw answer", True, "stop").encode()
+
+        def handle_message_stream(self, req, sampling=None, on_frame=None):
+            on_frame(H._response("test-model", "raw ", False).encode())
+            on_frame(H._response("test-model", "", True, "length").encode())
+            return 2
+
+    h = H.worker_api_handler(Bytes())
+    g = h(None, H.create_generate_request("test-model", "p", False, GenerateOptions(raw=True, temperature=0.0))).generate_response
+    assert g.response == "raw answer" and seen[0].options.raw and seen[0].options.temperature == 0.0
+    assert h(None, H.create_generate_request("test-model", "p", False, GenerateOptions(temperature=0.0))).generate_response.response == "PB Hello, p"
+    frames = []
+    h.stream(None, H.create_generate_request("test-model", "p", True, GenerateOptions(raw=True)), frames.append)
+    assert [f.generate_response.done for f in frames] == [False, True] and frames[-1].generate_response.done_reason == "length"
+
+
 def test_streaming_frames_on_the_inference_stream():
     """stream=true -> several length-prefixed GenerateResponse frames, Done only on the last."""
     class Duplex(io.BytesIO):
