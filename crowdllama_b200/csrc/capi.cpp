@@ -409,6 +409,26 @@ int cl_decode_greedy_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs, c
   std::lock_guard<std::mutex> lk(e->impl.mu_);
   CL_GUARD(return e->impl.decode_greedy(seqs, n_seqs, first_ids, n_steps, ids_out, device_ms);)
 }
+int cl_decode_step_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs, const int32_t* ids, float* logits_out, int32_t* argmax_out) {
+  if (!e || !seqs || !ids) return CL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(e->impl.mu_);
+  CL_GUARD(return e->impl.decode_step_batch(seqs, n_seqs, ids, logits_out, argmax_out);)
+}
+int cl_seq_fake_fill(cl_engine* e, cl_seq_t s, int32_t n_tokens) {
+  if (!e) return CL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(e->impl.mu_);
+  CL_GUARD(return e->impl.seq_fake_fill(s, n_tokens);)
+}
+int cl_debug_kv(cl_engine* e, cl_seq_t s, int32_t layer, int32_t which, int32_t t0, int32_t n, float* out) {
+  if (!e || !out) return CL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(e->impl.mu_);
+  CL_GUARD(return e->impl.debug_kv(s, layer, which, t0, n, out);)
+}
+int cl_time_dominant_kernel(cl_engine* e, cl_seq_t s, int32_t first_id, int32_t n_steps, float* kernel_ms, float* step_ms) {
+  if (!e) return CL_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(e->impl.mu_);
+  CL_GUARD(return e->impl.time_dominant_kernel(s, first_id, n_steps, kernel_ms, step_ms);)
+}
 int cl_debug_timeline(cl_engine* e, int64_t* out, int32_t n) {
   if (!e || !out) return CL_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(e->impl.mu_);

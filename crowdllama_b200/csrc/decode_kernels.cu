@@ -18,18 +18,19 @@
 
 namespace cl {
 
-static int g_sm_count = 0;
+static int g_sm_count[64] = {0};   // per device ordinal (one engine per GPU process, but a process may open several)
 static bool g_carveout_max = true;
 int sm_count() {
-  if (!g_sm_count) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = g_sm_count[dev & 63];
+  if (!n) {
     const char* cv = getenv("CL_CARVEOUT_MAX");
     if (cv && *cv == '0') g_carveout_max = false;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
   }
-  return g_sm_count;
+  return n;
 }
 
 // Every kernel of the token step asks for the maximum shared-memory carve-out: a different L1/shared
@@ -921,6 +922,49 @@ int launch_fill_u16(uint16_t* p, int64_t n, uint16_t v, cudaStream_t st) {
   if (blocks > 1184) blocks = 1184;
   if (blocks < 1) blocks = 1;
   fill_u16_kernel<<<blocks, 256, 0, st>>>(p, n, v);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ---- parity aid: fill a sequence's paged K/V with the oracle's cheap pattern (oracle/llama_oracle.c oc_seq_fake_fill:
+// every value is n/128 with n in [-128, 127], exact in bf16), the same in every layer.  i = token * kv_dim + head * hd + dim.
+__global__ void fake_fill_kv_kernel(__nv_bfloat16* kpool, __nv_bfloat16* vpool, size_t layer_elems, int n_layers, const int* bt,
+                                    int page, int n_kv, int hd, long long n_elems) {
+  const int kvd = n_kv * hd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long u = (unsigned long long)i;
+    const float kv = (float)((int)(((u * 2654435761ull) >> 24) & 0xffull) - 128) * (1.0f / 128.0f);
+    const float vv = (float)((int)(((u * 40503ull) >> 8) & 0xffull) - 128) * (1.0f / 128.0f);
+    const int t = (int)(i / kvd), r = (int)(i - (long long)t * kvd), g = r / hd, j = r - g * hd;
+    const size_t dst = (((size_t)bt[t / page] * n_kv + g) * page + (t % page)) * hd + j;
+    const __nv_bfloat16 kb = __float2bfloat16_rn(kv), vb = __float2bfloat16_rn(vv);
+    for (int l = 0; l < n_layers; ++l) { kpool[(size_t)l * layer_elems + dst] = kb; vpool[(size_t)l * layer_elems + dst] = vb; }
+  }
+}
+int launch_fake_fill_kv(__nv_bfloat16* kpool, __nv_bfloat16* vpool, size_t layer_elems, int n_layers, const int* block_table,
+                        int page_size, int n_kv, int head_dim, int n_tokens, cudaStream_t st) {
+  const long long n = (long long)n_tokens * n_kv * head_dim;
+  if (n <= 0) return 0;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  fake_fill_kv_kernel<<<blocks, 256, 0, st>>>(kpool, vpool, layer_elems, n_layers, block_table, page_size, n_kv, head_dim, n);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// parity aid: gather one layer's cached K or V rows of a sequence from the paged pool -> dense fp32 [n][n_kv*hd]
+__global__ void gather_kv_kernel(const __nv_bfloat16* pool, const int* bt, int page, int n_kv, int hd, int t0, long long n_elems, float* out) {
+  const int kvd = n_kv * hd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (long long)gridDim.x * blockDim.x) {
+    const int t = t0 + (int)(i / kvd), r = (int)(i % kvd), g = r / hd, j = r - g * hd;
+    out[i] = __bfloat162float(pool[(((size_t)bt[t / page] * n_kv + g) * page + (t % page)) * hd + j]);
+  }
+}
+int launch_gather_kv(const __nv_bfloat16* pool_layer, const int* block_table, int page_size, int n_kv, int head_dim, int t0, int n,
+                     float* out, cudaStream_t st) {
+  const long long ne = (long long)n * n_kv * head_dim;
+  if (ne <= 0) return 0;
+  int blocks = (int)((ne + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  gather_kv_kernel<<<blocks, 256, 0, st>>>(pool_layer, block_table, page_size, n_kv, head_dim, t0, ne, out);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -17,6 +17,8 @@
 // The LM head and the argmax tail stay separate kernels (decode_kernels.cu).
 // Built for the Llama-3-8B / Mistral-7B layer shape (d 4096, d_ff 14336, head_dim 128, 4 q heads per kv
 // head, page 32); other shapes use the per-op path.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -642,15 +644,43 @@ bool mega_supported(int d, int d_ff, int head_dim, int n_heads, int n_kv, int pa
          ((n_heads + 2 * n_kv) * HD) % 4 == 0;
 }
 
-int launch_decode_mega(const MegaArgs& a, cudaStream_t st) {
-  static bool attr = false;
-  constexpr size_t smem = (size_t)NS * SLOT + 2 * NS * 8 + (8 + CAP4 + 8 + CAP4 * 16 + 2 * NW * REP + NW * REP * HD + 2 * HALF) * 4 + 128 + 1024;
-  if (!attr) {
-    if (cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr = true;
+static constexpr size_t kMegaSmem =
+    (size_t)NS * SLOT + 2 * NS * 8 + (8 + CAP4 + 8 + CAP4 * 16 + 2 * NW * REP + NW * REP * HD + 2 * HALF) * 4 + 128 + 1024;
+
+// The grid barriers need every CTA resident at once.  Per device: opt in to the shared-memory size once, and check
+// that one CTA per SM fits (occupancy >= 1 with 288 threads + kMegaSmem); the engine falls back to the per-op path
+// otherwise.  All in-kernel waits are bounded (clock64 -> __trap), so a grid that is NOT co-resident after all (MPS, a
+// concurrent kernel of another context) ends as a kernel error, never as a hung GPU.  CL_MEGA_COOP=1 additionally asks
+// the driver for a cooperative launch, which guarantees co-residency or fails the launch.
+static bool g_mega_ready[64] = {false}, g_mega_ok[64] = {false};
+bool mega_prepare_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!g_mega_ready[dev]) {
+    g_mega_ready[dev] = true;
+    int nb = 0;
+    g_mega_ok[dev] = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMegaSmem) == cudaSuccess &&
+                     cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_mega_kernel, 288, kMegaSmem) == cudaSuccess && nb >= 1;
+    if (!g_mega_ok[dev]) cudaGetLastError();
   }
-  decode_mega_kernel<<<sm_count(), 288, smem, st>>>(a);
+  return g_mega_ok[dev];
+}
+
+int launch_decode_mega(const MegaArgs& a, cudaStream_t st) {
+  if (!mega_prepare_device()) return -1;
+  static const bool coop = getenv("CL_MEGA_COOP") && atoi(getenv("CL_MEGA_COOP")) != 0;
+  if (coop) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(sm_count()); cfg.blockDim = dim3(288); cfg.dynamicSmemBytes = kMegaSmem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, decode_mega_kernel, a) == cudaSuccess ? 1 : -1;
+  }
+  decode_mega_kernel<<<sm_count(), 288, kMegaSmem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -95,8 +95,6 @@ int Engine::init(const cl_engine_config& c) {
   skip_attn_ = env_int("CL_SKIP_ATTN", 0) != 0;   // timing experiments only (wrong results)
   use_flags_ = env_int("CL_FLAGS", 0) != 0;      // measured slower than griddepcontrol.wait (profiles/README.md)
   want_timeline_ = env_int("CL_TIMELINE", 0) != 0;
-  use_mega_ = env_int("CL_MEGA", 1) != 0 &&
-              mega_supported(cfg.d_model, cfg.d_ff, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads, page_size_, nsplit_);
   gemv_variant_ = c.decode_path == 1 ? 0 : 1;
   gemv_variant_ = env_int("CL_GEMV_VARIANT", gemv_variant_);
   q_dim_ = cfg.n_heads * cfg.head_dim;
@@ -104,6 +102,9 @@ int Engine::init(const cl_engine_config& c) {
   qkv_dim_ = q_dim_ + 2 * kv_dim_;
   nsplit_ = std::max(1, std::min(64, sm_count() / cfg.n_kv_heads));
   nsplit_ = std::max(1, std::min(64, env_int("CL_ATTN_NSPLIT", nsplit_)));
+  // decided AFTER nsplit_ is final: the persistent kernel's lane-parallel combine and part buffer are sized by it
+  use_mega_ = env_int("CL_MEGA", 1) != 0 &&
+              mega_supported(cfg.d_model, cfg.d_ff, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads, page_size_, nsplit_);
   max_pages_per_seq_ = (cfg.max_seq_len + page_size_ - 1) / page_size_;
 
   const size_t kv_bytes_per_token = (size_t)2 * cfg.n_layers * kv_dim_ * 2;
@@ -132,6 +133,10 @@ int Engine::init(const cl_engine_config& c) {
   }
   if (use_mega_ && !have_kv_maps_) {
     fprintf(stderr, "[clengine] KV tensor maps unavailable: using the per-op decode path\n");
+    use_mega_ = false;
+  }
+  if (use_mega_ && !mega_prepare_device()) {
+    fprintf(stderr, "[clengine] persistent decode kernel does not fit one CTA per SM on this device: using the per-op decode path\n");
     use_mega_ = false;
   }
   if (use_mega_) {
@@ -394,6 +399,7 @@ int Engine::enqueue_step(int B, bool tail) {
   int prev_n = 0, nc = 0;
   CL_LAUNCH(launch_embed(embed_, d, d_tok_, d_h_, d, d_slots_, B, stream_));
   const bool mega = use_mega_ && B == 1 && !skip_attn_ && d_mega_layers_ != nullptr;
+  if (probe_ev_) cudaEventRecord(probe_ev_[probe_idx_], stream_);
   if (mega) {
     MegaArgs m;
     m.layers = d_mega_layers_; m.n_layers = L_; m.q_dim = q_dim_; m.qkv_dim = qkv_dim_; m.n_heads = cfg.n_heads; m.n_kv = cfg.n_kv_heads;
@@ -458,6 +464,7 @@ int Engine::enqueue_step(int B, bool tail) {
     CL_LAUNCH(launch_gemv(gemv_variant_, EPI_RESID, false, w, stream_, use_pdl_, &nc));
     prev_cnt = cnt(l, 4); prev_n = nc;
   }
+  if (probe_ev_) cudaEventRecord(probe_ev_[probe_idx_ + 1], stream_);
   GemvArgs lm;
   lm.slots = d_slots_; lm.batch = B; lm.pdl_early = pdl_early_;
   lm.W = lm_head_; lm.N = cfg.vocab_size; lm.K = d; lm.h = d_h_; lm.gain = final_norm_; lm.eps = cfg.rms_eps;
@@ -666,6 +673,7 @@ int Engine::set_single_slot(cl_seq_t s) {
   if (last_single_slot_ != s) {
     CL_CUDA_OK(cudaMemcpyAsync(d_slots_, &s, 4, cudaMemcpyHostToDevice, stream_));
     last_single_slot_ = s;
+    slots_dirty_ = true;   // the scheduler's cached slot list no longer describes d_slots_
   }
   return CL_OK;
 }
@@ -743,6 +751,7 @@ int Engine::decode_greedy(const cl_seq_t* ss, int B, const int32_t* first_ids, i
   }
   CL_CUDA_OK(cudaMemcpyAsync(d_slots_, ss, (size_t)B * 4, cudaMemcpyHostToDevice, stream_));
   last_single_slot_ = B == 1 ? ss[0] : -1;
+  slots_dirty_ = true;
   float total_ms = 0.f;
   for (int done = 0; done < n_steps;) {
     const int chunk = std::min(ring_steps_, n_steps - done);
@@ -775,6 +784,121 @@ int Engine::decode_greedy(const cl_seq_t* ss, int B, const int32_t* first_ids, i
   }
   if (device_ms) *device_ms = total_ms;
   return CL_OK;
+}
+
+// ---- parity / benchmark aids ------------------------------------------------------------------------
+int Engine::seq_fake_fill(cl_seq_t s, int n_tokens) {
+  if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+  if (n_tokens < 0) { set_last_error("fake_fill: negative length"); return CL_ERR_INVALID_ARG; }
+  int rc = ensure_capacity(s, std::max(n_tokens, 1));
+  if (rc) return rc;
+  const int n = launch_fake_fill_kv(kpool_, vpool_, kv_layer_elems_, cfg.n_layers, d_bt_ + (size_t)s * max_pages_per_seq_, page_size_,
+                                    cfg.n_kv_heads, cfg.head_dim, n_tokens, stream_);
+  if (n < 0) { set_last_error(std::string("fake_fill: ") + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; }
+  launches_ += n;
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  seqs_[s].len = n_tokens;
+  seqs_[s].history.assign((size_t)n_tokens, 0);
+  return CL_OK;
+}
+
+int Engine::debug_kv(cl_seq_t s, int layer, int which, int t0, int n, float* out) {
+  if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+  if (layer < 0 || layer >= cfg.n_layers || t0 < 0 || n <= 0 || t0 + n > seqs_[s].len || !out) { set_last_error("debug_kv: bad range"); return CL_ERR_INVALID_ARG; }
+  float* tmp = nullptr;
+  const size_t bytes = (size_t)n * kv_dim_ * 4;
+  CL_CUDA_OK(cudaMalloc(&tmp, bytes));
+  const __nv_bfloat16* pool = (which ? vpool_ : kpool_) + (size_t)layer * kv_layer_elems_;
+  int rc = CL_OK;
+  if (launch_gather_kv(pool, d_bt_ + (size_t)s * max_pages_per_seq_, page_size_, cfg.n_kv_heads, cfg.head_dim, t0, n, tmp, stream_) < 0 ||
+      cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, stream_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess) {
+    set_last_error(std::string("debug_kv: ") + cudaGetErrorString(cudaGetLastError()));
+    rc = CL_ERR_CUDA;
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+// one batched step with caller-chosen input tokens (teacher forcing); logits_out [n_seqs][vocab] (may be NULL)
+int Engine::decode_step_batch(const cl_seq_t* ss, int B, const int32_t* ids, float* logits_out, int32_t* argmax_out) {
+  if (B <= 0 || B > max_batch_) { set_last_error("bad batch"); return CL_ERR_INVALID_ARG; }
+  for (int b = 0; b < B; ++b) {
+    const int s = ss[b];
+    if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+    for (int c = 0; c < b; ++c) if (ss[c] == s) { set_last_error("duplicate sequence in batch"); return CL_ERR_INVALID_ARG; }
+    if (ids[b] < 0 || ids[b] >= cfg.vocab_size) { set_last_error("token id out of range"); return CL_ERR_INVALID_ARG; }
+    const int rc = ensure_capacity(s, seqs_[s].len + 1);
+    if (rc) return rc;
+  }
+  for (int b = 0; b < B; ++b) {
+    const int s = ss[b];
+    CL_CUDA_OK(cudaMemcpyAsync(d_tok_ + s, &ids[b], 4, cudaMemcpyHostToDevice, stream_));
+    CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &seqs_[s].len, 4, cudaMemcpyHostToDevice, stream_));
+  }
+  CL_CUDA_OK(cudaMemcpyAsync(d_slots_, ss, (size_t)B * 4, cudaMemcpyHostToDevice, stream_));
+  last_single_slot_ = B == 1 ? ss[0] : -1;
+  slots_dirty_ = true;
+  const int rc = run_step_graph(B);
+  if (rc) return rc;
+  for (int b = 0; b < B; ++b) {
+    auto& q = seqs_[ss[b]];
+    q.len += 1;
+    q.history.push_back(ids[b]);
+    if (logits_out) { const int r2 = read_logits(ss[b], logits_out + (size_t)b * cfg.vocab_size); if (r2) return r2; }
+  }
+  if (argmax_out) {
+    CL_CUDA_OK(cudaMemcpyAsync(h_ids_pinned_, d_tok_, (size_t)max_seqs_ * 4, cudaMemcpyDeviceToHost, stream_));
+    CL_CUDA_OK(cudaStreamSynchronize(stream_));
+    for (int b = 0; b < B; ++b) argmax_out[b] = h_ids_pinned_[ss[b]];
+  } else {
+    CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  }
+  return CL_OK;
+}
+
+// bench.py's roofline.dominant_kernel: n_steps single-sequence greedy steps launched eagerly (the same kernels the
+// CUDA graph holds), with a CUDA-event pair on the launching stream around the step's dominant kernel — the persistent
+// whole-stack kernel (or, on the per-op path, the stack of per-layer kernels between the embedding and the LM head).
+int Engine::time_dominant_kernel(cl_seq_t s, int32_t first_id, int n_steps, float* kernel_ms, float* step_ms) {
+  if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+  if (n_steps <= 0 || n_steps > 4096 || first_id < 0 || first_id >= cfg.vocab_size) { set_last_error("bad steps / token"); return CL_ERR_INVALID_ARG; }
+  int rc = ensure_capacity(s, seqs_[s].len + n_steps);
+  if (rc) return rc;
+  CL_CUDA_OK(cudaMemcpyAsync(d_tok_ + s, &first_id, 4, cudaMemcpyHostToDevice, stream_));
+  CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &seqs_[s].len, 4, cudaMemcpyHostToDevice, stream_));
+  CL_CUDA_OK(cudaMemcpyAsync(d_slots_, &s, 4, cudaMemcpyHostToDevice, stream_));
+  last_single_slot_ = s;
+  slots_dirty_ = true;
+  CL_CUDA_OK(cudaMemsetAsync(d_step_counter_, 0, 4, stream_));
+  std::vector<cudaEvent_t> ev((size_t)2 * n_steps + 2);
+  for (auto& e : ev) CL_CUDA_OK(cudaEventCreate(&e));
+  probe_ev_ = ev.data();
+  CL_CUDA_OK(cudaEventRecord(ev[2 * n_steps], stream_));
+  for (int i = 0; i < n_steps && rc == CL_OK; ++i) {
+    probe_idx_ = 2 * i;
+    const int n = enqueue_step(1, true);
+    if (n < 0) rc = n; else launches_ += n;
+  }
+  probe_ev_ = nullptr;
+  if (rc == CL_OK && cudaEventRecord(ev[2 * n_steps + 1], stream_) != cudaSuccess) rc = CL_ERR_CUDA;
+  if (rc == CL_OK && cudaStreamSynchronize(stream_) != cudaSuccess) { set_last_error(cudaGetErrorString(cudaGetLastError())); rc = CL_ERR_CUDA; }
+  double k = 0.0;
+  float ms = 0.f;
+  if (rc == CL_OK) {
+    for (int i = 0; i < n_steps; ++i) { cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]); k += ms; }
+    cudaEventElapsedTime(&ms, ev[2 * n_steps], ev[2 * n_steps + 1]);
+    if (kernel_ms) *kernel_ms = (float)(k / n_steps);
+    if (step_ms) *step_ms = ms / n_steps;
+    // the device advanced tok/pos itself; mirror it on the host
+    CL_CUDA_OK(cudaMemcpy(h_ids_pinned_, d_ids_ring_, (size_t)std::min(n_steps, ring_steps_) * max_batch_ * 4, cudaMemcpyDeviceToHost));
+    auto& q = seqs_[s];
+    q.history.push_back(first_id);
+    for (int i = 0; i + 1 < n_steps; ++i) q.history.push_back(i < ring_steps_ ? h_ids_pinned_[(size_t)i * max_batch_] : 0);
+    q.len += n_steps;
+    tokens_generated_ += n_steps;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int Engine::debug_timeline(long long* out, int n) {

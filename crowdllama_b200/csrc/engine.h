@@ -141,6 +141,12 @@ class Engine {
   int decode_greedy(const cl_seq_t* seqs, int n_seqs, const int32_t* first_ids, int n_steps, int32_t* ids_out,
                     float* device_ms);
   int set_tensor(int layer, int kind, const uint16_t* data, int64_t n);
+  int load_safetensors(const std::string& path);   // HF llama-layout checkpoint (file or directory) -> set_tensor (weights_io.cpp)
+  // parity / benchmark aids (token level)
+  int debug_kv(cl_seq_t s, int layer, int which, int t0, int n, float* out);   // cached K/V rows -> host [n][n_kv*head_dim]
+  int seq_fake_fill(cl_seq_t s, int n_tokens);     // oracle oc_seq_fake_fill pattern into the paged cache of every layer
+  int decode_step_batch(const cl_seq_t* seqs, int n_seqs, const int32_t* ids, float* logits_out, int32_t* argmax_out);
+  int time_dominant_kernel(cl_seq_t s, int32_t first_id, int n_steps, float* kernel_ms, float* step_ms);
   int debug_hidden(float* out, int n);
   int debug_timeline(long long* out, int n);   // CL_TIMELINE=1: globaltimer stamps of the last step (CTA 0 of every node)
   int stats(cl_stats* out);
@@ -236,6 +242,9 @@ class Engine {
   int prefill_min_tokens_ = 16;
   bool graph_failed_ = false;
   int last_single_slot_ = -1;
+  bool slots_dirty_ = false;          // d_slots_ was rewritten outside the scheduler loop: its cached copy is stale
+  cudaEvent_t* probe_ev_ = nullptr;   // time_dominant_kernel: event pair recorded around the dominant kernel of an eager step
+  int probe_idx_ = 0;
 
   // stats
   std::atomic<int64_t> launches_{0}, tokens_generated_{0}, requests_completed_{0}, preemptions_{0};

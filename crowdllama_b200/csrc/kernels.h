@@ -117,6 +117,12 @@ int launch_synth_bf16(__nv_bfloat16* out, int64_t n_logical, int k_cols, int row
 int launch_synth_gain(float* out, int n, uint64_t seed, int key, float scale, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, int64_t n, cudaStream_t st);
 int launch_fill_u16(uint16_t* p, int64_t n, uint16_t v, cudaStream_t st);
+// parity aid: the oracle's oc_seq_fake_fill pattern into tokens 0..n_tokens-1 of one sequence, all layers
+int launch_fake_fill_kv(__nv_bfloat16* kpool, __nv_bfloat16* vpool, size_t layer_elems, int n_layers, const int* block_table,
+                        int page_size, int n_kv, int head_dim, int n_tokens, cudaStream_t st);
+
+int launch_gather_kv(const __nv_bfloat16* pool_layer, const int* block_table, int page_size, int n_kv, int head_dim, int t0, int n,
+                     float* out, cudaStream_t st);
 
 // ---- persistent whole-stack decode kernel (decode_mega.cu) ----------------------------------------
 struct MegaLayer {
@@ -152,6 +158,7 @@ struct MegaArgs {
 };
 bool make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows);
 bool mega_supported(int d, int d_ff, int head_dim, int n_heads, int n_kv, int page_size, int nsplit);
+bool mega_prepare_device();   // per device: shared-memory opt-in + "one CTA per SM fits" (call with the device current)
 int launch_decode_mega(const MegaArgs& a, cudaStream_t st);
 
 bool gemv_variant_supported(int variant, int N, int K);

@@ -281,9 +281,12 @@ void Engine::scheduler_main() {
     const int B = (int)active_.size();
     slots.resize(B);
     for (int b = 0; b < B; ++b) slots[b] = active_[b]->seq;
-    if (slots != last_slots) {
+    // slots_dirty_: an admission-time prefill (or a token-level call) rewrote d_slots_[0] since the last upload — the
+    // cached list would leave a finished request's slot in place and every later step would run on it
+    if (slots != last_slots || slots_dirty_) {
       cudaMemcpyAsync(d_slots_, slots.data(), (size_t)B * 4, cudaMemcpyHostToDevice, stream_);
       last_slots = slots;
+      slots_dirty_ = false;
       last_single_slot_ = B == 1 ? slots[0] : -1;
     }
     const int64_t t0 = now_ns();

@@ -65,7 +65,8 @@ EXPORTS = [
     "cl_greedy_sampling", "cl_model_preset", "cl_engine_create", "cl_engine_destroy", "cl_engine_model_config",
     "cl_engine_stats", "cl_engine_set_tensor", "cl_generate", "cl_generate_ids", "cl_generate_stream", "cl_result_free",
     "cl_handle_message", "cl_handle_message_stream", "cl_buffer_free", "cl_tokenize", "cl_detokenize", "cl_seq_create", "cl_seq_free",
-    "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_debug_hidden", "cl_debug_timeline",
+    "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_decode_step_batch", "cl_seq_fake_fill",
+    "cl_time_dominant_kernel", "cl_debug_kv", "cl_debug_hidden", "cl_debug_timeline",
     "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_qkv_rope_append", "cl_op_attn_decode",
     "cl_op_gemm_bf16", "cl_op_gemm_skinny", "cl_op_attn_prefill", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
     "cl_kvpool_reserve", "cl_kvpool_release", "cl_kvpool_pages_of", "cl_kvpool_free_pages", "cl_kvpool_used_pages",
@@ -119,6 +120,10 @@ def lib():
         "cl_decode_step": (C.c_int, [vp, i32, i32, vp, P(i32)]),
         "cl_decode_greedy": (C.c_int, [vp, i32, i32, i32, vp, P(f32)]),
         "cl_decode_greedy_batch": (C.c_int, [vp, vp, i32, vp, i32, vp, P(f32)]),
+        "cl_decode_step_batch": (C.c_int, [vp, vp, i32, vp, vp, vp]),
+        "cl_seq_fake_fill": (C.c_int, [vp, i32, i32]),
+        "cl_time_dominant_kernel": (C.c_int, [vp, i32, i32, i32, P(f32), P(f32)]),
+        "cl_debug_kv": (C.c_int, [vp, i32, i32, i32, i32, i32, vp]),
         "cl_debug_hidden": (C.c_int, [vp, vp, i32]),
         "cl_debug_timeline": (C.c_int, [vp, vp, i32]),
         "cl_op_gemv": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, i32, i32, i32, P(f32)]),
@@ -311,6 +316,32 @@ class Engine:
         _check(lib().cl_decode_greedy_batch(self._h, _ptr(seqs), len(seqs), _ptr(first), n_steps, _ptr(ids),
                                             C.byref(ms)), "cl_decode_greedy_batch")
         return ids, ms.value
+
+    def decode_step_batch(self, seqs, toks, want_logits: bool = True):
+        """One batched step with caller-chosen tokens; returns (logits [B][V] or None, greedy next ids [B])."""
+        seqs = np.ascontiguousarray(seqs, dtype=np.int32)
+        toks = np.ascontiguousarray(toks, dtype=np.int32)
+        out = np.empty((len(seqs), self.cfg["vocab_size"]), np.float32) if want_logits else None
+        am = np.empty(len(seqs), np.int32)
+        _check(lib().cl_decode_step_batch(self._h, _ptr(seqs), len(seqs), _ptr(toks), _ptr(out) if want_logits else None, _ptr(am)),
+               "cl_decode_step_batch")
+        return out, am
+
+    def seq_fake_fill(self, s: int, n_tokens: int):
+        """Fill the sequence's paged KV (all layers) with the CPU oracle's synthetic cache pattern (parity aid)."""
+        _check(lib().cl_seq_fake_fill(self._h, s, n_tokens), "cl_seq_fake_fill")
+
+    def debug_kv(self, s: int, layer: int, which: int, t0: int, n: int) -> np.ndarray:
+        """Cached K (which=0) / V (which=1) rows of `layer` for tokens t0..t0+n-1: [n][n_kv*head_dim] fp32."""
+        out = np.empty((n, self.cfg["n_kv_heads"] * self.cfg["head_dim"]), np.float32)
+        _check(lib().cl_debug_kv(self._h, s, layer, which, t0, n, _ptr(out)), "cl_debug_kv")
+        return out
+
+    def time_dominant_kernel(self, s: int, first_id: int, n_steps: int):
+        """(kernel_ms, step_ms): mean CUDA-event time of the dominant kernel / of the whole eagerly launched step."""
+        k, t = C.c_float(0), C.c_float(0)
+        _check(lib().cl_time_dominant_kernel(self._h, s, int(first_id), n_steps, C.byref(k), C.byref(t)), "cl_time_dominant_kernel")
+        return k.value, t.value
 
     def debug_hidden(self) -> np.ndarray:
         out = np.empty(self.cfg["d_model"], np.float32)

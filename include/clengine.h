@@ -209,6 +209,23 @@ int cl_decode_greedy(cl_engine* e, cl_seq_t seq, int32_t first_id, int32_t n_ste
 int cl_decode_greedy_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs,
                            const int32_t* first_ids, int32_t n_steps, int32_t* ids_out,
                            float* device_ms);
+/* One batched decode step with caller-chosen input tokens (teacher forcing for the parity tests of the batched
+ * path): ids[n_seqs]; logits_out (host, may be NULL) receives [n_seqs][vocab_size] fp32; argmax_out (may be NULL)
+ * the greedy next ids. */
+int cl_decode_step_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs, const int32_t* ids, float* logits_out,
+                         int32_t* argmax_out);
+/* Parity aid: make the sequence hold n_tokens cached tokens whose K/V, in every layer, are the CPU oracle's
+ * synthetic cache pattern (oracle/llama_oracle.c oc_seq_fake_fill: k[i] = (((i * 2654435761) >> 24 & 255) - 128) / 128,
+ * v[i] = (((i * 40503) >> 8 & 255) - 128) / 128 with i = token * n_kv * head_dim + head * head_dim + dim; exact in
+ * bf16).  Lets the long-context decode kernels be compared with the oracle without a long CPU prefill. */
+int cl_seq_fake_fill(cl_engine* e, cl_seq_t seq, int32_t n_tokens);
+/* Parity aid: cached K (which = 0) / V (which = 1) rows of `layer`, tokens t0..t0+n-1 of the sequence, gathered from
+ * the paged pool: out[n][n_kv_heads*head_dim] fp32 (the bf16 cache values).  Checks EVERY position of a long prefill. */
+int cl_debug_kv(cl_engine* e, cl_seq_t seq, int32_t layer, int32_t which, int32_t t0, int32_t n, float* out);
+/* bench.py's roofline.dominant_kernel: n_steps greedy single-sequence steps launched eagerly with a CUDA-event pair
+ * (on the launching stream) around the step's dominant kernel — decode_mega_kernel, or the per-layer kernel stack
+ * on the per-op path.  kernel_ms / step_ms (may be NULL): mean per step. */
+int cl_time_dominant_kernel(cl_engine* e, cl_seq_t seq, int32_t first_id, int32_t n_steps, float* kernel_ms, float* step_ms);
 /* debugging / parity: copy the residual stream after `layer` (or the final norm input when
  * layer == n_layers) of the most recent single-sequence step to host (d_model floats). */
 int cl_debug_hidden(cl_engine* e, float* out, int32_t n);

@@ -439,6 +439,103 @@ int oc_forward(oc_model* m, oc_seq* s, const int32_t* ids, int32_t n, float* log
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* layer-major prefill: the SAME per-token arithmetic as step() (every y[t][r] is the same      */
+/* dot_bf16 of the same operands, so results are bit-identical to feeding the tokens one by one */
+/* through oc_forward), but each weight row is reused over a tile of tokens — what makes a      */
+/* 4096-token prompt affordable on the CPU.  Used only to check the engine's long prefill.      */
+/* ------------------------------------------------------------------------------------------ */
+#define OC_TB 32
+static void gemm_tiled(const uint16_t* w, const float* x, size_t xs, float* y, size_t ys, int t, int n_rows, int k) {
+  for (int t0 = 0; t0 < t; t0 += OC_TB) {
+    int t1 = t0 + OC_TB < t ? t0 + OC_TB : t;
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < n_rows; ++r)
+      for (int ti = t0; ti < t1; ++ti) y[(size_t)ti * ys + r] = dot_bf16(w + (size_t)r * k, x + (size_t)ti * xs, k);
+  }
+}
+
+int oc_prefill_block(oc_model* m, oc_seq* s, const int32_t* ids, int32_t n, float* logits) {
+  const oc_config* c = &m->c;
+  int d = c->d_model, hd = c->head_dim, H = c->n_heads, KV = c->n_kv_heads, F = c->d_ff;
+  int qd = H * hd, kvd = KV * hd, pos0 = s->len;
+  if (n <= 0) return -1;
+  if (pos0 + n > s->max_len) return -2;
+  for (int t = 0; t < n; ++t) if (ids[t] < 0 || ids[t] >= c->vocab_size) return -1;
+  size_t wide = (size_t)(F > qd ? F : qd);
+  if ((size_t)d > wide) wide = (size_t)d;
+  float* h = (float*)xcalloc((size_t)n * d, 4);
+  float* xn = (float*)xcalloc((size_t)n * wide, 4);      /* bf16-rounded GEMV inputs (norm out / attention out / SwiGLU act) */
+  float* q = (float*)xcalloc((size_t)n * qd, 4);
+  float* kk = (float*)xcalloc((size_t)n * kvd, 4);
+  float* vv = (float*)xcalloc((size_t)n * kvd, 4);
+  float* g = (float*)xcalloc((size_t)n * F, 4);
+  float* u = (float*)xcalloc((size_t)n * F, 4);
+  float* tmp = (float*)xcalloc((size_t)n * d, 4);
+  for (int t = 0; t < n; ++t)
+    for (int i = 0; i < d; ++i) h[(size_t)t * d + i] = oc_f32_from_bf16(m->embed[(size_t)ids[t] * d + i]);
+  memcpy(m->dbg_hidden, h + (size_t)(n - 1) * d, (size_t)d * 4);
+  for (int l = 0; l < c->n_layers; ++l) {
+    oc_layer* L = &m->layers[l];
+    float* kc = s->kc + (size_t)l * s->max_len * kvd;
+    float* vc = s->vc + (size_t)l * s->max_len * kvd;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < n; ++t) oc_op_rmsnorm(h + (size_t)t * d, L->attn_norm, c->rms_eps, d, m->act_rounding, xn + (size_t)t * d);
+    gemm_tiled(L->wq, xn, d, q, qd, n, qd, d);
+    gemm_tiled(L->wk, xn, d, kk, kvd, n, kvd, d);
+    gemm_tiled(L->wv, xn, d, vv, kvd, n, kvd, d);
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < n; ++t) {
+      const float* tab = m->rope + (size_t)(pos0 + t) * (hd / 2) * 2;
+      rope_with_table(q + (size_t)t * qd, H, hd, tab);
+      rope_with_table(kk + (size_t)t * kvd, KV, hd, tab);
+      float* kb = kc + (size_t)(pos0 + t) * kvd;
+      float* vb = vc + (size_t)(pos0 + t) * kvd;
+      for (int i = 0; i < kvd; ++i) { kb[i] = rnd(m, kk[(size_t)t * kvd + i]); vb[i] = rnd(m, vv[(size_t)t * kvd + i]); }
+      for (int i = 0; i < qd; ++i) q[(size_t)t * qd + i] = rnd(m, q[(size_t)t * qd + i]);
+    }
+    for (int t = 0; t < n; ++t) {   /* attention_core parallelises over heads */
+      float* att = xn + (size_t)t * qd;
+      attention_core(q + (size_t)t * qd, kc, vc, (size_t)kvd, pos0 + t + 1, H, KV, hd, m->scores, att);
+      for (int i = 0; i < qd; ++i) att[i] = rnd(m, att[i]);
+    }
+    gemm_tiled(L->wo, xn, qd, tmp, d, n, d, qd);
+    for (size_t i = 0; i < (size_t)n * d; ++i) h[i] += tmp[i];
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < n; ++t) oc_op_rmsnorm(h + (size_t)t * d, L->ffn_norm, c->rms_eps, d, m->act_rounding, xn + (size_t)t * d);
+    gemm_tiled(L->wg, xn, d, g, F, n, F, d);
+    gemm_tiled(L->wu, xn, d, u, F, n, F, d);
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < n; ++t)
+      for (int i = 0; i < F; ++i) {
+        float gg = g[(size_t)t * F + i];
+        float si = gg / (1.0f + expf(-gg));
+        xn[(size_t)t * F + i] = rnd(m, si * u[(size_t)t * F + i]);
+      }
+    gemm_tiled(L->wd, xn, F, tmp, d, n, d, F);
+    for (size_t i = 0; i < (size_t)n * d; ++i) h[i] += tmp[i];
+    memcpy(m->dbg_hidden + (size_t)(l + 1) * d, h + (size_t)(n - 1) * d, (size_t)d * 4);
+  }
+  s->len = pos0 + n;
+  memcpy(m->h, h + (size_t)(n - 1) * d, (size_t)d * 4);
+  if (logits) {
+    oc_op_rmsnorm(m->h, m->final_norm, c->rms_eps, d, m->act_rounding, m->xn);
+    oc_op_gemv(m->lm_head, m->xn, logits, c->vocab_size, d);
+  }
+  free(h); free(xn); free(q); free(kk); free(vv); free(g); free(u); free(tmp);
+  return 0;
+}
+
+/* cached K (which = 0) or V (which = 1) of `layer`, tokens t0 .. t0+n-1: out[n][n_kv*head_dim] */
+int oc_seq_kv(const oc_seq* s, int32_t layer, int32_t which, int32_t t0, int32_t n, float* out) {
+  const oc_config* c = &s->m->c;
+  size_t kvd = (size_t)c->n_kv_heads * c->head_dim;
+  if (layer < 0 || layer >= c->n_layers || t0 < 0 || n < 0 || t0 + n > s->len) return -1;
+  const float* src = (which ? s->vc : s->kc) + ((size_t)layer * s->max_len + t0) * kvd;
+  memcpy(out, src, (size_t)n * kvd * 4);
+  return 0;
+}
+
 int oc_debug_hidden(oc_model* m, int32_t layer, float* out) {
   if (layer < 0 || layer > m->c.n_layers) return -1;
   memcpy(out, m->dbg_hidden + (size_t)layer * m->c.d_model, (size_t)m->c.d_model * 4);

@@ -69,6 +69,11 @@ void oc_seq_fake_fill(oc_seq* s, int32_t len);
 
 /* Append n tokens.  all_logits==0: logits[vocab] of the last position; else logits[n][vocab]. */
 int oc_forward(oc_model* m, oc_seq* s, const int32_t* ids, int32_t n, float* logits, int32_t all_logits);
+/* Append n tokens layer by layer (weight rows reused over tiles of tokens): bit-identical to oc_forward with
+ * all_logits == 0, but affordable for prompts of thousands of tokens.  logits[vocab] of the last position (may be NULL). */
+int oc_prefill_block(oc_model* m, oc_seq* s, const int32_t* ids, int32_t n, float* logits);
+/* cached K (which = 0) / V (which = 1) of `layer`, tokens t0..t0+n-1: out[n][n_kv*head_dim] */
+int oc_seq_kv(const oc_seq* s, int32_t layer, int32_t which, int32_t t0, int32_t n, float* out);
 /* residual stream of the last processed token after `layer` layers (0..n_layers) */
 int oc_debug_hidden(oc_model* m, int32_t layer, float* out);
 int oc_debug_vec(oc_model* m, int32_t which, float* out);

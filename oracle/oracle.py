@@ -94,6 +94,8 @@ def lib():
             "oc_seq_truncate": (None, [vp, i32]),
             "oc_seq_fake_fill": (None, [vp, i32]),
             "oc_forward": (C.c_int, [vp, vp, vp, i32, vp, i32]),
+            "oc_prefill_block": (C.c_int, [vp, vp, vp, i32, vp]),
+            "oc_seq_kv": (C.c_int, [vp, i32, i32, i32, i32, vp]),
             "oc_debug_hidden": (C.c_int, [vp, i32, vp]),
             "oc_argmax": (i32, [vp, i32]),
             "oc_debug_vec": (C.c_int, [vp, i32, vp]),
@@ -241,6 +243,23 @@ class Seq:
         rc = lib().oc_forward(self.m._h, self._h, _ptr(ids), len(ids), _ptr(out), 1 if all_logits else 0)
         if rc:
             raise RuntimeError(f"oc_forward rc={rc}")
+        return out
+
+    def prefill_block(self, ids) -> np.ndarray:
+        """Layer-major prefill (bit-identical to forward(ids), fast enough for thousands of tokens); last-position logits."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        out = np.empty(self.m.cfg["vocab_size"], np.float32)
+        rc = lib().oc_prefill_block(self.m._h, self._h, _ptr(ids), len(ids), _ptr(out))
+        if rc:
+            raise RuntimeError(f"oc_prefill_block rc={rc}")
+        return out
+
+    def kv(self, layer: int, which: int, t0: int, n: int) -> np.ndarray:
+        """Cached K (which=0) / V (which=1) of `layer`, tokens t0..t0+n-1 as [n][n_kv*head_dim] fp32."""
+        out = np.empty((n, self.m.cfg["n_kv_heads"] * self.m.cfg["head_dim"]), np.float32)
+        rc = lib().oc_seq_kv(self._h, layer, which, t0, n, _ptr(out))
+        if rc:
+            raise RuntimeError(f"oc_seq_kv rc={rc}")
         return out
 
     def greedy(self, first_id: int, n_steps: int):
