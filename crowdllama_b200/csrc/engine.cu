@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <sys/stat.h>
+
 #include "common.cuh"
 #include "engine.h"
 
@@ -52,8 +54,15 @@ Engine::~Engine() {
 
 int Engine::init(const cl_engine_config& c) {
   if (c.abi_version != CL_ABI_VERSION) { set_last_error("abi_version mismatch"); return CL_ERR_INVALID_ARG; }
+  const std::string wpath = c.weights_path ? c.weights_path : "";
+  struct stat wst{};
+  const bool wdir = !wpath.empty() && stat(wpath.c_str(), &wst) == 0 && S_ISDIR(wst.st_mode);
   if (c.preset) {
     if (cl_model_preset(c.preset, &cfg) != CL_OK) { set_last_error("unknown preset"); return CL_ERR_UNKNOWN_MODEL; }
+  } else if (c.model.n_layers == 0 && wdir) {
+    // a model directory describes itself: config.json (HF LlamaConfig / MistralConfig field names)
+    const int rc0 = model_config_from_dir(wpath, &cfg);
+    if (rc0) return rc0;
   } else {
     cfg = c.model;
   }
@@ -118,11 +127,8 @@ int Engine::init(const cl_engine_config& c) {
   CL_CUDA_OK(cudaEventCreate(&ev1_));
   int rc = alloc_weights();
   if (rc) return rc;
-  if (c.weights_path && *c.weights_path) {
-    set_last_error("weights_path: no checkpoint loader in this round; push tensors with cl_engine_set_tensor");
-    return CL_ERR_IO;
-  }
-  rc = fill_synthetic(c.weights_seed);
+  // weights_path: HF llama-layout safetensors (file or model directory, weights_io.cpp); else seeded synthetic weights
+  rc = wpath.empty() ? fill_synthetic(c.weights_seed) : load_safetensors(wpath);
   if (rc) return rc;
   rc = alloc_state();
   if (rc) return rc;
@@ -150,6 +156,16 @@ int Engine::init(const cl_engine_config& c) {
   pool_.reset(new KvPool(n_pages_, page_size_));
   seqs_.assign(max_seqs_, SeqState());
   tok.reset(new ByteTokenizer(cfg.vocab_size));
+  if (wdir) {   // a model directory brings its vocabulary: tokenizer.json replaces the byte-level fallback
+    const std::string tj = wpath + "/tokenizer.json";
+    if (stat(tj.c_str(), &wst) == 0) {
+      std::string err;
+      std::unique_ptr<Tokenizer> t = load_hf_tokenizer(tj, "", &err);
+      if (!t) { set_last_error("tokenizer.json: " + err); return CL_ERR_IO; }
+      if (t->vocab_size() > cfg.vocab_size) { set_last_error("tokenizer.json has more ids than the model's vocabulary"); return CL_ERR_IO; }
+      tok = std::move(t);
+    }
+  }
   CL_CUDA_OK(cudaStreamSynchronize(stream_));
   {
     // Advertised throughput = CAPACITY: decode steps per second x max_batch, i.e. what this worker delivers with a

@@ -85,6 +85,9 @@ class ByteTokenizer : public Tokenizer {
 // "zephyr" | "chatml" | "" (auto-detect from the added tokens).  nullptr + *err on failure.
 std::unique_ptr<Tokenizer> load_hf_tokenizer(const std::string& path, const std::string& chat_family, std::string* err);
 
+// HF config.json of a model directory -> cl_model_config (weights_io.cpp)
+int model_config_from_dir(const std::string& dir, cl_model_config* out);
+
 // ---- sampler (host; mirrors oracle oc_sample) ---------------------------------------------------
 int32_t sample_token(const float* logits, int32_t vocab, const cl_sampling& sp, const int32_t* history, int32_t n_history,
                      uint64_t step);

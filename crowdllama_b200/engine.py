@@ -63,7 +63,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "cl_abi_version", "cl_strerror", "cl_last_error", "cl_default_engine_config", "cl_default_sampling",
     "cl_greedy_sampling", "cl_model_preset", "cl_engine_create", "cl_engine_destroy", "cl_engine_model_config",
-    "cl_engine_stats", "cl_engine_set_tensor", "cl_generate", "cl_generate_ids", "cl_generate_stream", "cl_result_free",
+    "cl_engine_stats", "cl_engine_set_tensor", "cl_checkpoint_info", "cl_generate", "cl_generate_ids", "cl_generate_stream", "cl_result_free",
     "cl_handle_message", "cl_handle_message_stream", "cl_buffer_free", "cl_tokenize", "cl_detokenize", "cl_seq_create", "cl_seq_free",
     "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_decode_step_batch", "cl_seq_fake_fill",
     "cl_time_dominant_kernel", "cl_debug_kv", "cl_debug_hidden", "cl_debug_timeline",
@@ -104,6 +104,7 @@ def lib():
         "cl_engine_model_config": (C.c_int, [vp, P(ModelConfig)]),
         "cl_engine_stats": (C.c_int, [vp, P(Stats)]),
         "cl_engine_set_tensor": (C.c_int, [vp, i32, i32, vp, i64]),
+        "cl_checkpoint_info": (C.c_int, [C.c_char_p, P(ModelConfig), P(i32), P(i64)]),
         "cl_generate": (C.c_int, [vp, C.c_char_p, C.c_char_p, sz, P(Sampling), P(Result)]),
         "cl_generate_ids": (C.c_int, [vp, vp, i32, P(Sampling), P(Result)]),
         "cl_generate_stream": (C.c_int, [vp, C.c_char_p, C.c_char_p, sz, P(Sampling), TOKEN_CB, vp, P(Result)]),
@@ -194,6 +195,14 @@ def model_preset(name: str) -> dict:
     return mc.as_dict()
 
 
+def checkpoint_info(path, model: dict | None = None):
+    """cl_checkpoint_info: (model config, tensors, parameters) of an HF safetensors checkpoint; host-only validation."""
+    mc = ModelConfig(**model) if model else ModelConfig()
+    nt, npar = C.c_int32(0), C.c_int64(0)
+    _check(lib().cl_checkpoint_info(str(path).encode(), C.byref(mc), C.byref(nt), C.byref(npar)), "cl_checkpoint_info")
+    return mc.as_dict(), nt.value, npar.value
+
+
 def greedy(max_new_tokens: int, ignore_eos: bool = False) -> Sampling:
     s = Sampling()
     lib().cl_greedy_sampling(C.byref(s), max_new_tokens)
@@ -226,7 +235,7 @@ class Engine:
     def __init__(self, preset: str | None = None, model: dict | None = None, model_name: str | None = None,
                  device: int = 0, seed: int = 1234, max_batch: int = 8, max_seqs: int | None = None,
                  page_size: int = 32, kv_pool_bytes: int = 0, use_cuda_graph: bool = True, decode_path: int = 0,
-                 start_scheduler: bool = False):
+                 start_scheduler: bool = False, weights_path: str | None = None):
         L = lib()
         cfg = EngineConfig()
         L.cl_default_engine_config(C.byref(cfg))
@@ -238,6 +247,9 @@ class Engine:
             cfg.preset = None
             cfg.model = ModelConfig(**model)
         cfg.weights_seed = seed
+        if weights_path is not None:
+            self._keep.append(str(weights_path).encode())
+            cfg.weights_path = self._keep[-1]
         cfg.max_batch = max_batch
         cfg.max_seqs = max_seqs or max_batch
         cfg.page_size = page_size

@@ -72,7 +72,9 @@ typedef struct cl_engine_config {
   const char* preset;      /* "llama3-8b" | "mistral-7b" | "tinyllama-1.1b" | "tiny-test" | NULL
                               (NULL => take `model` below) */
   cl_model_config model;   /* used when preset == NULL */
-  const char* weights_path;/* NULL => synthetic seeded weights (no checkpoints exist offline) */
+  const char* weights_path;/* HF llama-layout checkpoint: a .safetensors file, or a model directory with *.safetensors shards
+                              (+ config.json, used when preset == NULL and model.n_layers == 0, + tokenizer.json, loaded
+                              when present); BF16 / F16 / F32 tensors -> bf16.  NULL => synthetic seeded weights */
   uint64_t weights_seed;   /* seed of the counter-based synthetic weight generator */
   int64_t kv_pool_bytes;   /* bytes of HBM for the paged KV pool; 0 => derive from max_seqs */
   int32_t page_size;       /* tokens per KV page: 16, 32 or 64 (0 => 32) */
@@ -149,6 +151,12 @@ int cl_engine_stats(cl_engine* e, cl_stats* out);
  * 7 wo, 8 ffn_norm, 9 w_gate, 10 w_up, 11 w_down (same numbering as the synthetic generator).
  * Used to load real checkpoints tensor by tensor and by the HF golden-vector parity tests. */
 int cl_engine_set_tensor(cl_engine* e, int32_t layer, int32_t kind, const uint16_t* data, int64_t n);
+
+/* Host-only check of a checkpoint (no GPU needed): parses config.json (when cfg_io->n_layers == 0 and path is a model
+ * directory; the result is written back) and every safetensors header, validating tensor names, dtypes, shapes and
+ * offsets against the architecture exactly as cl_engine_create does.  n_tensors / n_params (may be NULL): what the
+ * engine would load. */
+int cl_checkpoint_info(const char* path, cl_model_config* cfg_io, int32_t* n_tensors, int64_t* n_params);
 
 /* ---- request level (what the Go shim calls) --------------------------------------------- */
 /* replaces: callOllamaAPI, api.go:108-160.  Blocking; enqueues into the continuous-batching

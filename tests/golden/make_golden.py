@@ -7,7 +7,8 @@ architecture that IS importable here: HF transformers' LlamaForCausalLM / Mistra
 run on CPU in float32 over bf16-representable seeded weights.
 
   python tests/golden/make_golden.py      -> tests/golden/hf_tiny_llama.npz, hf_tiny_mistral.npz,
-                                              hf_tiny_llama3geom.npz, synth_kat.npz
+                                              hf_tiny_llama3geom.npz, synth_kat.npz,
+                                              hf_tiny_llama_ckpt/ (config.json + model.safetensors)
 
 Fixtures are small (< 1 MB each) and committed; tests never import transformers.
 """
@@ -24,7 +25,7 @@ from oracle import oracle as oc  # noqa: E402
 OUT = Path(__file__).resolve().parent
 
 
-def hf_fixture(kind: str, path: Path, seed: int):
+def hf_fixture(kind: str, path: Path, seed: int, ckpt_dir: Path | None = None):
     from transformers import LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM
     # head_dim 64 and heads/kv in {2, 4} so the same fixtures also drive the CUDA engine
     # (its attention kernels are built for head_dim 64|128).
@@ -84,6 +85,17 @@ def hf_fixture(kind: str, path: Path, seed: int):
             save[f"L{l}.{k}"] = b16(tensors[pre + v])
     np.savez_compressed(path, **save)
     print("wrote", path, path.stat().st_size, "bytes")
+    if ckpt_dir is not None:
+        # the same model as an HF checkpoint directory (config.json + model.safetensors, bf16 — lossless, the weights
+        # are bf16-representable): pins the engine's safetensors / config.json loader (csrc/weights_io.cpp) against
+        # the real HF writer; tests/test_gpu_checkpoint.py loads it by path and compares with the logits above
+        import shutil
+        shutil.rmtree(ckpt_dir, ignore_errors=True)
+        model.to(torch.bfloat16).save_pretrained(ckpt_dir, safe_serialization=True)
+        for f in ckpt_dir.iterdir():
+            if f.name not in ("config.json", "model.safetensors"):
+                f.unlink()
+        print("wrote", ckpt_dir, sorted(f.name for f in ckpt_dir.iterdir()))
 
 
 def synth_kat(path: Path):
@@ -100,7 +112,7 @@ def synth_kat(path: Path):
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else None     # e.g. `make_golden.py llama3geom` regenerates one fixture
     if only in (None, "llama"):
-        hf_fixture("llama", OUT / "hf_tiny_llama.npz", 0)
+        hf_fixture("llama", OUT / "hf_tiny_llama.npz", 0, ckpt_dir=OUT / "hf_tiny_llama_ckpt")
     if only in (None, "mistral"):
         hf_fixture("mistral", OUT / "hf_tiny_mistral.npz", 1)
     if only in (None, "llama3geom"):

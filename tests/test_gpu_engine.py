@@ -315,3 +315,30 @@ def test_megakernel_and_per_op_path_match_oracle(monkeypatch, mega):
         ids, _ = e.decode_greedy(s, first, 24)
         k = len(ref) if margins.min() > MARGIN_TOL else int(np.argmax(margins <= MARGIN_TOL))
         np.testing.assert_array_equal(ids[:k], ref[:k])
+
+
+def test_short_request_admitted_during_a_long_one_does_not_disturb_it():
+    """Regression (scheduler.cpp): a request that finishes during admission (num_predict = 1) used to leave
+    d_slots_[0] pointing at its freed slot; the running request then stopped advancing and repeated one token.  A long
+    greedy request must return exactly its solo ids while one-token requests come and go."""
+    import threading
+    cfg = oc.PRESETS["tiny-test"]
+    V = cfg["vocab_size"]
+    long_prompt = _prompt(20, V)
+    shorts = [np.array([(7 * i + 3 * j + 1) % V for j in range(5 + i % 4)], np.int32) for i in range(24)]
+    with eng.Engine(preset="tiny-test", seed=11, max_batch=4, max_seqs=4, start_scheduler=True) as e:
+        solo = e.generate_ids(long_prompt, eng.greedy(400, ignore_eos=True)).token_ids
+        short_solo = [int(e.generate_ids(p, eng.greedy(1, ignore_eos=True)).token_ids[0]) for p in shorts]
+        out = {}
+
+        def run_long():
+            out["long"] = e.generate_ids(long_prompt, eng.greedy(400, ignore_eos=True))
+        th = threading.Thread(target=run_long)
+        th.start()
+        got = [int(e.generate_ids(p, eng.greedy(1, ignore_eos=True)).token_ids[0]) for p in shorts]
+        th.join()
+        assert out["long"].n_generated == 400
+        np.testing.assert_array_equal(out["long"].token_ids, solo)
+        assert got == short_solo
+        st = e.stats()
+        assert st["kv_pages_used"] == 0 and st["active_seqs"] == 0

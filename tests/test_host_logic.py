@@ -383,3 +383,43 @@ def test_resource_json_round_trip():
     assert r.get_dht_key() == "/ipns/12D3KooW"
     with pytest.raises(ValueError, match="failed to unmarshal CrowdLlamaResource"):
         Resource.from_json(b"{nope")
+
+
+def test_checkpoint_validation_is_host_logic(tmp_path):
+    """csrc/weights_io.cpp without a GPU: config.json + safetensors headers of the HF-written fixture
+    (tests/golden/hf_tiny_llama_ckpt) and of hand-written F32 / sharded / broken variants."""
+    import numpy as np
+    from st_util import hf_tensors_from_fixture, write_safetensors
+    G = Path(__file__).resolve().parent / "golden"
+    cfg, nt, npar = eng.checkpoint_info(G / "hf_tiny_llama_ckpt")
+    assert (cfg["n_layers"], cfg["d_model"], cfg["n_heads"], cfg["n_kv_heads"], cfg["head_dim"], cfg["d_ff"], cfg["vocab_size"]) == \
+           (2, 128, 2, 1, 64, 256, 256)
+    assert abs(cfg["rope_theta"] - 1e4) < 1e-3 and nt == 3 + 2 * 9
+    z = np.load(G / "hf_tiny_llama.npz")
+    tensors = hf_tensors_from_fixture(z, cfg)
+    assert npar == sum(int(np.prod(shape)) for _, shape in tensors.values())
+    write_safetensors(tmp_path / "f32.safetensors", tensors, "F32")
+    assert eng.checkpoint_info(tmp_path / "f32.safetensors", cfg)[1:] == (nt, npar)
+    # tied embeddings: lm_head is synthesised from embed_tokens
+    tied = {k: v for k, v in tensors.items() if k != "lm_head.weight"}
+    write_safetensors(tmp_path / "tied.safetensors", tied)
+    assert eng.checkpoint_info(tmp_path / "tied.safetensors", cfg)[1] == nt
+    # broken inputs fail with CL_ERR_IO and a message naming the tensor
+    missing = {k: v for k, v in tensors.items() if k != "model.layers.1.mlp.up_proj.weight"}
+    write_safetensors(tmp_path / "missing.safetensors", missing)
+    with pytest.raises(eng.EngineError) as ei:
+        eng.checkpoint_info(tmp_path / "missing.safetensors", cfg)
+    assert ei.value.status == eng.CL_ERR_IO and "L1:10" in ei.value.detail
+    wrong = dict(cfg); wrong["n_kv_heads"] = 2
+    with pytest.raises(eng.EngineError) as ei:
+        eng.checkpoint_info(tmp_path / "f32.safetensors", wrong)
+    assert "k_proj" in ei.value.detail
+    raw = (tmp_path / "f32.safetensors").read_bytes()
+    (tmp_path / "trunc.safetensors").write_bytes(raw[: len(raw) // 2])
+    with pytest.raises(eng.EngineError):
+        eng.checkpoint_info(tmp_path / "trunc.safetensors", cfg)
+    (tmp_path / "garbage.safetensors").write_bytes(b"\xff" * 64)
+    with pytest.raises(eng.EngineError):
+        eng.checkpoint_info(tmp_path / "garbage.safetensors", cfg)
+    with pytest.raises(eng.EngineError):
+        eng.checkpoint_info(tmp_path, None)                     # a directory without config.json
