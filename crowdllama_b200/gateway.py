@@ -47,7 +47,7 @@ class PeerTable:
                 r = Resource.from_json(data)
                 with self.lock:
                     self.peers[a] = r
-            except OSError:
+            except Exception:  # noqa: BLE001 — refused, reset, closed without JSON, partial JSON: drop THIS peer, keep probing
                 with self.lock:
                     self.peers.pop(a, None)
 

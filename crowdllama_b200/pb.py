@@ -62,8 +62,12 @@ def _fields(b: bytes):
                 raise ValueError("truncated field")
             v, i = b[i:i + n], i + n
         elif wt == 1:
+            if i + 8 > len(b):
+                raise ValueError("truncated fixed64 field")
             v, i = b[i:i + 8], i + 8
         elif wt == 5:
+            if i + 4 > len(b):
+                raise ValueError("truncated fixed32 field")
             v, i = b[i:i + 4], i + 4
         else:
             raise ValueError(f"unsupported wire type {wt}")

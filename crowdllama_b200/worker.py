@@ -22,6 +22,7 @@ from .router import resource_from_engine
 
 INFERENCE_PROTOCOL = "/crowdllama/inference/1.0.0"     # pkg/crowdllama/types.go:20
 METADATA_PROTOCOL = "/crowdllama/metadata/1.0.0"       # pkg/crowdllama/types.go:16
+STOP_PROTOCOL = "/crowdllama-b200/bench-stop/1.0.0"    # harness only: the load generator tells the worker peers it is done
 
 
 class _Stream:
@@ -47,6 +48,7 @@ class WorkerServer(socketserver.ThreadingTCPServer):
         self.engine, self.peer_id = engine, peer_id
         self.api_handler = H.worker_api_handler(engine, sampling)
         self.served = 0
+        self.stop_event = threading.Event()
         self._lock = threading.Lock()
         super().__init__(addr, _Conn)
 
@@ -58,6 +60,8 @@ class _Conn(socketserver.BaseRequestHandler):
         proto = s.r.readline().decode(errors="replace").strip()
         if proto == METADATA_PROTOCOL:
             s.write(resource_from_engine(srv.peer_id, srv.engine).to_json())
+        elif proto == STOP_PROTOCOL:
+            srv.stop_event.set()
         elif proto == INFERENCE_PROTOCOL:
             if H.handle_inference_stream(srv.api_handler, s, worker_mode=True):
                 with srv._lock:

@@ -160,3 +160,63 @@ def test_generate_endpoint_options_and_streaming():
         assert "".join(x["message"]["content"] for x in lines).strip().endswith("You asked: x") and lines[-1]["done"]
     finally:
         g.shutdown(); g.server_close(); w.shutdown(); w.server_close()
+
+
+def test_bench_box_load_generator_against_two_mock_peers():
+    """bench.py's request-level leg (BASELINE.json configs[3]) without a GPU: two worker peers with mock engines play the
+    two ranks of `bench.py --gpus 2`; the load generator (its own process, as in the benchmark) routes 64 concurrent
+    chats through the gateway stand-in, reports req/s and per-worker counts, and tells every peer to stop."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    base = _free_port() + 1
+    srvs = [_spawn_worker(base + i, "llama3:8b") for i in range(2)]
+    try:
+        out = subprocess.run([sys.executable, str(root / "bench.py"), "--box-client", "--workers", "2", "--base-port", str(base)],
+                             capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+        assert "error" not in res, res
+        for key, conc in (("config4", 64), ("saturated", 64)):
+            sc = res[key]
+            assert sc["concurrency"] == conc and sc["ok"] == sc["requests"] and not sc["errors"] and sc["req_per_s"] > 0
+            assert sum(sc["per_worker_requests"].values()) == sc["requests"] and len(sc["per_worker_requests"]) == 2
+        assert all(s.stop_event.wait(5) for s in srvs)          # the ranks leave their serving loop
+    finally:
+        for s in srvs:
+            s.shutdown()
+
+
+def test_peer_table_survives_a_peer_that_answers_garbage():
+    """a worker that accepts the metadata stream and closes without (valid) JSON must be dropped from the
+    table, not kill the refresh thread — the healthy peer stays routable."""
+    import socketserver
+
+    class _Bad(socketserver.BaseRequestHandler):
+        def handle(self):
+            self.request.recv(64)
+            self.request.sendall(b'{"peer_id": "half')          # partial JSON, then close
+
+    bad_port, good_port = _free_port(), _free_port()
+    bad = socketserver.ThreadingTCPServer(("127.0.0.1", bad_port), _Bad)
+    threading.Thread(target=bad.serve_forever, daemon=True).start()
+    good = _spawn_worker(good_port, "m")
+    try:
+        t = gateway.PeerTable([("127.0.0.1", bad_port), ("127.0.0.1", good_port), ("127.0.0.1", _free_port())])
+        t.probe()                                                 # must not raise
+        t.probe()
+        assert list(t.peers) == [("127.0.0.1", good_port)]
+        addr, w = t.best("m")
+        assert addr == ("127.0.0.1", good_port) and w.peer_id == f"w{good_port}"
+    finally:
+        bad.shutdown(); good.shutdown()
+
+
+def test_pb_rejects_truncated_fixed_width_fields():
+    from crowdllama_b200 import pb
+    with pytest.raises(ValueError):
+        list(pb._fields(bytes([0x0d, 1, 2])))                     # field 1, wire type 5 (fixed32), only 2 bytes
+    with pytest.raises(ValueError):
+        list(pb._fields(bytes([0x09, 1, 2, 3, 4])))               # field 1, wire type 1 (fixed64), only 4 bytes
+    assert [(f, wt) for f, wt, _ in pb._fields(bytes([0x0d, 0, 0, 0x80, 0x3f]))] == [(1, 5)]
