@@ -189,6 +189,9 @@ struct AttnPrefillArgs {
   __nv_bfloat16* out;                // [T][H*D]
 };
 int launch_attn_prefill(const AttnPrefillArgs& a, cudaStream_t st);
+// tcgen05 variant (attn_prefill_tc.cu): head_dim 128, page 32; kmap / vmap = pool-wide 2-D tensor maps (box {64, 32})
+bool attn_prefill_tc_supported(int n_heads, int n_kv, int head_dim, int page_size, int pos0, int T);
+int launch_attn_prefill_tc(const AttnPrefillArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, long long layer_row0, cudaStream_t st);
 // act = bf16(silu(gu[:, 2i]) * gu[:, 2i+1])
 int launch_silu_mul_bf16(const float* gu, __nv_bfloat16* act, int T, int d_ff, cudaStream_t st);
 // ---- batched-decode projections (gemm_skinny.cu): T <= 32 token columns, weight-stream bound ----------

@@ -65,7 +65,10 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
       CL_LAUNCH(launch_rope_scatter(ra, stream_));
       AttnPrefillArgs aa{w.q, kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_, bt, page_size_,
                          pos0, T, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, w.attn};
-      CL_LAUNCH(launch_attn_prefill(aa, stream_));
+      if (have_kv_maps_ && attn_prefill_tc_supported(cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, page_size_, pos0, T))
+        CL_LAUNCH(launch_attn_prefill_tc(aa, kmap_, vmap_, (long long)l * n_pages_ * cfg.n_kv_heads * page_size_, stream_));
+      else
+        CL_LAUNCH(launch_attn_prefill(aa, stream_));
       CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.h, w.h, T, d, q_dim_, stream_));
       CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.ffn_norm, cfg.rms_eps, w.xn, T, d, stream_));
       CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.gu, nullptr, T, 2 * F, d, stream_));
@@ -215,8 +218,9 @@ int cl_op_gemm_skinny(int device, const uint16_t* x, const uint16_t* w, float* y
   return CL_OK;
 }
 
-int cl_op_attn_prefill(int device, const uint16_t* q, const uint16_t* k, const uint16_t* v, int32_t t, int32_t n_heads, int32_t n_kv,
-                       int32_t head_dim, float* out) {
+// variant: -1 auto (tcgen05 kernel when the shape allows, CL_PREFILL_ATTN_TC=0 forces the other), 0 mma.sync kernel, 1 tcgen05 kernel
+static int attn_prefill_impl(int device, const uint16_t* q, const uint16_t* k, const uint16_t* v, int32_t t, int32_t n_heads, int32_t n_kv,
+                             int32_t head_dim, int variant, int iters, float* out, float* ms) {
   if (!q || !k || !v || !out || t <= 0) return CL_ERR_INVALID_ARG;
   int rc = check_device(device);
   if (rc) return rc;
@@ -240,14 +244,46 @@ int cl_op_attn_prefill(int device, const uint16_t* q, const uint16_t* k, const u
   CL_CUDA_OK(dv.upload(vp.data(), pool * 2));
   CL_CUDA_OK(dbt.upload(bt.data(), bt.size() * 4));
   CL_CUDA_OK(dout.alloc((size_t)t * qd * 2));
+  CL_CUDA_OK(cudaMemset(dout.p, 0xff, (size_t)t * qd * 2));   // NaN pattern: every output must be written
   CL_CUDA_OK(dout32.alloc((size_t)t * qd * 4));
   AttnPrefillArgs a{dq.as<__nv_bfloat16>(), dk.as<__nv_bfloat16>(), dv.as<__nv_bfloat16>(), dbt.as<int>(), P, 0, t, n_heads, n_kv, HD,
                     dout.as<__nv_bfloat16>()};
-  if (launch_attn_prefill(a, nullptr) < 0) { CL_CUDA_OK(cudaGetLastError()); return CL_ERR_CUDA; }
+  CUtensorMap km, vm;
+  bool tc = variant != 0 && attn_prefill_tc_supported(n_heads, n_kv, HD, P, 0, t);
+  if (variant == 1 && !tc && head_dim == 128) tc = (t + P - 1) / P <= 320;          // explicit request overrides the env switch
+  if (tc) tc = make_tmap_2d_bf16(&km, dk.p, (uint64_t)n_pages * n_kv * P, HD, 64, 32) && make_tmap_2d_bf16(&vm, dv.p, (uint64_t)n_pages * n_kv * P, HD, 64, 32);
+  if (variant == 1 && !tc) { set_last_error("tcgen05 prefill attention does not support this shape"); return CL_ERR_INVALID_ARG; }
+  auto run = [&]() { return tc ? launch_attn_prefill_tc(a, km, vm, 0, nullptr) : launch_attn_prefill(a, nullptr); };
+  if (run() < 0) { CL_CUDA_OK(cudaGetLastError()); set_last_error("prefill attention launch failed"); return CL_ERR_CUDA; }
   if (launch_bf16_to_f32(dout.as<__nv_bfloat16>(), dout32.as<float>(), (int64_t)t * qd, nullptr) < 0) return CL_ERR_CUDA;
   CL_CUDA_OK(cudaDeviceSynchronize());
   CL_CUDA_OK(cudaMemcpy(out, dout32.p, (size_t)t * qd * 4, cudaMemcpyDeviceToHost));
+  if (iters > 0 && ms) {
+    cudaEvent_t e0, e1;
+    CL_CUDA_OK(cudaEventCreate(&e0));
+    CL_CUDA_OK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) run();
+    CL_CUDA_OK(cudaDeviceSynchronize());
+    CL_CUDA_OK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) run();
+    CL_CUDA_OK(cudaEventRecord(e1));
+    CL_CUDA_OK(cudaDeviceSynchronize());
+    float tm = 0.f;
+    CL_CUDA_OK(cudaEventElapsedTime(&tm, e0, e1));
+    *ms = tm / (float)iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   return CL_OK;
+}
+
+int cl_op_attn_prefill(int device, const uint16_t* q, const uint16_t* k, const uint16_t* v, int32_t t, int32_t n_heads, int32_t n_kv,
+                       int32_t head_dim, float* out) {
+  return attn_prefill_impl(device, q, k, v, t, n_heads, n_kv, head_dim, -1, 0, out, nullptr);
+}
+int cl_op_attn_prefill_variant(int device, int variant, const uint16_t* q, const uint16_t* k, const uint16_t* v, int32_t t, int32_t n_heads,
+                               int32_t n_kv, int32_t head_dim, float* out, int32_t iters, float* ms) {
+  return attn_prefill_impl(device, q, k, v, t, n_heads, n_kv, head_dim, variant, iters, out, ms);
 }
 
 }  // extern "C"

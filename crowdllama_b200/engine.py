@@ -68,7 +68,7 @@ EXPORTS = [
     "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_decode_step_batch", "cl_seq_fake_fill",
     "cl_time_dominant_kernel", "cl_debug_kv", "cl_debug_hidden", "cl_debug_timeline",
     "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_qkv_rope_append", "cl_op_attn_decode",
-    "cl_op_gemm_bf16", "cl_op_gemm_skinny", "cl_op_attn_prefill", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
+    "cl_op_gemm_bf16", "cl_op_gemm_skinny", "cl_op_attn_prefill", "cl_op_attn_prefill_variant", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
     "cl_kvpool_reserve", "cl_kvpool_release", "cl_kvpool_pages_of", "cl_kvpool_free_pages", "cl_kvpool_used_pages",
     "cl_tokenizer_load", "cl_tokenizer_free", "cl_tokenizer_encode", "cl_tokenizer_decode", "cl_tokenizer_info", "cl_engine_load_tokenizer",
 ]
@@ -136,6 +136,7 @@ def lib():
         "cl_op_gemm_bf16": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, P(f32)]),
         "cl_op_gemm_skinny": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, P(f32), vp]),
         "cl_op_attn_prefill": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, vp]),
+        "cl_op_attn_prefill_variant": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, i32, i32, i32, i32, vp, i32, P(f32)]),
         "cl_op_synth_weights": (C.c_int, [C.c_int, u64, i32, i64, f32, vp]),
         "cl_tokenizer_load": (C.c_int, [C.c_char_p, C.c_char_p, P(vp)]),
         "cl_tokenizer_free": (None, [vp]),
@@ -340,7 +341,8 @@ class Engine:
         return out, am
 
     def seq_fake_fill(self, s: int, n_tokens: int):
-        """Fill the sequence's paged KV (all layers) with the CPU oracle's synthetic cache pattern (parity aid)."""
+        """Fill the sequence's paged KV (all layers) with the synthetic cache pattern the parity tests' CPU checker also
+        generates (include/clengine.h: cl_seq_fake_fill) — a parity aid."""
         _check(lib().cl_seq_fake_fill(self._h, s, n_tokens), "cl_seq_fake_fill")
 
     def debug_kv(self, s: int, layer: int, which: int, t0: int, n: int) -> np.ndarray:
@@ -560,6 +562,19 @@ def op_attn_prefill(q_bf16, k_bf16, v_bf16, n_heads, n_kv, head_dim, device=0):
     _check(lib().cl_op_attn_prefill(device, _ptr(q), _ptr(k), _ptr(v), t, n_heads, n_kv, head_dim, _ptr(out)),
            "cl_op_attn_prefill")
     return out
+
+
+def op_attn_prefill_variant(q_bf16, k_bf16, v_bf16, n_heads, n_kv, head_dim, variant, iters=0, device=0):
+    """variant 0: mma.sync kernel, 1: tcgen05 kernel, -1: auto.  Returns (out, ms per launch or None)."""
+    q = np.ascontiguousarray(q_bf16, dtype=np.uint16)
+    k = np.ascontiguousarray(k_bf16, dtype=np.uint16)
+    v = np.ascontiguousarray(v_bf16, dtype=np.uint16)
+    t = q.shape[0]
+    out = np.empty((t, n_heads * head_dim), np.float32)
+    ms = C.c_float(0)
+    _check(lib().cl_op_attn_prefill_variant(device, variant, _ptr(q), _ptr(k), _ptr(v), t, n_heads, n_kv, head_dim, _ptr(out), iters,
+                                            C.byref(ms)), "cl_op_attn_prefill_variant")
+    return out, (ms.value if iters > 0 else None)
 
 
 def op_synth_weights(seed, key, n, scale, device=0):

@@ -283,6 +283,10 @@ int cl_op_gemm_skinny(int device, const uint16_t* x, const uint16_t* w, float* y
 /* causal prefill attention: q [t][n_heads][d], k,v [t][n_kv][d] bf16 (roped), out bf16-rounded fp32 */
 int cl_op_attn_prefill(int device, const uint16_t* q, const uint16_t* k, const uint16_t* v,
                        int32_t t, int32_t n_heads, int32_t n_kv, int32_t head_dim, float* out);
+/* the same with the kernel chosen explicitly — variant 0: mma.sync kernel (prefill_kernels.cu, any head_dim 64|128),
+ * 1: tcgen05 kernel (attn_prefill_tc.cu, head_dim 128), -1: what the engine would pick — and an optional timing loop */
+int cl_op_attn_prefill_variant(int device, int variant, const uint16_t* q, const uint16_t* k, const uint16_t* v, int32_t t,
+                               int32_t n_heads, int32_t n_kv, int32_t head_dim, float* out, int32_t iters, float* ms);
 /* synthetic weight generator (device kernel) -> host copy, for known-answer tests */
 int cl_op_synth_weights(int device, uint64_t seed, int32_t tensor_key, int64_t n, float scale,
                         uint16_t* out_bf16);

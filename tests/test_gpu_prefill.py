@@ -57,6 +57,27 @@ def test_attn_prefill_matches_oracle(n_heads, n_kv, hd, t):
     assert np.abs(got - ref).max() <= 2 ** -6 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("t,n_heads,n_kv", [(1, 4, 1), (127, 4, 1), (128, 8, 2), (129, 4, 4), (255, 4, 1), (257, 8, 2), (640, 4, 1), (1000, 8, 2),
+                                            (2049, 4, 1)])
+def test_attn_prefill_kernels_head_dim_128(variant, t, n_heads, n_kv):
+    """Both prefill attention kernels at head_dim 128 — variant 1 = tcgen05 (S and O in TMEM, K/V pages by 2-D TMA,
+    V as an MN-major operand), variant 0 = the mma.sync kernel — against the oracle's per-position attention: ragged
+    lengths around the 128-row tile / 256-row item / 128-token block boundaries, reversed page order, GQA 1:1 ... 4:1.
+    Score scale ~ N(0, 4): rows whose maximum moves by more than 2^8 between blocks exercise the TMEM rescale path."""
+    rng = np.random.default_rng(t * 5 + n_heads + n_kv)
+    hd = 128
+    q = _rand_bf16(rng, (t, n_heads * hd), 2.0)
+    k = _rand_bf16(rng, (t, n_kv, hd), 2.0)
+    v = _rand_bf16(rng, (t, n_kv, hd))
+    got, _ = eng.op_attn_prefill_variant(q, k, v, n_heads, n_kv, hd, variant)
+    assert np.isfinite(got).all()                  # the op pre-fills the output with NaNs: every row must be written
+    qf, kf, vf = oc.np_f32_from_bf16(q), oc.np_f32_from_bf16(k), oc.np_f32_from_bf16(v)
+    ref = np.stack([oc.attention(qf[i], kf[:i + 1], vf[:i + 1], n_heads, n_kv, hd) for i in range(t)])
+    err = np.abs(got - ref)
+    assert err.max() <= 2 ** -6 * max(1.0, np.abs(ref).max()), (int(err.argmax() // (n_heads * hd)), float(err.max()))
+
+
 def _prompt(n, vocab, salt=0):
     return np.array([(i * 7919 + 13 + salt) % vocab for i in range(n)], np.int32)
 

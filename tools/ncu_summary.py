@@ -55,5 +55,35 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def _to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+
+
+def traffic(src, dst, note=""):
+    """profiles/ncu_traffic.json: DRAM bytes per launch of every kernel in an `ncu --set full` capture (mean over the
+    captured launches) — bench.py copies the dominant kernel's figure into `roofline.traffic`."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw, it, ik = (hdr.index(k) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "Kernel Name"))
+    agg = collections.OrderedDict()
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[ik]).split("::")[-1].split("<")[0].replace("void ", "").strip()
+        agg.setdefault(name, []).append((_to_bytes(r[ir], units[ir]), _to_bytes(r[iw], units[iw]), float(r[it].replace(",", "")), units[it]))
+    db = json.load(open(dst)) if os.path.exists(dst) else {}
+    for name, v in agg.items():
+        n = len(v)
+        tm = sum(x[2] for x in v) / n
+        tm_ms = tm if v[0][3] == "ms" else tm / 1e3 if v[0][3] == "us" else tm / 1e6
+        db[name] = {"dram_bytes_read_per_launch": int(sum(x[0] for x in v) / n), "dram_bytes_write_per_launch": int(sum(x[1] for x in v) / n),
+                    "dram_bytes_per_launch": int(sum(x[0] + x[1] for x in v) / n), "launches_captured": n, "ncu_gpu_time_ms": round(tm_ms, 5),
+                    "source": os.path.basename(src), "note": note}
+    json.dump(db, open(dst, "w"), indent=1, sort_keys=True)
+    print(json.dumps({k: db[k] for k in agg}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
