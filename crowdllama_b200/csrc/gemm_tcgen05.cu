@@ -9,6 +9,11 @@
 //   UMMA A operand = W tile  [128 rows n ][64 k]  -> accumulator lanes  (TMEM lane  = n)
 //   UMMA B operand = X tile  [BT  rows t ][64 k]  -> accumulator columns (TMEM column = t)
 //   accumulator D[128][BT] fp32 in TMEM, double buffered (2*BT columns).
+//   MT = 2 (prefill, T >= 256): one CTA owns a 256 (n) x 256 (t) tile as two M = 128 MMAs per k-step that share the token
+//   operand.  The 128 x 256 tile needs 96 B/clk/SM of operands from L2 at full MMA rate = 14.2 KB/clk for the chip, more
+//   than twice what the L2 slices deliver (~6.3 KB/clk, B300_MICROARCH.md "LTS throughput cap"); the 256 x 256 tile needs
+//   64 B/clk/SM.  Its two accumulators fill TMEM (512 columns), so the epilogue no longer overlaps the next tile — with
+//   K >= 4096 a tile is >= 65K clk of MMA against ~2K clk of epilogue.
 // Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0   TMA producer  : cp.async.bulk.tensor.2d (128B swizzle) into an NST-stage mbarrier ring
 //   warp 1   MMA issuer    : tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit -> frees smem stage /
@@ -18,6 +23,8 @@
 // Tile order: consecutive tiles share the W tile (t fastest), so W streams from HBM once and X
 // (<= 32 MB) stays L2-resident.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -36,14 +43,16 @@ struct GemmParams {
   int k_splits;           // > 1: split-K; split s writes its partial to Y + s * T * ldy (the consumer sums in fixed order)
 };
 
-template <int BT, int NST>
+template <int BT, int NST, int MT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr uint32_t A_BYTES = BM * BK * 2;   // 16 KB
+  constexpr int BMT = BM * MT;                      // W rows per tile
+  constexpr uint32_t A_BYTES = BMT * BK * 2;        // 16 KB per M = 128 sub-tile
   constexpr uint32_t B_BYTES = BT * BK * 2;
   constexpr uint32_t STAGE = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BT < 32 ? 32 : 2 * BT;
+  constexpr int NACC = (2 * MT * BT <= 512) ? 2 : 1;   // accumulator sets in TMEM
+  constexpr uint32_t TMEM_COLS = NACC * MT * BT < 32 ? 32 : NACC * MT * BT;
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns: power of two <= 512");
   // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for the 128B swizzle
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
@@ -54,7 +63,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_t = (p.T + BT - 1) / BT, num_n = (p.N + BM - 1) / BM;
+  const int num_t = (p.T + BT - 1) / BT, num_n = (p.N + BMT - 1) / BMT;
   const int ksp = p.k_splits > 1 ? p.k_splits : 1;
   const int num_tiles = num_t * num_n * ksp;          // split index is the slowest dimension
   const int num_kb_all = (p.K + BK - 1) / BK;
@@ -64,7 +73,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     prefetch_tmap(&map_w);
     prefetch_tmap(&map_x);
     for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }   // [NACC] used
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -86,7 +95,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int bt_ = tile % (num_t * num_n), ks = tile / (num_t * num_n);
-        const int n0 = (bt_ / num_t) * BM, t0 = (bt_ % num_t) * BT;
+        const int n0 = (bt_ / num_t) * BMT, t0 = (bt_ % num_t) * BT;
         const int kb0 = ks * kb_per, kb1 = min(num_kb_all, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
@@ -105,7 +114,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BT);
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * MT * BT);
       const int ks = tile / (num_t * num_n);
       const int kb0 = ks * kb_per, num_kb = max(0, min(num_kb_all, kb0 + kb_per) - kb0);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -116,15 +125,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k)  // advance 32 bytes (= 2 x 16 B units) per UMMA_K inside the swizzle atom
-            umma_f16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)     // M sub-tiles: 128 W rows = 16 KB (1024 x 16 B units) apart, same token operand
+              umma_f16(d_addr + (uint32_t)(m * BT), adesc + (uint64_t)(2 * k + m * 1024), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == NST) { stage = 0; phase ^= 1u; }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
@@ -133,24 +143,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int bt_ = tile % (num_t * num_n), ks = tile / (num_t * num_n);
-      const int n0 = (bt_ / num_t) * BM, t0 = (bt_ % num_t) * BT;
+      const int n0 = (bt_ / num_t) * BMT, t0 = (bt_ % num_t) * BT;
       float* Yb = p.Y + (size_t)ks * p.T * p.ldy;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int n = n0 + q * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BT; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BT + c0), v);
-        tmem_ld_wait();
-        if (n < p.N) {
+      for (int m = 0; m < MT; ++m) {
+        const int n = n0 + m * BM + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BT; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + m) * BT + c0), v);
+          tmem_ld_wait();
+          if (n < p.N) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int t = t0 + c0 + c;
-            if (t < p.T) {
-              float* dst = Yb + (size_t)t * p.ldy + n;
-              const float r = __uint_as_float(v[c]);
-              *dst = p.accumulate_into_y ? (*dst + r) : r;
+            for (int c = 0; c < 32; ++c) {
+              const int t = t0 + c0 + c;
+              if (t < p.T) {
+                float* dst = Yb + (size_t)t * p.ldy + n;
+                const float r = __uint_as_float(v[c]);
+                *dst = p.accumulate_into_y ? (*dst + r) : r;
+              }
             }
           }
         }
@@ -158,8 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -215,17 +227,17 @@ bool make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 
 namespace {
 
-template <int BT, int NST>
+template <int BT, int NST, int MT = 1>
 cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st, bool pdl) {
-  auto kern = gemm_tcgen05_kernel<BT, NST>;
-  constexpr size_t smem = (size_t)NST * (BM * BK * 2 + BT * BK * 2) + 1024 + 256;
+  auto kern = gemm_tcgen05_kernel<BT, NST, MT>;
+  constexpr size_t smem = (size_t)NST * (MT * BM * BK * 2 + BT * BK * 2) + 1024 + 256;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const int tiles = ((p.T + BT - 1) / BT) * ((p.N + BM - 1) / BM) * (p.k_splits > 1 ? p.k_splits : 1);
+  const int tiles = ((p.T + BT - 1) / BT) * ((p.N + BM * MT - 1) / (BM * MT)) * (p.k_splits > 1 ? p.k_splits : 1);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -245,14 +257,18 @@ int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, c
   if (!gemm_tcgen05_supported(T, N, K)) return -1;
   if (resid && resid != Y) return -1;  // residual add is in place
   const int BT = T > 128 ? 256 : T > 64 ? 128 : T > 32 ? 64 : 32;
+  // 256 x 256 tiles (two M sub-tiles per CTA) for prompt-sized T: the operand stream from L2, not the tensor pipe, bounds
+  // the 128 x 256 tile.  CL_GEMM_MT=1 keeps the single sub-tile (A/B measurements).
+  static const int mt_env = getenv("CL_GEMM_MT") ? atoi(getenv("CL_GEMM_MT")) : 2;
+  const int MT = (BT == 256 && k_splits <= 1 && N >= 2 * BM && mt_env >= 2) ? 2 : 1;
   CUtensorMap mw, mx;
-  if (!make_map(&mw, W, N, K, BM) || !make_map(&mx, X, T, K, BT)) return -1;
+  if (!make_map(&mw, W, N, K, BM * MT) || !make_map(&mx, X, T, K, BT)) return -1;
   if (k_splits > 1 && (resid || (K + BK - 1) / BK < k_splits)) return -1;   // every split needs >= 1 k-block (an empty split would never signal its epilogue)
   if (k_splits > 1 && ((K + BK - 1) / BK + k_splits - 1) / k_splits * (k_splits - 1) >= (K + BK - 1) / BK) return -1;
   GemmParams p{Y, T, N, K, N, resid ? 1 : 0, k_splits};
   cudaError_t e;
   switch (BT) {
-    case 256: e = launch_inst<256, 4>(mw, mx, p, st, pdl); break;
+    case 256: e = MT == 2 ? launch_inst<256, 3, 2>(mw, mx, p, st, pdl) : launch_inst<256, 4>(mw, mx, p, st, pdl); break;
     case 128: e = launch_inst<128, 6>(mw, mx, p, st, pdl); break;
     case 64: e = launch_inst<64, 8>(mw, mx, p, st, pdl); break;
     default: e = launch_inst<32, 8>(mw, mx, p, st, pdl); break;

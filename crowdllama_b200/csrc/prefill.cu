@@ -4,7 +4,10 @@
 // prefill and decode share one logits/argmax tail.  Also: cl_op_gemm_bf16 / cl_op_attn_prefill.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -51,7 +54,21 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
   CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
   const int* bt = d_bt_ + (size_t)s * max_pages_per_seq_;
   int launches = 0, r;
-#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; } while (0)
+  // CL_PREFILL_PROFILE=1: a CUDA event after every launch, per-kernel-class device time printed to stderr (in-pipeline
+  // times incl. the gap before each kernel; the ncu launch list measures cold, serialised launches instead)
+  static const bool prof = getenv("CL_PREFILL_PROFILE") && atoi(getenv("CL_PREFILL_PROFILE")) != 0;
+  std::vector<cudaEvent_t> pev;
+  std::vector<const char*> pname;
+  auto mark = [&](const char* name) {
+    if (!prof) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream_);
+    pev.push_back(e);
+    pname.push_back(name);
+  };
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; mark(#call); } while (0)
+  mark("start");
   for (int c0 = 0; c0 < n; c0 += w.cap_tokens) {
     const int T = std::min(w.cap_tokens, n - c0);
     const int pos0 = q.len + c0;
@@ -95,6 +112,26 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
   t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = 1;
   CL_LAUNCH(launch_step_tail(t, stream_));
 #undef CL_LAUNCH
+  if (prof && pev.size() > 1) {
+    cudaStreamSynchronize(stream_);
+    std::map<std::string, std::pair<double, int>> acc;
+    double total = 0.0;
+    for (size_t i = 1; i < pev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pev[i - 1], pev[i]);
+      std::string key(pname[i]);
+      key = key.substr(0, key.find('('));
+      if (key == "launch_gemm_bf16") {   // split by projection: the 3rd argument names the output buffer
+        const std::string full(pname[i]);
+        key += full.find("L.wqkv") != std::string::npos ? ":qkv" : full.find("L.wo") != std::string::npos ? ":o" : full.find("L.wgu") != std::string::npos ? ":gate|up" : ":down";
+      }
+      acc[key].first += ms; acc[key].second += 1;
+      total += ms;
+    }
+    fprintf(stderr, "[prefill profile] %d tokens, %zu launches, %.3f ms on the device\n", n, pev.size() - 1, total);
+    for (auto& kv : acc) fprintf(stderr, "[prefill profile]   %-32s n=%4d total %8.3f ms  mean %8.2f us\n", kv.first.c_str(), kv.second.second, kv.second.first, 1e3 * kv.second.first / kv.second.second);
+    for (auto e : pev) cudaEventDestroy(e);
+  }
   launches_ += launches;
   q.len += n;
   q.history.insert(q.history.end(), ids, ids + n);

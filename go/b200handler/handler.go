@@ -4,7 +4,7 @@
 // crowdllama.WorkerAPIHandler (api.go:45-96), replacing the HTTP round trip to Ollama
 // (callOllamaAPI, api.go:108-160) by one blocking C call into libclengine.so.
 //
-// NOTE: this file cannot be compiled in the build image (no Go toolchain, no module proxy); it is
+// NOTE: this package cannot be compiled in the build image (no Go toolchain, no module proxy); it is
 // the reference-side binding a maintainer adds.  The C-ABI it binds is exercised by the Python
 // ctypes binding and tests in this repository.  See INTEGRATION.md.
 package b200handler
@@ -21,101 +21,140 @@ import "C"
 import (
 	"context"
 	"fmt"
+	"math"
 	"runtime/cgo"
-	"time"
 	"unsafe"
 
 	"google.golang.org/protobuf/proto"
-	"google.golang.org/protobuf/types/known/timestamppb"
 
 	llamav1 "github.com/crowdllama/crowdllama-pb/llama/v1"
 	"github.com/crowdllama/crowdllama/pkg/crowdllama"
 )
 
 // Engine owns one GPU (one worker process per GPU; the 8 GPUs of a box are 8 worker peers).
-type Engine struct{ h *C.cl_engine }
+type Engine struct {
+	h     *C.cl_engine
+	model string
+}
 
 // Config mirrors the CROWDLLAMA_* knobs added for the B200 worker (pkg/config/config.go:58-79 style).
 type Config struct {
-	Device    int    // CROWDLLAMA_B200_DEVICE
-	ModelName string // name advertised in Resource.SupportedModels, e.g. "llama3:8b"
-	Preset    string // "llama3-8b" | "mistral-7b" | "tinyllama-1.1b"
-	Seed      uint64
-	MaxBatch  int
-	KVBytes   int64
+	Device     int    // CROWDLLAMA_B200_DEVICE
+	ModelName  string // name advertised in Resource.SupportedModels and matched exactly (manager.go:349-354), e.g. "llama3:8b"
+	ModelDir   string // CROWDLLAMA_B200_MODEL_DIR: HF checkpoint directory (*.safetensors + config.json [+ tokenizer.json]) or one .safetensors file
+	Preset     string // architecture when ModelDir has no config.json / synthetic weights: "llama3-8b" | "mistral-7b" | "tinyllama-1.1b"
+	Tokenizer  string // tokenizer.json outside ModelDir (optional; ModelDir/tokenizer.json is picked up by the engine itself)
+	ChatFamily string // "llama3" | "mistral" | "zephyr" | "chatml" | "" (auto-detect from the added tokens)
+	Seed       uint64 // synthetic weights only (ModelDir == "")
+	MaxBatch   int
+	KVBytes    int64
 }
 
 func lastErr(rc C.int) error {
 	return fmt.Errorf("%s: %s", C.GoString(C.cl_strerror(rc)), C.GoString(C.cl_last_error()))
 }
 
+func cstr(s string) (*C.char, func()) {
+	if s == "" {
+		return nil, func() {}
+	}
+	p := C.CString(s)
+	return p, func() { C.free(unsafe.Pointer(p)) }
+}
+
 // New replaces "start the embedded Ollama server" (cmd/crowdllama/main.go:283-297).
 func New(cfg Config) (*Engine, error) {
 	var c C.cl_engine_config
 	C.cl_default_engine_config(&c)
-	name, preset := C.CString(cfg.ModelName), C.CString(cfg.Preset)
-	defer C.free(unsafe.Pointer(name))
-	defer C.free(unsafe.Pointer(preset))
-	c.device, c.model_name, c.preset = C.int32_t(cfg.Device), name, preset
+	name, f1 := cstr(cfg.ModelName)
+	preset, f2 := cstr(cfg.Preset)
+	dir, f3 := cstr(cfg.ModelDir)
+	defer f1()
+	defer f2()
+	defer f3()
+	c.device, c.model_name, c.preset, c.weights_path = C.int32_t(cfg.Device), name, preset, dir
 	c.weights_seed, c.max_batch, c.max_seqs = C.uint64_t(cfg.Seed), C.int32_t(cfg.MaxBatch), C.int32_t(cfg.MaxBatch)
 	c.kv_pool_bytes, c.start_scheduler = C.int64_t(cfg.KVBytes), 1
 	var h *C.cl_engine
 	if rc := C.cl_engine_create(&c, &h); rc != C.CL_OK {
 		return nil, lastErr(rc)
 	}
-	return &Engine{h: h}, nil
+	e := &Engine{h: h, model: cfg.ModelName}
+	if cfg.Tokenizer != "" {
+		tok, f4 := cstr(cfg.Tokenizer)
+		fam, f5 := cstr(cfg.ChatFamily)
+		defer f4()
+		defer f5()
+		if rc := C.cl_engine_load_tokenizer(h, tok, fam); rc != C.CL_OK {
+			err := lastErr(rc)
+			e.Close()
+			return nil, err
+		}
+	}
+	return e, nil
 }
 
 func (e *Engine) Close() { C.cl_engine_destroy(e.h) }
 
-// Handler returns the drop-in for crowdllama.WorkerAPIHandler(ollamaBaseURL).  It is safe to call
-// from many goroutines (one per inbound stream, pkg/peer/peer.go:177-182): cl_generate enqueues into
-// the engine's continuous-batching scheduler and blocks; each in-flight call pins one OS thread.
+// Handler returns the drop-in for crowdllama.WorkerAPIHandler(ollamaBaseURL).  It is safe to call from many
+// goroutines (one per inbound stream, pkg/peer/peer.go:177-182): the library enqueues into the engine's
+// continuous-batching scheduler and blocks; each in-flight call pins one OS thread.
+//
+// The request travels as bytes through cl_handle_message_stream, so GenerateRequest.Options (field 4: seed,
+// temperature, num_predict ... — the §8f-row-3 wire extension) is applied inside the library exactly as for streamed
+// requests, and ctx cancellation (gateway timeout, client gone) reaches the scheduler: the frame callback returns
+// nonzero once ctx is done and the request ends with done_reason "cancelled".  A request without options gets
+// Ollama's defaults, like the reference (api.go:109-118 sends none).  Response fields as api.go:77-92: WorkerId
+// "worker", TotalDuration = UnixNano (kept bug-for-bug), one Done=true message.
 func (e *Engine) Handler() crowdllama.UnifiedAPIHandler {
-	return func(_ context.Context, req *llamav1.BaseMessage) (*llamav1.BaseMessage, error) {
+	return func(ctx context.Context, req *llamav1.BaseMessage) (*llamav1.BaseMessage, error) {
 		generateReq := req.GetGenerateRequest()
 		if generateReq == nil { // api.go:48-51
 			return nil, fmt.Errorf("expected GenerateRequest, got different message type")
 		}
-		model := C.CString(generateReq.Model)
-		defer C.free(unsafe.Pointer(model))
-		prompt := C.CString(generateReq.Prompt) // copied: C never retains Go memory
-		defer C.free(unsafe.Pointer(prompt))
-		var res C.cl_result
-		// nil sampling = Ollama defaults (the reference sends no options, api.go:109-118)
-		if rc := C.cl_generate(e.h, model, prompt, C.size_t(len(generateReq.Prompt)), nil, &res); rc != C.CL_OK {
-			return nil, fmt.Errorf("failed to call B200 engine: %w", lastErr(rc))
+		one := proto.Clone(req).(*llamav1.BaseMessage)
+		one.GetGenerateRequest().Stream = false // this entry point answers with exactly one message (api.go:155 rejects stream:true)
+		var last *llamav1.BaseMessage
+		err := e.HandleStream(ctx, one, func(frame *llamav1.BaseMessage) error {
+			last = frame
+			return nil
+		})
+		if err != nil {
+			return nil, err
 		}
-		defer C.cl_result_free(&res)
-		return &llamav1.BaseMessage{Message: &llamav1.BaseMessage_GenerateResponse{
-			GenerateResponse: &llamav1.GenerateResponse{
-				Model:         generateReq.Model,
-				CreatedAt:     timestamppb.Now(),
-				Response:      C.GoStringN(res.text, C.int(res.text_len)),
-				Done:          true,
-				DoneReason:    C.GoString(res.done_reason),
-				WorkerId:      "worker",              // api.go:83
-				TotalDuration: time.Now().UnixNano(), // api.go:84 (kept bug-for-bug)
-			}}}, nil
+		if last == nil || last.GetGenerateResponse() == nil {
+			return nil, fmt.Errorf("failed to call B200 engine: no response frame")
+		}
+		if ctx.Err() != nil {
+			return nil, ctx.Err()
+		}
+		return last, nil
 	}
 }
 
 // HandleStream is the streaming form (SURVEY.md §8f row 4; the reference rejects stream:true, api.go:155): the
 // request is handed to libclengine as bytes, every response frame (Done=false text deltas, then Done=true) comes
-// back through emit on the calling goroutine.  GenerateRequest.Options (field 4, the §8f-row-3 extension) is
-// applied inside the library.  The frame callback is exported to C as goFrameCallback (see callbacks.go in a real
-// build: //export goFrameCallback, cgo.Handle carries `emit`).
-func (e *Engine) HandleStream(req *llamav1.BaseMessage, emit func(*llamav1.BaseMessage) error) error {
+// back through emit on the calling goroutine.  A failing emit or a done ctx cancels the request inside the engine.
+func (e *Engine) HandleStream(ctx context.Context, req *llamav1.BaseMessage, emit func(*llamav1.BaseMessage) error) error {
 	raw, err := proto.Marshal(req)
 	if err != nil {
 		return err
 	}
+	var emitErr error
 	h := cgo.NewHandle(func(frame []byte) error {
+		if ctx.Err() != nil {
+			return ctx.Err()
+		}
 		var m llamav1.BaseMessage
 		if err := proto.Unmarshal(frame, &m); err != nil {
+			emitErr = err
 			return err
 		}
-		return emit(&m)
+		if err := emit(&m); err != nil {
+			emitErr = err
+			return err
+		}
+		return nil
 	})
 	defer h.Delete()
 	buf := C.CBytes(raw) // copied: C never retains Go memory
@@ -124,7 +163,25 @@ func (e *Engine) HandleStream(req *llamav1.BaseMessage, emit func(*llamav1.BaseM
 		C.cl_frame_cb(C.goFrameCallback), unsafe.Pointer(&h)); rc != C.CL_OK {
 		return fmt.Errorf("failed to call B200 engine: %w", lastErr(rc))
 	}
-	return nil
+	return emitErr
+}
+
+// AdvertisedThroughput quantises the measured capacity to half-octave buckets, AdvertisedLoad to two levels — the
+// same rule as crowdllama_b200/router.py (advertised_throughput / advertised_load) and INTEGRATION.md "What to
+// advertise": FindBestWorker (pkg/peermanager/manager.go:338-387) takes a strict maximum over metadata that is
+// 10-30 s old, so raw numbers send every request to one worker between two refreshes.
+func AdvertisedThroughput(tokensPerSec float64) float64 {
+	if tokensPerSec <= 0 {
+		return 0
+	}
+	return math.Round(math.Pow(2, math.Round(math.Log2(tokensPerSec)*2)/2)*10) / 10
+}
+
+func AdvertisedLoad(load float64) float64 {
+	if load >= 1 {
+		return 1
+	}
+	return 0
 }
 
 // Stats feeds truthful routing metadata into crowdllama.Resource (pkg/crowdllama/types.go:30-40),
@@ -134,18 +191,9 @@ func (e *Engine) Stats(r *crowdllama.Resource) error {
 	if rc := C.cl_engine_stats(e.h, &s); rc != C.CL_OK {
 		return lastErr(rc)
 	}
-	r.TokensThroughput, r.Load = float64(s.tokens_per_sec), float64(s.load)
+	r.TokensThroughput = AdvertisedThroughput(float64(s.tokens_per_sec))
+	r.Load = AdvertisedLoad(float64(s.load))
 	r.VRAMGB, r.GPUModel = int(s.vram_gb), C.GoString(&s.gpu_model[0])
+	r.SupportedModels = []string{e.model}
 	return nil
 }
-
-// callbacks.go (same package; cgo requires //export functions to live in a file without C definitions):
-//
-//	//export goFrameCallback
-//	func goFrameCallback(user unsafe.Pointer, msg *C.uint8_t, n C.size_t) C.int {
-//		emit := (*cgo.Handle)(user).Value().(func([]byte) error)
-//		if err := emit(C.GoBytes(unsafe.Pointer(msg), C.int(n))); err != nil {
-//			return 1 // cancels the request: done_reason "cancelled"
-//		}
-//		return 0
-//	}

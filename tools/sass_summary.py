@@ -39,7 +39,7 @@ def main(dst):
             if m:
                 ins = m.group(1)
                 for p in PAT:
-                    if re.search(r"(^|\s)" + re.escape(p) + r"[A-Z0-9_.]*\s", ins + " "):
+                    if re.search(r"(^|\s)" + re.escape(p) + r"[A-Za-z0-9_.]*\s", ins + " "):
                         counts[cur][p] += 1
         names = demangle(list(counts))
         for (mangled, c), name in zip(counts.items(), names):
