@@ -178,6 +178,7 @@ int Engine::init(const cl_engine_config& c) {
                           (double)cfg.vocab_size * cfg.d_model;
     tok_per_sec_ewma_ = 0.7 * 6.5e12 / (2.0 * params) * (double)max_batch_;
   }
+  sched_prefill_chunk_ = std::max(16, env_int("CL_SCHED_PREFILL_CHUNK", 1024));
   if (c.start_scheduler) start_scheduler();
   return CL_OK;
 }
@@ -585,7 +586,24 @@ int Engine::enqueue_step_batched(int B) {
   if (use_skinny_ && d_skinny_cnt_) return enqueue_step_skinny(B);
   const int d = cfg.d_model, F = cfg.d_ff, L_ = cfg.n_layers, V = cfg.vocab_size;
   int n = 0, r;
-#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; } while (0)
+  // CL_STEP_PROFILE=1 (eager launches only, CL_GRAPH=0): a CUDA event after every launch; per-kernel-class device time of
+  // the step — gap before the kernel included — goes to stderr
+  static const bool prof_env = env_int("CL_STEP_PROFILE", 0) != 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream_, &cap);
+  const bool prof = prof_env && cap == cudaStreamCaptureStatusNone;
+  std::vector<cudaEvent_t> pev;
+  std::vector<const char*> pname;
+  auto mark = [&](const char* name) {
+    if (!prof) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream_);
+    pev.push_back(e);
+    pname.push_back(name);
+  };
+  mark("start");
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; mark(#call); } while (0)
   BatchWs& w = *bws_;
   static const int batch_attn_ctas = env_int("CL_BATCH_ATTN_CTAS", sm_count());
   static const bool bpdl_env = env_int("CL_BATCH_PDL", 1) != 0;
@@ -632,6 +650,25 @@ int Engine::enqueue_step_batched(int B) {
   t.sync_counters = d_sync_; t.n_sync_counters = n_sync_;
   CL_LAUNCH(launch_step_tail(t, stream_));
 #undef CL_LAUNCH
+  if (prof && pev.size() > 1) {
+    cudaStreamSynchronize(stream_);
+    std::map<std::string, std::pair<double, int>> acc;
+    double total = 0.0;
+    for (size_t i = 1; i < pev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pev[i - 1], pev[i]);
+      const std::string full(pname[i]);
+      std::string key = full.substr(0, full.find('('));
+      if (key == "launch_gemm_bf16")
+        key += full.find("L.wqkv") != std::string::npos ? ":qkv" : full.find("L.wo") != std::string::npos ? ":o" : full.find("L.wgu") != std::string::npos ? ":gate|up"
+               : full.find("lm_head_") != std::string::npos ? ":lm_head" : ":down";
+      acc[key].first += ms; acc[key].second += 1;
+      total += ms;
+    }
+    fprintf(stderr, "[step profile] B=%d, %zu launches, %.3f ms on the device\n", B, pev.size() - 1, total);
+    for (auto& kv : acc) fprintf(stderr, "[step profile]   %-34s n=%4d total %8.3f ms  mean %8.2f us\n", kv.first.c_str(), kv.second.second, kv.second.first, 1e3 * kv.second.first / kv.second.second);
+    for (auto e : pev) cudaEventDestroy(e);
+  }
   return n;
 }
 

@@ -261,6 +261,8 @@ class Engine {
   std::condition_variable q_cv_;
   std::deque<std::shared_ptr<Request>> queue_;
   std::vector<std::shared_ptr<Request>> active_;
+  std::shared_ptr<Request> prefilling_;   // the one request whose prompt is being prefilled chunk by chunk (scheduler.cpp)
+  int sched_prefill_chunk_ = 1024;        // tokens per admission chunk while other sequences are decoding (CL_SCHED_PREFILL_CHUNK)
   std::atomic<bool> stop_{false};
   bool sched_started_ = false;
   friend struct Request;

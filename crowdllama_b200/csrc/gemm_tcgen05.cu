@@ -41,9 +41,11 @@ struct GemmParams {
   int T, N, K, ldy;
   int accumulate_into_y;  // 1: Y += result (residual add in place)
   int k_splits;           // > 1: split-K; split s writes its partial to Y + s * T * ldy (the consumer sums in fixed order)
+  GemmEpi epi;            // fused prefill epilogues (EPI template parameter != 0): see kernels.h
 };
+enum { EPI_F32 = 0, EPI_SILU = 1, EPI_ROPE = 2 };
 
-template <int BT, int NST, int MT>
+template <int BT, int NST, int MT, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -155,14 +157,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + m) * BT + c0), v);
           tmem_ld_wait();
-          if (n < p.N) {
+          if constexpr (EPI == EPI_F32) {
+            if (n < p.N) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const int t = t0 + c0 + c;
+                if (t < p.T) {
+                  float* dst = Yb + (size_t)t * p.ldy + n;
+                  const float r = __uint_as_float(v[c]);
+                  *dst = p.accumulate_into_y ? (*dst + r) : r;
+                }
+              }
+            }
+          } else if constexpr (EPI == EPI_SILU) {
+            // rows are interleaved (2i = gate_i, 2i+1 = up_i): the lane pair (2j, 2j+1) holds one SwiGLU input pair per
+            // token; the even lane writes act[t][i] — 16 lanes x bf16 = one full 32-byte sector per token and warp
+            const int i = n >> 1;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
+              const float mine = __uint_as_float(v[c]);
+              const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
               const int t = t0 + c0 + c;
-              if (t < p.T) {
-                float* dst = Yb + (size_t)t * p.ldy + n;
-                const float r = __uint_as_float(v[c]);
-                *dst = p.accumulate_into_y ? (*dst + r) : r;
+              if (!(lane & 1) && n < p.N && t < p.T)
+                p.epi.act[(size_t)t * p.epi.ld_act + i] = __float2bfloat16_rn(mine / (1.0f + __expf(-mine)) * other);
+            }
+          } else {
+            // q|k|v rows are rope-pair-interleaved per head (row 2j = dim j, row 2j+1 = dim j + 64; BM = head_dim = 128, so
+            // a 128-row sub-tile is exactly one head): the lane pair holds one rotation pair per token.  Rotate at the
+            // token's position, round to bf16, write q to q_out[t][head][dim] and k / v straight into the paged cache.
+            const int head = (n0 + m * BM) >> 7, w = n & 127, j = w >> 1;
+            const int dim = (lane & 1) ? j + 64 : j;
+            const GemmEpi& e = p.epi;
+#pragma unroll 4
+            for (int c = 0; c < 32; ++c) {
+              const float mine = __uint_as_float(v[c]);
+              const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+              const int t = t0 + c0 + c;
+              if (t >= p.T || n >= p.N) continue;
+              const int pos = e.pos0 + t;
+              float val = mine;
+              if (head < e.n_heads + e.n_kv) {
+                const float2 cs = __ldg(e.rope + (size_t)pos * 64 + j);
+                // even lane: v0 = mine (dim j), v1 = other -> v0 cos - v1 sin; odd lane: v1 = mine (dim j + 64) -> v1 cos + v0 sin
+                val = (lane & 1) ? mine * cs.x + other * cs.y : mine * cs.x - other * cs.y;
+              }
+              if (head < e.n_heads) {
+                e.q_out[(size_t)t * e.q_dim + head * 128 + dim] = __float2bfloat16_rn(val);
+              } else {
+                const int g = head < e.n_heads + e.n_kv ? head - e.n_heads : head - e.n_heads - e.n_kv;
+                __nv_bfloat16* pool = head < e.n_heads + e.n_kv ? e.kpool : e.vpool;
+                const int page = __ldg(e.block_table + pos / e.page_size), off = pos % e.page_size;
+                pool[(((size_t)page * e.n_kv + g) * e.page_size + off) * 128 + dim] = __float2bfloat16_rn(val);
               }
             }
           }
@@ -227,9 +272,9 @@ bool make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 
 namespace {
 
-template <int BT, int NST, int MT = 1>
+template <int BT, int NST, int MT = 1, int EPI = EPI_F32>
 cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st, bool pdl) {
-  auto kern = gemm_tcgen05_kernel<BT, NST, MT>;
+  auto kern = gemm_tcgen05_kernel<BT, NST, MT, EPI>;
   constexpr size_t smem = (size_t)NST * (MT * BM * BK * 2 + BT * BK * 2) + 1024 + 256;
   static bool attr = false;
   if (!attr) {
@@ -265,13 +310,41 @@ int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, c
   if (!make_map(&mw, W, N, K, BM * MT) || !make_map(&mx, X, T, K, BT)) return -1;
   if (k_splits > 1 && (resid || (K + BK - 1) / BK < k_splits)) return -1;   // every split needs >= 1 k-block (an empty split would never signal its epilogue)
   if (k_splits > 1 && ((K + BK - 1) / BK + k_splits - 1) / k_splits * (k_splits - 1) >= (K + BK - 1) / BK) return -1;
-  GemmParams p{Y, T, N, K, N, resid ? 1 : 0, k_splits};
+  GemmParams p{Y, T, N, K, N, resid ? 1 : 0, k_splits, GemmEpi()};
   cudaError_t e;
   switch (BT) {
     case 256: e = MT == 2 ? launch_inst<256, 3, 2>(mw, mx, p, st, pdl) : launch_inst<256, 4>(mw, mx, p, st, pdl); break;
     case 128: e = launch_inst<128, 6>(mw, mx, p, st, pdl); break;
     case 64: e = launch_inst<64, 8>(mw, mx, p, st, pdl); break;
     default: e = launch_inst<32, 8>(mw, mx, p, st, pdl); break;
+  }
+  return e == cudaSuccess ? 1 : -1;
+}
+
+// Prefill projections with a fused epilogue (no fp32 round trip through HBM): kind 1 = gate|up -> bf16(SiLU(g) * u),
+// kind 2 = q|k|v -> RoPE + bf16 + q buffer / paged KV cache.  One CTA per 128 x BT tile (no split-K, no M pairing).
+int launch_gemm_bf16_epi(const __nv_bfloat16* X, const __nv_bfloat16* W, int T, int N, int K, const GemmEpi& epi, cudaStream_t st) {
+  if (!gemm_tcgen05_supported(T, N, K) || (epi.kind != 1 && epi.kind != 2) || (N & 1)) return -1;
+  if (epi.kind == 2 && (N % 128 || N != (epi.n_heads + 2 * epi.n_kv) * 128)) return -1;   // head_dim 128 = one M sub-tile per head
+  const int BT = T > 128 ? 256 : T > 64 ? 128 : T > 32 ? 64 : 32;
+  CUtensorMap mw, mx;
+  if (!make_map(&mw, W, N, K, BM) || !make_map(&mx, X, T, K, BT)) return -1;
+  GemmParams p{nullptr, T, N, K, N, 0, 1, epi};
+  cudaError_t e;
+  if (epi.kind == 1) {
+    switch (BT) {
+      case 256: e = launch_inst<256, 4, 1, EPI_SILU>(mw, mx, p, st, false); break;
+      case 128: e = launch_inst<128, 6, 1, EPI_SILU>(mw, mx, p, st, false); break;
+      case 64: e = launch_inst<64, 8, 1, EPI_SILU>(mw, mx, p, st, false); break;
+      default: e = launch_inst<32, 8, 1, EPI_SILU>(mw, mx, p, st, false); break;
+    }
+  } else {
+    switch (BT) {
+      case 256: e = launch_inst<256, 4, 1, EPI_ROPE>(mw, mx, p, st, false); break;
+      case 128: e = launch_inst<128, 6, 1, EPI_ROPE>(mw, mx, p, st, false); break;
+      case 64: e = launch_inst<64, 8, 1, EPI_ROPE>(mw, mx, p, st, false); break;
+      default: e = launch_inst<32, 8, 1, EPI_ROPE>(mw, mx, p, st, false); break;
+    }
   }
   return e == cudaSuccess ? 1 : -1;
 }

@@ -170,6 +170,17 @@ int sm_count();
 int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, const float* resid, int T, int N, int K,
                      cudaStream_t st, int k_splits = 1, bool pdl = false);
 bool gemm_tcgen05_supported(int T, int N, int K);
+// fused prefill epilogues of the tcgen05 GEMM (gemm_tcgen05.cu): the fp32 result never leaves the SM
+struct GemmEpi {
+  int kind = 0;                              // 1: gate|up rows interleaved (2i gate, 2i+1 up) -> act[t][i] = bf16(silu(g) * u)
+                                             // 2: q|k|v rows rope-pair-interleaved, head_dim 128 -> RoPE at pos0 + t, bf16, q_out / paged cache
+  __nv_bfloat16* act = nullptr; int ld_act = 0;
+  const float2* rope = nullptr; int pos0 = 0;
+  __nv_bfloat16* q_out = nullptr; int q_dim = 0;
+  __nv_bfloat16* kpool = nullptr; __nv_bfloat16* vpool = nullptr;   // this layer
+  const int* block_table = nullptr; int page_size = 0, n_heads = 0, n_kv = 0;
+};
+int launch_gemm_bf16_epi(const __nv_bfloat16* X, const __nv_bfloat16* W, int T, int N, int K, const GemmEpi& epi, cudaStream_t st);
 // xn[t] = bf16(rmsnorm(h[t]) * gain)
 int launch_rmsnorm_bf16(const float* h, const float* gain, float eps, __nv_bfloat16* out, int T, int d, cudaStream_t st);
 // rope q,k of T tokens starting at pos0; q -> bf16 [T][H][D]; k,v -> paged cache (bf16) and optional dense copies

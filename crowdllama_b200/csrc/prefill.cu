@@ -51,6 +51,7 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
     pws_->cap_tokens = (int)T;
   }
   PrefillWs& w = *pws_;
+  static const bool fused = !(getenv("CL_PREFILL_FUSED") && atoi(getenv("CL_PREFILL_FUSED")) == 0);   // 0: separate RoPE / SiLU kernels
   CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
   const int* bt = d_bt_ + (size_t)s * max_pages_per_seq_;
   int launches = 0, r;
@@ -76,10 +77,18 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
     for (int l = 0; l < cfg.n_layers; ++l) {
       const auto& L = layers_[l];
       CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.attn_norm, cfg.rms_eps, w.xn, T, d, stream_));
-      CL_LAUNCH(launch_gemm_bf16(w.xn, L.wqkv, w.qkv, nullptr, T, qkv_dim_, d, stream_));
-      RopeScatterArgs ra{w.qkv, qkv_dim_, rope_, pos0, T, w.q, kpool_ + (size_t)l * kv_layer_elems_,
-                         vpool_ + (size_t)l * kv_layer_elems_, bt, page_size_, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim};
-      CL_LAUNCH(launch_rope_scatter(ra, stream_));
+      if (fused && cfg.head_dim == 128) {   // RoPE + bf16 + q / paged-cache scatter in the GEMM epilogue
+        GemmEpi eq;
+        eq.kind = 2; eq.rope = rope_; eq.pos0 = pos0; eq.q_out = w.q; eq.q_dim = q_dim_;
+        eq.kpool = kpool_ + (size_t)l * kv_layer_elems_; eq.vpool = vpool_ + (size_t)l * kv_layer_elems_;
+        eq.block_table = bt; eq.page_size = page_size_; eq.n_heads = cfg.n_heads; eq.n_kv = cfg.n_kv_heads;
+        CL_LAUNCH(launch_gemm_bf16_epi(w.xn, L.wqkv, T, qkv_dim_, d, eq, stream_));
+      } else {
+        CL_LAUNCH(launch_gemm_bf16(w.xn, L.wqkv, w.qkv, nullptr, T, qkv_dim_, d, stream_));
+        RopeScatterArgs ra{w.qkv, qkv_dim_, rope_, pos0, T, w.q, kpool_ + (size_t)l * kv_layer_elems_,
+                           vpool_ + (size_t)l * kv_layer_elems_, bt, page_size_, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim};
+        CL_LAUNCH(launch_rope_scatter(ra, stream_));
+      }
       AttnPrefillArgs aa{w.q, kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_, bt, page_size_,
                          pos0, T, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, w.attn};
       if (have_kv_maps_ && attn_prefill_tc_supported(cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, page_size_, pos0, T))
@@ -88,8 +97,14 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
         CL_LAUNCH(launch_attn_prefill(aa, stream_));
       CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.h, w.h, T, d, q_dim_, stream_));
       CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.ffn_norm, cfg.rms_eps, w.xn, T, d, stream_));
-      CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.gu, nullptr, T, 2 * F, d, stream_));
-      CL_LAUNCH(launch_silu_mul_bf16(w.gu, w.act, T, F, stream_));
+      if (fused) {                          // SiLU(g) * u -> bf16 in the GEMM epilogue
+        GemmEpi eg;
+        eg.kind = 1; eg.act = w.act; eg.ld_act = F;
+        CL_LAUNCH(launch_gemm_bf16_epi(w.xn, L.wgu, T, 2 * F, d, eg, stream_));
+      } else {
+        CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.gu, nullptr, T, 2 * F, d, stream_));
+        CL_LAUNCH(launch_silu_mul_bf16(w.gu, w.act, T, F, stream_));
+      }
       CL_LAUNCH(launch_gemm_bf16(w.act, L.wdown, w.h, w.h, T, d, F, stream_));
     }
     if (c0 + T == n) {

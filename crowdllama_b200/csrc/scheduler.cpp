@@ -37,6 +37,8 @@ struct Request {
   std::atomic<bool> cancel{false};
   int64_t t_arrive = 0, prefill_ns = 0, decode_ns = 0, t_done = 0;
   uint64_t arrival = 0;
+  std::vector<int32_t> full;        // prompt + tokens generated before a preemption: what the (re-)prefill has to process
+  size_t prefilled = 0;             // tokens of `full` already in the cache (chunked admission)
   bool greedy() const { return sp.temperature <= 0.f; }
 };
 
@@ -206,37 +208,65 @@ void Engine::scheduler_main() {
   while (true) {
     {
       std::unique_lock<std::mutex> lk(q_mu_);
-      q_cv_.wait(lk, [&] { return stop_ || !queue_.empty() || !active_.empty(); });
+      q_cv_.wait(lk, [&] { return stop_ || !queue_.empty() || !active_.empty() || prefilling_; });
       if (stop_) break;
     }
     std::lock_guard<std::mutex> elk(mu_);
-    // ---- admit (prefill) while there is batch room
-    while ((int)active_.size() < max_batch_) {
-      std::shared_ptr<Request> r;
-      {
-        std::lock_guard<std::mutex> lk(q_mu_);
-        if (queue_.empty()) break;
-        r = queue_.front();
-      }
-      std::vector<int32_t> full(r->prompt);
-      full.insert(full.end(), r->out.begin(), r->out.end());
-      const int need_pages = ((int)full.size() + 1 + page_size_ - 1) / page_size_;
-      if (need_pages > pool_->free_pages()) {
-        if (active_.empty()) {
-          { std::lock_guard<std::mutex> lk(q_mu_); queue_.pop_front(); }
-          complete(r, CL_ERR_OOM, "prompt does not fit in the KV page pool");
-          continue;
+    // ---- admission.  A prompt is prefilled in chunks of sched_prefill_chunk_ tokens, ONE chunk per scheduler iteration,
+    // interleaved with the decode steps of the running batch: an admit never stalls active sequences for more than one
+    // chunk (a 4096-token prompt used to hold every running request for the whole ~85 ms prefill).
+    // Several short prompts may be admitted in one iteration as long as their tokens fit the same budget (a burst of
+    // 128-token chats fills the batch in a few iterations instead of one request per decode step).
+    int budget = sched_prefill_chunk_;
+    while (budget > 0) {
+      if (!prefilling_ && (int)active_.size() < max_batch_) {
+        std::shared_ptr<Request> r;
+        {
+          std::lock_guard<std::mutex> lk(q_mu_);
+          if (!queue_.empty()) r = queue_.front();
         }
-        break;  // wait for running requests to release pages
+        if (r) {
+          r->full.assign(r->prompt.begin(), r->prompt.end());
+          r->full.insert(r->full.end(), r->out.begin(), r->out.end());
+          const int need_pages = ((int)r->full.size() + 1 + page_size_ - 1) / page_size_;
+          if (need_pages > pool_->free_pages()) {
+            if (active_.empty()) {
+              { std::lock_guard<std::mutex> lk(q_mu_); queue_.pop_front(); }
+              complete(r, CL_ERR_OOM, "prompt does not fit in the KV page pool");
+              continue;
+            }
+            // else: wait for running requests to release pages
+          } else {
+            { std::lock_guard<std::mutex> lk(q_mu_); queue_.pop_front(); }
+            int rc = seq_create(&r->seq);
+            if (rc == CL_OK) rc = ensure_capacity(r->seq, (int)r->full.size() + 1);   // all pages up front: a later chunk cannot run dry
+            if (rc) { if (r->seq >= 0) seq_free(r->seq); r->seq = -1; complete(r, rc, get_last_error()); continue; }
+            r->prefilled = 0;
+            prefilling_ = r;
+          }
+        }
       }
-      { std::lock_guard<std::mutex> lk(q_mu_); queue_.pop_front(); }
-      int rc = seq_create(&r->seq);
-      if (rc) { complete(r, rc, get_last_error()); continue; }
+      if (!prefilling_) break;
+      auto r = prefilling_;
+      if (r->cancel.load(std::memory_order_relaxed)) {
+        seq_free(r->seq); r->seq = -1; r->done_reason = "cancelled"; prefilling_.reset();
+        requests_completed_++;
+        complete(r, CL_OK, "");
+        continue;
+      }
+      const size_t left = r->full.size() - r->prefilled;
+      const size_t chunk = active_.empty() ? left : std::min(left, (size_t)budget);   // nobody to stall: the whole prompt at once
+      const bool last = chunk == left;
       const int64_t t0 = now_ns();
-      rc = prefill(r->seq, full.data(), (int)full.size(), logits.data());
+      const int rc = prefill(r->seq, r->full.data() + r->prefilled, (int)chunk, last ? logits.data() : nullptr);
       r->prefill_ns += now_ns() - t0;
-      if (rc) { seq_free(r->seq); complete(r, rc, get_last_error()); continue; }
-      const int32_t next = sample_token(logits.data(), V, r->sp, full.data(), (int)full.size(), (uint64_t)r->out.size());
+      slots_dirty_ = true;                // prefill rewrote d_slots_[0]
+      budget -= (int)std::min(chunk, (size_t)budget);
+      if (rc) { seq_free(r->seq); r->seq = -1; prefilling_.reset(); complete(r, rc, get_last_error()); continue; }
+      r->prefilled += chunk;
+      if (!last) break;                   // budget used up in the middle of a prompt
+      prefilling_.reset();
+      const int32_t next = sample_token(logits.data(), V, r->sp, r->full.data(), (int)r->full.size(), (uint64_t)r->out.size());
       r->out.push_back(next);
       publish(*r, next);
       if (!r->greedy()) cudaMemcpyAsync(d_tok_ + r->seq, &r->out.back(), 4, cudaMemcpyHostToDevice, stream_);
@@ -245,15 +275,26 @@ void Engine::scheduler_main() {
         requests_completed_++;
         tokens_generated_ += 1;
         complete(r, CL_OK, "");
-        continue;
+      } else {
+        active_.push_back(r);
       }
-      active_.push_back(r);
     }
     if (active_.empty()) continue;
     // ---- make room for one more token per active request; preempt the youngest on OOM
     for (size_t i = 0; i < active_.size();) {
       auto& r = active_[i];
       int rc = ensure_capacity(r->seq, seqs_[r->seq].len + 1);
+      if (rc == CL_ERR_OOM && prefilling_) {
+        // the request still being admitted is the youngest of all: it gives its pages back and waits at the queue's head
+        auto v = prefilling_;
+        seq_free(v->seq);
+        v->seq = -1;
+        v->n_preempted++;
+        preemptions_++;
+        prefilling_.reset();
+        { std::lock_guard<std::mutex> lk(q_mu_); queue_.push_front(v); }
+        continue;                       // retry this request's capacity
+      }
       if (rc == CL_ERR_OOM && active_.size() > 1) {
         size_t victim = 0;
         for (size_t k = 1; k < active_.size(); ++k) if (active_[k]->arrival > active_[victim]->arrival) victim = k;
@@ -339,6 +380,7 @@ void Engine::scheduler_main() {
   std::lock_guard<std::mutex> elk(mu_);
   for (auto& r : active_) { if (r->seq >= 0) seq_free(r->seq); complete(r, CL_ERR_SHUTDOWN, "engine shutting down"); }
   active_.clear();
+  if (prefilling_) { if (prefilling_->seq >= 0) seq_free(prefilling_->seq); complete(prefilling_, CL_ERR_SHUTDOWN, "engine shutting down"); prefilling_.reset(); }
   std::deque<std::shared_ptr<Request>> rest;
   { std::lock_guard<std::mutex> lk(q_mu_); rest.swap(queue_); }
   for (auto& r : rest) complete(r, CL_ERR_SHUTDOWN, "engine shutting down");

@@ -112,23 +112,30 @@ func (e *Engine) Handler() crowdllama.UnifiedAPIHandler {
 		if generateReq == nil { // api.go:48-51
 			return nil, fmt.Errorf("expected GenerateRequest, got different message type")
 		}
+		// Ask the engine for frames even though one message goes back: the frame callback is where ctx is polled, so
+		// a cancelled request stops decoding within one batch of tokens instead of running to num_predict.
 		one := proto.Clone(req).(*llamav1.BaseMessage)
-		one.GetGenerateRequest().Stream = false // this entry point answers with exactly one message (api.go:155 rejects stream:true)
-		var last *llamav1.BaseMessage
+		one.GetGenerateRequest().Stream = true
+		var text []byte
+		var last *llamav1.GenerateResponse
 		err := e.HandleStream(ctx, one, func(frame *llamav1.BaseMessage) error {
-			last = frame
+			if g := frame.GetGenerateResponse(); g != nil {
+				text = append(text, g.Response...)
+				last = g
+			}
 			return nil
 		})
 		if err != nil {
 			return nil, err
 		}
-		if last == nil || last.GetGenerateResponse() == nil {
-			return nil, fmt.Errorf("failed to call B200 engine: no response frame")
-		}
 		if ctx.Err() != nil {
 			return nil, ctx.Err()
 		}
-		return last, nil
+		if last == nil || !last.Done {
+			return nil, fmt.Errorf("failed to call B200 engine: no final response frame")
+		}
+		last.Response = string(text) // api.go:80: the full assistant text in ONE message (the reference never streams, api.go:155)
+		return &llamav1.BaseMessage{Message: &llamav1.BaseMessage_GenerateResponse{GenerateResponse: last}}, nil
 	}
 }
 

@@ -342,3 +342,45 @@ def test_short_request_admitted_during_a_long_one_does_not_disturb_it():
         assert got == short_solo
         st = e.stats()
         assert st["kv_pages_used"] == 0 and st["active_seqs"] == 0
+
+
+def test_long_prompt_is_admitted_in_chunks_between_decode_steps(monkeypatch):
+    """scheduler.cpp admission: with another request decoding, a long prompt is prefilled CL_SCHED_PREFILL_CHUNK tokens
+    per scheduler iteration (here 16), so the running request keeps producing tokens while the newcomer is admitted; a
+    burst of short prompts shares one iteration's budget.  Results must be those of the requests run alone (chunk
+    boundaries only change the order of a few fp32 additions: allow a near-tie flip)."""
+    import threading
+    import time
+    monkeypatch.setenv("CL_SCHED_PREFILL_CHUNK", "16")
+    cfg = oc.PRESETS["tiny-test"]
+    V = cfg["vocab_size"]
+    long_prompt = np.array([(i * 31 + 7) % V for i in range(200)], np.int32)
+    a_prompt = _prompt(12, V)
+    shorts = [np.array([(11 * i + 5 * j + 2) % V for j in range(6 + i)], np.int32) for i in range(5)]
+    with eng.Engine(preset="tiny-test", seed=21, max_batch=8, max_seqs=8, start_scheduler=True) as e:
+        a_solo = e.generate_ids(a_prompt, eng.greedy(400, ignore_eos=True)).token_ids
+        b_solo = e.generate_ids(long_prompt, eng.greedy(24, ignore_eos=True)).token_ids
+        s_solo = [e.generate_ids(p, eng.greedy(10, ignore_eos=True)).token_ids for p in shorts]
+        out, stamps = {}, []
+
+        def run_a():
+            sp = eng.greedy(400, ignore_eos=True)
+            out["a"] = e.generate_ids(a_prompt, sp)
+
+        def run(name, p, n):
+            out[name] = e.generate_ids(p, eng.greedy(n, ignore_eos=True))
+        ta = threading.Thread(target=run_a)
+        ta.start()
+        time.sleep(0.02)                                            # A is decoding
+        th = [threading.Thread(target=run, args=("b", long_prompt, 24))] + \
+             [threading.Thread(target=run, args=(f"s{i}", p, 10)) for i, p in enumerate(shorts)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        ta.join()
+        assert out["a"].n_generated == 400 and out["b"].n_generated == 24
+        assert (out["a"].token_ids == a_solo).mean() > 0.9          # identical up to a possible near-tie flip late in the run
+        assert out["b"].token_ids[0] == b_solo[0] and (out["b"].token_ids == b_solo).mean() > 0.7
+        for i in range(len(shorts)):
+            assert out[f"s{i}"].n_generated == 10 and out[f"s{i}"].token_ids[0] == s_solo[i][0]
+        st = e.stats()
+        assert st["kv_pages_used"] == 0 and st["active_seqs"] == 0 and st["requests_completed"] >= 7 + 7
