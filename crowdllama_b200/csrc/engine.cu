@@ -179,6 +179,7 @@ int Engine::init(const cl_engine_config& c) {
     tok_per_sec_ewma_ = 0.7 * 6.5e12 / (2.0 * params) * (double)max_batch_;
   }
   sched_prefill_chunk_ = std::max(16, env_int("CL_SCHED_PREFILL_CHUNK", 1024));
+  prefill_small_max_ = std::min(256, env_int("CL_PREFILL_SMALL_MAX", 256));
   if (c.start_scheduler) start_scheduler();
   return CL_OK;
 }
@@ -505,6 +506,7 @@ int Engine::enqueue_step(int B, bool tail) {
 // rounds(= ceil(tiles * s / SMs)) x k-blocks per unit.  224 gate|up tiles on 148 SMs cost 2 x 64 k-blocks unsplit but
 // 8 x 13 with 5 splits (ideal 96.9); down 56 -> 50 with 9.  Among the counts within 10 % of the best the smallest wins
 // (fewer partials for the consumer kernel to sum).
+int pick_splits_public(int n_rows, int K) { return pick_splits(n_rows, K); }
 static int pick_splits(int n_rows, int K) {
   const int tiles = (n_rows + 127) / 128, nkb = (K + 63) / 64, sms = sm_count();
   int best_cost = 1 << 30;
@@ -783,7 +785,11 @@ int Engine::prefill(cl_seq_t s, const int32_t* ids, int n, float* logits_out) {
   for (int i = 0; i < n; ++i)
     if (ids[i] < 0 || ids[i] >= cfg.vocab_size) { set_last_error("token id out of range"); return CL_ERR_INVALID_ARG; }
   if (seqs_[s].len + n > cfg.max_seq_len) { set_last_error("sequence exceeds max_seq_len"); return CL_ERR_TOO_LONG; }
-  if (n >= prefill_min_tokens_ && prefill_path_ok()) return prefill_chunked(s, ids, n, logits_out);
+  if (n >= prefill_min_tokens_ && prefill_path_ok()) {
+    // short prompts: split-K projections so that every SM streams weights (d_model <= 8192: one 1024-thread CTA per row in the glue)
+    if (n <= prefill_small_max_ && cfg.d_model <= 8192 && cfg.d_model % 4 == 0) return prefill_small(s, ids, n, logits_out);
+    return prefill_chunked(s, ids, n, logits_out);
+  }
   return prefill_tokenwise(s, ids, n, logits_out);
 }
 

@@ -178,6 +178,7 @@ class Engine {
   int read_logits(int slot, float* out);
   int prefill_tokenwise(cl_seq_t s, const int32_t* ids, int n, float* logits_out);
   int prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits_out);  // tcgen05 path (prefill.cu)
+  int prefill_small(cl_seq_t s, const int32_t* ids, int n, float* logits_out);    // short prompts: split-K projections (prefill.cu)
   bool prefill_path_ok() const;
   int set_single_slot(cl_seq_t s);
 
@@ -229,6 +230,10 @@ class Engine {
     __nv_bfloat16* act = nullptr;   // [T][F]
   };
   std::unique_ptr<PrefillWs> pws_;
+  struct SmallPrefillWs { float* part = nullptr; __nv_bfloat16* xn = nullptr; __nv_bfloat16* q = nullptr; __nv_bfloat16* attn = nullptr;
+                          float* h = nullptr; __nv_bfloat16* act = nullptr; int* iota = nullptr; };
+  std::unique_ptr<SmallPrefillWs> sws_;
+  int prefill_small_max_ = 256;       // prompts up to this many tokens take the split-K path (CL_PREFILL_SMALL_MAX, 0 = off)
   struct BatchWs { __nv_bfloat16* xn = nullptr; __nv_bfloat16* attn = nullptr; __nv_bfloat16* act = nullptr; float* part = nullptr; float* logits = nullptr; };
   std::unique_ptr<BatchWs> bws_;
   bool use_batch_gemm_ = false, use_skinny_ = true;

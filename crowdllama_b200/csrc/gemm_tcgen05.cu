@@ -302,9 +302,11 @@ int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, c
   if (!gemm_tcgen05_supported(T, N, K)) return -1;
   if (resid && resid != Y) return -1;  // residual add is in place
   const int BT = T > 128 ? 256 : T > 64 ? 128 : T > 32 ? 64 : 32;
-  // 256 x 256 tiles (two M sub-tiles per CTA) for prompt-sized T: the operand stream from L2, not the tensor pipe, bounds
-  // the 128 x 256 tile.  CL_GEMM_MT=1 keeps the single sub-tile (A/B measurements).
-  static const int mt_env = getenv("CL_GEMM_MT") ? atoi(getenv("CL_GEMM_MT")) : 2;
+  // 256 x 256 tiles (two M sub-tiles per CTA, CL_GEMM_MT=2) cut the operand stream from L2 by a third, but measured
+  // SLOWER on the Llama-3-8B shapes at T = 4096 (r2d: 1122 vs 1216 TFLOP/s sustained per layer; only the K = 14336
+  // down-projection gains, 1316 vs 1132): wave quantisation (256 instead of 512 tiles on 148 SMs) and the lost
+  // epilogue overlap cost more than the L2 traffic saves.  Kept opt-in for the measurements.
+  static const int mt_env = getenv("CL_GEMM_MT") ? atoi(getenv("CL_GEMM_MT")) : 1;
   const int MT = (BT == 256 && k_splits <= 1 && N >= 2 * BM && mt_env >= 2) ? 2 : 1;
   CUtensorMap mw, mx;
   if (!make_map(&mw, W, N, K, BM * MT) || !make_map(&mx, X, T, K, BT)) return -1;

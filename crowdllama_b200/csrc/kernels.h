@@ -190,6 +190,7 @@ struct RopeScatterArgs {
   __nv_bfloat16* q_out;              // [T][H*D]
   __nv_bfloat16* kpool; __nv_bfloat16* vpool; const int* block_table; int page_size;
   int n_heads, n_kv, head_dim;
+  int n_split = 1; size_t split_stride = 0;   // qkv = sum of n_split split-K partials, split_stride floats apart (fixed order)
 };
 int launch_rope_scatter(const RopeScatterArgs& a, cudaStream_t st);
 // causal attention of T new tokens (positions pos0..pos0+T-1) against the paged cache

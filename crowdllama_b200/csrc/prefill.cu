@@ -24,6 +24,97 @@ bool Engine::prefill_path_ok() const {
   return !disabled && gemm_tcgen05_supported(16, cfg.d_model, cfg.d_model);
 }
 
+// split-K rule shared with the batched decode step (engine.cu)
+int pick_splits_public(int n_rows, int K);
+
+// Short prompts (prefill_min_tokens_ <= n <= 256, e.g. a 128-token chat): one token tile per W row tile means only
+// N/128 CTAs stream the weights of a projection (48 for q|k|v, 32 for o and down) — 11 ms for 128 tokens where the
+// weight stream alone needs 2.4.  Same recipe as the batched decode step: split-K so that ~148 CTAs share every
+// projection's weights, fp32 partials in a workspace, the per-row glue kernels (batch_kernels.cu) fold them in fixed
+// order into the residual stream / RoPE / SiLU.  Rows are the prompt's tokens, attention is the causal prefill kernel.
+int Engine::prefill_small(cl_seq_t s, const int32_t* ids, int n, float* logits_out) {
+  auto& q = seqs_[s];
+  int rc = ensure_capacity(s, q.len + n);
+  if (rc) return rc;
+  const int d = cfg.d_model, F = cfg.d_ff, T = n, pos0 = q.len;
+  const int s_qkv = pick_splits_public(qkv_dim_, d), s_o = pick_splits_public(d, q_dim_), s_gu = pick_splits_public(2 * F, d), s_dn = pick_splits_public(d, F);
+  if (!sws_) {
+    sws_.reset(new SmallPrefillWs());
+    const size_t Tm = 256;
+    size_t part = 0;
+    part = std::max(part, (size_t)s_qkv * Tm * qkv_dim_);
+    part = std::max(part, (size_t)s_o * Tm * d);
+    part = std::max(part, (size_t)s_gu * Tm * 2 * F);
+    part = std::max(part, (size_t)s_dn * Tm * d);
+    auto alloc = [&](auto*& p, size_t bytes) -> int {
+      void* v = nullptr;
+      if (cudaMalloc(&v, bytes) != cudaSuccess) { cudaGetLastError(); set_last_error("short-prompt prefill workspace: out of memory"); return CL_ERR_OOM; }
+      allocs_.push_back(v);
+      p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(v);
+      return CL_OK;
+    };
+    if ((rc = alloc(sws_->part, part * 4)) || (rc = alloc(sws_->xn, Tm * d * 2)) || (rc = alloc(sws_->q, Tm * q_dim_ * 2)) ||
+        (rc = alloc(sws_->attn, Tm * q_dim_ * 2)) || (rc = alloc(sws_->h, Tm * d * 4)) || (rc = alloc(sws_->act, Tm * F * 2)) ||
+        (rc = alloc(sws_->iota, Tm * 4))) { sws_.reset(); return rc; }
+    std::vector<int> io(Tm);
+    for (size_t i = 0; i < Tm; ++i) io[i] = (int)i;
+    CL_CUDA_OK(cudaMemcpy(sws_->iota, io.data(), Tm * 4, cudaMemcpyHostToDevice));
+  }
+  SmallPrefillWs& w = *sws_;
+  CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+  const int* bt = d_bt_ + (size_t)s * max_pages_per_seq_;
+  int launches = 0, r;
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; } while (0)
+  CL_LAUNCH(launch_embed_rows(embed_, d, d_prompt_, w.h, T, stream_));
+  const float* pending = nullptr;   // split-K partials of the previous residual projection, folded in by the next norm
+  int pending_s = 0;
+  for (int l = 0; l < cfg.n_layers; ++l) {
+    const auto& L = layers_[l];
+    CL_LAUNCH(launch_batch_resid_norm(w.h, d, pending, pending_s, T, L.attn_norm, cfg.rms_eps, w.xn, w.iota, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wqkv, w.part, nullptr, T, qkv_dim_, d, stream_, s_qkv));
+    RopeScatterArgs ra{w.part, qkv_dim_, rope_, pos0, T, w.q, kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_,
+                       bt, page_size_, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim};
+    ra.n_split = s_qkv; ra.split_stride = (size_t)T * qkv_dim_;
+    CL_LAUNCH(launch_rope_scatter(ra, stream_));
+    AttnPrefillArgs aa{w.q, kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_, bt, page_size_,
+                       pos0, T, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, w.attn};
+    if (have_kv_maps_ && attn_prefill_tc_supported(cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, page_size_, pos0, T))
+      CL_LAUNCH(launch_attn_prefill_tc(aa, kmap_, vmap_, (long long)l * n_pages_ * cfg.n_kv_heads * page_size_, stream_));
+    else
+      CL_LAUNCH(launch_attn_prefill(aa, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.part, nullptr, T, d, q_dim_, stream_, s_o));
+    CL_LAUNCH(launch_batch_resid_norm(w.h, d, w.part, s_o, T, L.ffn_norm, cfg.rms_eps, w.xn, w.iota, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.part, nullptr, T, 2 * F, d, stream_, s_gu));
+    CL_LAUNCH(launch_batch_silu(w.part, s_gu, T, F, w.act, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.act, L.wdown, w.part, nullptr, T, d, F, stream_, s_dn));
+    pending = w.part; pending_s = s_dn;
+  }
+  // fold the last down-projection into the residual rows (the normalised copy it also writes is not used), then the shared tail
+  CL_LAUNCH(launch_batch_resid_norm(w.h, d, pending, pending_s, T, final_norm_, cfg.rms_eps, w.xn, w.iota, stream_));
+  CL_CUDA_OK(cudaMemcpyAsync(d_h_ + (size_t)s * d, w.h + (size_t)(T - 1) * d, (size_t)d * 4, cudaMemcpyDeviceToDevice, stream_));
+  const int last_pos = q.len + n - 1;
+  CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &last_pos, 4, cudaMemcpyHostToDevice, stream_));
+  rc = set_single_slot(s);
+  if (rc) return rc;
+  GemvArgs lm;
+  lm.slots = d_slots_; lm.batch = 1;
+  lm.W = lm_head_; lm.N = cfg.vocab_size; lm.K = d; lm.h = d_h_; lm.gain = final_norm_; lm.eps = cfg.rms_eps;
+  lm.y = d_logits_; lm.x_stride = d; lm.y_stride = cfg.vocab_size;
+  CL_LAUNCH(launch_gemv(gemv_variant_, EPI_STORE, true, lm, stream_, false));
+  StepTailArgs t;
+  t.logits = d_logits_; t.vocab = cfg.vocab_size; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
+  t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
+  t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = 1;
+  CL_LAUNCH(launch_step_tail(t, stream_));
+#undef CL_LAUNCH
+  launches_ += launches;
+  q.len += n;
+  q.history.insert(q.history.end(), ids, ids + n);
+  if (logits_out) return read_logits(s, logits_out);
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  return CL_OK;
+}
+
 int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits_out) {
   auto& q = seqs_[s];
   int rc = ensure_capacity(s, q.len + n);

@@ -68,11 +68,17 @@ __global__ void __launch_bounds__(256) rope_scatter_kernel(const RopeScatterArgs
   const float* row = a.qkv + (size_t)t * a.qkv_stride;
   const float2* rope = a.rope + (size_t)pos * half;
   const int qd = a.n_heads * HD, kvd = a.n_kv * HD;
+  // split-K GEMM output (short prompts): the value is the fixed-order sum of n_split partials, split_stride floats apart
+  auto val = [&](int col) {
+    float v = row[col];
+    for (int s = 1; s < a.n_split; ++s) v += row[(size_t)s * a.split_stride + col];
+    return v;
+  };
   // q heads
   for (int i = threadIdx.x; i < a.n_heads * half; i += blockDim.x) {
     const int hh = i / half, j = i % half;
     const float2 cs = rope[j];
-    const float x0 = row[hh * HD + 2 * j], x1 = row[hh * HD + 2 * j + 1];   // rope-pair-interleaved GEMM output
+    const float x0 = val(hh * HD + 2 * j), x1 = val(hh * HD + 2 * j + 1);   // rope-pair-interleaved GEMM output
     a.q_out[(size_t)t * qd + hh * HD + j] = __float2bfloat16_rn(x0 * cs.x - x1 * cs.y);
     a.q_out[(size_t)t * qd + hh * HD + j + half] = __float2bfloat16_rn(x1 * cs.x + x0 * cs.y);
   }
@@ -80,7 +86,7 @@ __global__ void __launch_bounds__(256) rope_scatter_kernel(const RopeScatterArgs
   for (int i = threadIdx.x; i < a.n_kv * half; i += blockDim.x) {
     const int g = i / half, j = i % half;
     const float2 cs = rope[j];
-    const float x0 = row[qd + g * HD + 2 * j], x1 = row[qd + g * HD + 2 * j + 1];
+    const float x0 = val(qd + g * HD + 2 * j), x1 = val(qd + g * HD + 2 * j + 1);
     const size_t base = (((size_t)page * a.n_kv + g) * a.page_size + off) * HD;
     a.kpool[base + j] = __float2bfloat16_rn(x0 * cs.x - x1 * cs.y);
     a.kpool[base + j + half] = __float2bfloat16_rn(x1 * cs.x + x0 * cs.y);
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(256) rope_scatter_kernel(const RopeScatterArgs
     const int g = i / HD, w = i % HD;                      // stored column w -> dim (w even ? w/2 : w/2 + half)
     const int j = (w & 1) ? (w >> 1) + half : (w >> 1);
     const size_t base = (((size_t)page * a.n_kv + g) * a.page_size + off) * HD;
-    a.vpool[base + j] = __float2bfloat16_rn(row[qd + kvd + i]);
+    a.vpool[base + j] = __float2bfloat16_rn(val(qd + kvd + i));
   }
 }
 int launch_rope_scatter(const RopeScatterArgs& a, cudaStream_t st) {

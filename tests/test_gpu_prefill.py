@@ -82,8 +82,12 @@ def _prompt(n, vocab, salt=0):
     return np.array([(i * 7919 + 13 + salt) % vocab for i in range(n)], np.int32)
 
 
+@pytest.mark.parametrize("small_max", ["256", "0"])
 @pytest.mark.parametrize("n_prompt", [16, 40, 97, 200])
-def test_engine_chunked_prefill_matches_oracle(n_prompt):
+def test_engine_chunked_prefill_matches_oracle(monkeypatch, n_prompt, small_max):
+    """Both tensor-core prefill paths against the oracle: short prompts (<= 256 tokens) on the split-K projections
+    (prefill_small), and — CL_PREFILL_SMALL_MAX=0 — the same prompts on the full-tile path with its fused epilogues."""
+    monkeypatch.setenv("CL_PREFILL_SMALL_MAX", small_max)
     cfg = oc.PRESETS["tiny-test"]
     m = oc.Model(cfg, seed=1234)
     with eng.Engine(preset="tiny-test", seed=1234) as e:
@@ -109,12 +113,27 @@ def test_engine_chunked_prefill_matches_oracle(n_prompt):
 
 
 def test_prefill_paths_agree_on_llama_shapes():
-    """Token-wise (decode kernels) and chunked (tcgen05) prefill of the same prompt give the same
-    logits within tolerance at Llama-3-8B layer shapes (2 layers)."""
+    """Token-wise (decode kernels), full-tile (tcgen05, fused epilogues) and short-prompt (split-K) prefill of the same
+    prompts give the same logits within tolerance at Llama-3-8B layer shapes (2 layers); the short-prompt path is also
+    compared with the oracle directly."""
     cfg = dict(oc.PRESETS["llama3-8b"])
     cfg["n_layers"] = 2
     cfg["max_seq_len"] = 512
     with eng.Engine(model=cfg, seed=1234, max_batch=2) as e:
+        m = oc.Model(cfg, seed=1234)
+        for n_small in (128, 250):
+            ps = _prompt(n_small, cfg["vocab_size"], salt=3)
+            so = m.new_seq()
+            lo = so.prefill_block(ps)
+            ss = e.seq_create()
+            ls = e.prefill(ss, ps)                 # <= 256 tokens: split-K projections
+            assert np.abs(ls - lo).max() < 0.125, float(np.abs(ls - lo).max())
+            tok = int(lo.argmax())
+            for _ in range(3):
+                lo = so.forward([tok]); ls, _ = e.decode_step(ss, tok)
+                assert np.abs(ls - lo).max() < 0.125
+                tok = int(lo.argmax())
+            e.seq_free(ss)
         p = _prompt(300, cfg["vocab_size"])
         s1 = e.seq_create()
         a = e.prefill(s1, p)                       # tcgen05
