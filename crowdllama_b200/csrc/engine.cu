@@ -333,24 +333,11 @@ int Engine::alloc_state() {
     DMALLOC(bws_->xn, Bm * d * 2);
     DMALLOC(bws_->attn, Bm * q_dim_ * 2);
     DMALLOC(bws_->act, Bm * (size_t)cfg.d_ff * 2);
-    use_skinny_ = env_int("CL_BATCH_SKINNY", 0) != 0;   // fused-epilogue variant: measured 5.8-6.2 ms vs 4.7 ms per B=8 step (profiles/README.md)
-    // split-K partial workspace: the old path uses <= 4 splits; the skinny path up to K/64/kb splits of [B][N]
+    // split-K partial workspace of the four projections (pick_splits)
     size_t part_floats = 4 * Bm * widest;
-    for (int nk : {0, 1, 2, 3}) {   // split-K partials of the four projections (pick_splits)
+    for (int nk : {0, 1, 2, 3}) {
       const int N = nk == 0 ? qkv_dim_ : nk == 2 ? 2 * cfg.d_ff : d, K = nk == 1 ? q_dim_ : nk == 3 ? cfg.d_ff : d;
       part_floats = std::max(part_floats, (size_t)pick_splits(N, K) * Bm * (size_t)N);
-    }
-    if (use_skinny_) {
-      const int kb_small = env_int("CL_SKINNY_KB", 4), kb_gu = env_int("CL_SKINNY_KB_GU", 8), kb_lm = env_int("CL_SKINNY_KB_LM", 16);
-      part_floats = std::max(part_floats, (size_t)skinny_splits(d, kb_small) * Bm * qkv_dim_);
-      part_floats = std::max(part_floats, (size_t)skinny_splits(q_dim_, kb_small) * Bm * d);
-      part_floats = std::max(part_floats, (size_t)skinny_splits(d, kb_gu) * Bm * 2 * cfg.d_ff);
-      part_floats = std::max(part_floats, (size_t)skinny_splits(cfg.d_ff, kb_small) * Bm * d);
-      part_floats = std::max(part_floats, (size_t)skinny_splits(d, kb_lm) * Bm * cfg.vocab_size);
-      skinny_cnt_stride_ = skinny_counter_words(std::max<int>(cfg.vocab_size, 2 * cfg.d_ff));
-      const size_t words = skinny_cnt_stride_ * (size_t)(4 * cfg.n_layers + 1);
-      DMALLOC(d_skinny_cnt_, words * 4);
-      CL_CUDA_OK(cudaMemsetAsync(d_skinny_cnt_, 0, words * 4, stream_));
     }
     DMALLOC(bws_->part, part_floats * 4);
     DMALLOC(bws_->logits, Bm * (size_t)cfg.vocab_size * 4);
@@ -523,69 +510,7 @@ static int pick_splits(int n_rows, int K) {
   return 1;
 }
 
-// ---- batched token step, v2: skinny tensor-core projections with fused epilogues (gemm_skinny.cu), 7 kernels per
-// layer chained with programmatic dependent launch: norm -> q|k|v (+RoPE, KV append) -> attention (bf16 out) ->
-// o (+residual) -> norm -> gate|up (+SiLU*mul) -> down (+residual)
-int Engine::enqueue_step_skinny(int B) {
-  const int d = cfg.d_model, F = cfg.d_ff, L_ = cfg.n_layers, V = cfg.vocab_size;
-  int n = 0, r;
-#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; } while (0)
-  BatchWs& w = *bws_;
-  static const int kb_small = env_int("CL_SKINNY_KB", 4), kb_gu = env_int("CL_SKINNY_KB_GU", 8), kb_lm = env_int("CL_SKINNY_KB_LM", 16);
-  static const int attn_ctas = env_int("CL_BATCH_ATTN_CTAS", sm_count());
-  const bool pdl = use_pdl_;
-  int site = 0;
-  auto gemm = [&](const __nv_bfloat16* X, const __nv_bfloat16* W, int N, int K, int kb, int epi) {
-    SkinnyArgs a;
-    static const int old_splits = env_int("CL_SKINNY_SPLITS_OLD", 0);
-    a.X = X; a.W = W; a.T = B; a.N = N; a.K = K; a.k_splits = old_splits ? pick_splits(N, K) : skinny_splits(K, kb); a.epi = epi;
-    a.part = w.part; a.counters = d_skinny_cnt_ + (size_t)(site++) * skinny_cnt_stride_; a.slots = d_slots_;
-    return a;
-  };
-  CL_LAUNCH(launch_embed(embed_, d, d_tok_, d_h_, d, d_slots_, B, stream_));
-  for (int l = 0; l < L_; ++l) {
-    const auto& L = layers_[l];
-    CL_LAUNCH(launch_batch_norm(d_h_, d, B, L.attn_norm, cfg.rms_eps, w.xn, d_slots_, stream_, pdl));
-    SkinnyArgs gq = gemm(w.xn, L.wqkv, qkv_dim_, d, kb_small, SK_QKV);
-    gq.qkv.rope = rope_; gq.qkv.pos = d_pos_; gq.qkv.block_tables = d_bt_; gq.qkv.bt_stride = max_pages_per_seq_;
-    gq.qkv.kpool = kpool_ + (size_t)l * kv_layer_elems_; gq.qkv.vpool = vpool_ + (size_t)l * kv_layer_elems_;
-    gq.qkv.n_heads = cfg.n_heads; gq.qkv.n_kv = cfg.n_kv_heads; gq.qkv.head_dim = cfg.head_dim; gq.qkv.page_size = page_size_;
-    gq.q_out = d_q_; gq.q_stride = q_dim_;
-    CL_LAUNCH(launch_gemm_skinny(gq, stream_, pdl));
-    AttnDecodeArgs a;
-    a.q = d_q_; a.q_stride = q_dim_;
-    a.kpool = gq.qkv.kpool; a.vpool = gq.qkv.vpool; a.block_tables = d_bt_; a.bt_stride = max_pages_per_seq_; a.pos = d_pos_;
-    a.out = d_attn_; a.out_stride = q_dim_; a.out_bf16 = w.attn; a.part = d_attn_part_; a.counters = d_attn_cnt_;
-    a.slots = d_slots_; a.batch = B; a.n_heads = cfg.n_heads; a.n_kv = cfg.n_kv_heads; a.head_dim = cfg.head_dim;
-    a.page_size = page_size_; a.nsplit = std::max(1, std::min(nsplit_, attn_ctas / (cfg.n_kv_heads * B))); a.pdl_early = 1;
-    CL_LAUNCH(launch_attn_decode(a, stream_, pdl));
-    SkinnyArgs go = gemm(w.attn, L.wo, d, q_dim_, kb_small, SK_RESID);
-    go.y = d_h_; go.ldy = d;
-    CL_LAUNCH(launch_gemm_skinny(go, stream_, pdl));
-    CL_LAUNCH(launch_batch_norm(d_h_, d, B, L.ffn_norm, cfg.rms_eps, w.xn, d_slots_, stream_, pdl));
-    SkinnyArgs gu = gemm(w.xn, L.wgu, 2 * F, d, kb_gu, SK_GATEUP);
-    gu.act = w.act;
-    CL_LAUNCH(launch_gemm_skinny(gu, stream_, pdl));
-    SkinnyArgs gd = gemm(w.act, L.wdown, d, F, kb_small, SK_RESID);
-    gd.y = d_h_; gd.ldy = d;
-    CL_LAUNCH(launch_gemm_skinny(gd, stream_, pdl));
-  }
-  CL_LAUNCH(launch_batch_norm(d_h_, d, B, final_norm_, cfg.rms_eps, w.xn, d_slots_, stream_, pdl));
-  SkinnyArgs lm = gemm(w.xn, lm_head_, V, d, kb_lm, SK_STORE);
-  lm.y = d_logits_; lm.ldy = V;
-  CL_LAUNCH(launch_gemm_skinny(lm, stream_, pdl));
-  StepTailArgs t;
-  t.logits = d_logits_; t.vocab = V; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
-  t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
-  t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = B;
-  t.sync_counters = d_sync_; t.n_sync_counters = n_sync_;
-  CL_LAUNCH(launch_step_tail(t, stream_));
-#undef CL_LAUNCH
-  return n;
-}
-
 int Engine::enqueue_step_batched(int B) {
-  if (use_skinny_ && d_skinny_cnt_) return enqueue_step_skinny(B);
   const int d = cfg.d_model, F = cfg.d_ff, L_ = cfg.n_layers, V = cfg.vocab_size;
   int n = 0, r;
   // CL_STEP_PROFILE=1 (eager launches only, CL_GRAPH=0): a CUDA event after every launch; per-kernel-class device time of

@@ -236,10 +236,7 @@ class Engine {
   int prefill_small_max_ = 256;       // prompts up to this many tokens take the split-K path (CL_PREFILL_SMALL_MAX, 0 = off)
   struct BatchWs { __nv_bfloat16* xn = nullptr; __nv_bfloat16* attn = nullptr; __nv_bfloat16* act = nullptr; float* part = nullptr; float* logits = nullptr; };
   std::unique_ptr<BatchWs> bws_;
-  bool use_batch_gemm_ = false, use_skinny_ = true;
-  unsigned* d_skinny_cnt_ = nullptr;   // per call site: [2 + n_tiles] self-cleaning counters (gemm_skinny.cu)
-  size_t skinny_cnt_stride_ = 0;
-  int enqueue_step_skinny(int B);
+  bool use_batch_gemm_ = false;
   int batch_gemm_min_ = 3;
   int prefill_chunk_tokens_ = 4096;
 

@@ -206,28 +206,6 @@ bool attn_prefill_tc_supported(int n_heads, int n_kv, int head_dim, int page_siz
 int launch_attn_prefill_tc(const AttnPrefillArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, long long layer_row0, cudaStream_t st);
 // act = bf16(silu(gu[:, 2i]) * gu[:, 2i+1])
 int launch_silu_mul_bf16(const float* gu, __nv_bfloat16* act, int T, int d_ff, cudaStream_t st);
-// ---- batched-decode projections (gemm_skinny.cu): T <= 32 token columns, weight-stream bound ----------
-enum SkinnyEpi { SK_STORE = 0, SK_RESID = 1, SK_GATEUP = 2, SK_QKV = 3 };
-struct SkinnyArgs {
-  const __nv_bfloat16* X = nullptr;    // [T][K] bf16
-  const __nv_bfloat16* W = nullptr;    // [N][K] bf16
-  int T = 0, N = 0, K = 0;
-  int k_splits = 1;                    // see skinny_splits()
-  int epi = SK_STORE;
-  float* part = nullptr;               // workspace >= k_splits * T * N floats (k_splits > 1)
-  unsigned* counters = nullptr;        // skinny_counter_words(N) zero-initialised words owned by THIS call site (self-cleaning);
-                                       // nullptr: static unit order, k_splits must be 1
-  float* y = nullptr; int ldy = 0;     // SK_STORE: y[row(t)][n] = v; SK_RESID: y[row(t)][n] += v; row(t) = slots ? slots[t] : t
-  const int* slots = nullptr;
-  __nv_bfloat16* act = nullptr;        // SK_GATEUP: act[t][N/2] = bf16(silu(gate) * up), rows interleaved (2i gate, 2i+1 up)
-  QkvEpi qkv;                          // SK_QKV: RoPE + bf16 + q_out[slot][..] + paged KV append (rows rope-pair-interleaved)
-  float* q_out = nullptr; int q_stride = 0;
-  long long* dbg = nullptr;            // diagnostics: 16 globaltimer stamps of CTA 0
-};
-int skinny_splits(int K, int target_kb);
-size_t skinny_counter_words(int N);
-int launch_gemm_skinny(const SkinnyArgs& a, cudaStream_t st, bool pdl);
-
 // ---- batched decode glue (batch_kernels.cu) ------------------------------------------------------
 int launch_batch_resid_norm(float* h, int d, const float* ypart, int n_split, int B, const float* gain, float eps, __nv_bfloat16* xn,
                             const int* slots, cudaStream_t st, bool pdl = false);

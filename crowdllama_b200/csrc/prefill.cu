@@ -313,54 +313,6 @@ int cl_op_gemm_bf16(int device, const uint16_t* x, const uint16_t* w, float* y, 
   return CL_OK;
 }
 
-int cl_op_gemm_skinny(int device, const uint16_t* x, const uint16_t* w, float* y, int32_t t, int32_t n, int32_t k, int32_t target_kb,
-                      int32_t iters, float* ms, int64_t* dbg16) {
-  if (!x || !w || !y || t <= 0 || t > 32 || n <= 0 || k <= 0 || k % 8) return CL_ERR_INVALID_ARG;
-  int rc = check_device(device);
-  if (rc) return rc;
-  // timing runs rotate over enough copies of W that no launch finds its weights in the 126 MB L2
-  const size_t wbytes = (size_t)n * k * 2;
-  const int nrep = iters > 0 ? (int)std::min<size_t>(16, std::max<size_t>(1, ((size_t)512 << 20) / wbytes + 1)) : 1;
-  DevBuf dx, dw, dy, dpart, dcnt, ddbg;
-  CL_CUDA_OK(dx.upload(x, (size_t)t * k * 2));
-  CL_CUDA_OK(dw.alloc(wbytes * nrep));
-  for (int r = 0; r < nrep; ++r) CL_CUDA_OK(cudaMemcpy((uint8_t*)dw.p + wbytes * r, w, wbytes, cudaMemcpyHostToDevice));
-  CL_CUDA_OK(dy.alloc((size_t)t * n * 4));
-  CL_CUDA_OK(cudaMemset(dy.p, 0xff, (size_t)t * n * 4));
-  const int ksp = skinny_splits(k, target_kb);
-  CL_CUDA_OK(dpart.alloc((size_t)ksp * t * n * 4));
-  const size_t words = skinny_counter_words(n);
-  CL_CUDA_OK(dcnt.alloc(words * 4));
-  CL_CUDA_OK(cudaMemset(dcnt.p, 0, words * 4));
-  CL_CUDA_OK(ddbg.alloc(512 * 8));
-  CL_CUDA_OK(cudaMemset(ddbg.p, 0, 512 * 8));
-  SkinnyArgs a;
-  a.X = dx.as<__nv_bfloat16>(); a.W = dw.as<__nv_bfloat16>(); a.T = t; a.N = n; a.K = k; a.k_splits = ksp; a.epi = SK_STORE;
-  a.part = dpart.as<float>(); a.counters = dcnt.as<unsigned>(); a.y = dy.as<float>(); a.ldy = n; a.dbg = ddbg.as<long long>();
-  if (launch_gemm_skinny(a, nullptr, false) < 0) { CL_CUDA_OK(cudaGetLastError()); set_last_error("launch_gemm_skinny failed"); return CL_ERR_CUDA; }
-  CL_CUDA_OK(cudaDeviceSynchronize());
-  CL_CUDA_OK(cudaMemcpy(y, dy.p, (size_t)t * n * 4, cudaMemcpyDeviceToHost));
-  if (iters > 0 && ms) {
-    cudaEvent_t e0, e1;
-    CL_CUDA_OK(cudaEventCreate(&e0));
-    CL_CUDA_OK(cudaEventCreate(&e1));
-    auto run = [&](int i) { a.W = reinterpret_cast<const __nv_bfloat16*>((const uint8_t*)dw.p + wbytes * (i % nrep)); return launch_gemm_skinny(a, nullptr, false); };
-    for (int i = 0; i < 3; ++i) run(i);
-    CL_CUDA_OK(cudaDeviceSynchronize());
-    CL_CUDA_OK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) run(i + 3);
-    CL_CUDA_OK(cudaEventRecord(e1));
-    CL_CUDA_OK(cudaDeviceSynchronize());
-    float tm = 0.f;
-    CL_CUDA_OK(cudaEventElapsedTime(&tm, e0, e1));
-    *ms = tm / (float)iters;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-  }
-  if (dbg16) CL_CUDA_OK(cudaMemcpy(dbg16, ddbg.p, 512 * 8, cudaMemcpyDeviceToHost));
-  return CL_OK;
-}
-
 // variant: -1 auto (tcgen05 kernel when the shape allows, CL_PREFILL_ATTN_TC=0 forces the other), 0 mma.sync kernel, 1 tcgen05 kernel
 static int attn_prefill_impl(int device, const uint16_t* q, const uint16_t* k, const uint16_t* v, int32_t t, int32_t n_heads, int32_t n_kv,
                              int32_t head_dim, int variant, int iters, float* out, float* ms) {

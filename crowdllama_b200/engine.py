@@ -68,7 +68,7 @@ EXPORTS = [
     "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_decode_step_batch", "cl_seq_fake_fill",
     "cl_time_dominant_kernel", "cl_debug_kv", "cl_debug_hidden", "cl_debug_timeline",
     "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_qkv_rope_append", "cl_op_attn_decode",
-    "cl_op_gemm_bf16", "cl_op_gemm_skinny", "cl_op_attn_prefill", "cl_op_attn_prefill_variant", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
+    "cl_op_gemm_bf16", "cl_op_attn_prefill", "cl_op_attn_prefill_variant", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
     "cl_kvpool_reserve", "cl_kvpool_release", "cl_kvpool_pages_of", "cl_kvpool_free_pages", "cl_kvpool_used_pages",
     "cl_tokenizer_load", "cl_tokenizer_free", "cl_tokenizer_encode", "cl_tokenizer_decode", "cl_tokenizer_info", "cl_engine_load_tokenizer",
 ]
@@ -134,7 +134,6 @@ def lib():
         "cl_op_attn_decode": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "cl_op_qkv_rope_append": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, f32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
         "cl_op_gemm_bf16": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, P(f32)]),
-        "cl_op_gemm_skinny": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, P(f32), vp]),
         "cl_op_attn_prefill": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, vp]),
         "cl_op_attn_prefill_variant": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, i32, i32, i32, i32, vp, i32, P(f32)]),
         "cl_op_synth_weights": (C.c_int, [C.c_int, u64, i32, i64, f32, vp]),
@@ -536,20 +535,6 @@ def op_gemm_bf16(x_bf16, w_bf16, iters=0, device=0):
     ms = C.c_float(0)
     _check(lib().cl_op_gemm_bf16(device, _ptr(x), _ptr(w), _ptr(y), x.shape[0], w.shape[0], w.shape[1], iters,
                                  C.byref(ms)), "cl_op_gemm_bf16")
-    return (y, ms.value) if iters else y
-
-
-def op_gemm_skinny(x_bf16, w_bf16, target_kb=4, iters=0, device=0, want_dbg=False):
-    """Batched-decode projection (T <= 32): returns y, or (y, ms) when iters > 0 (weights rotated through > L2-sized copies)."""
-    x = np.ascontiguousarray(x_bf16, dtype=np.uint16)
-    w = np.ascontiguousarray(w_bf16, dtype=np.uint16)
-    y = np.empty((x.shape[0], w.shape[0]), np.float32)
-    ms = C.c_float(0)
-    dbg = np.zeros(512, np.int64)
-    _check(lib().cl_op_gemm_skinny(device, _ptr(x), _ptr(w), _ptr(y), x.shape[0], w.shape[0], w.shape[1], target_kb, iters,
-                                   C.byref(ms), _ptr(dbg)), "cl_op_gemm_skinny")
-    if want_dbg:
-        return y, ms.value, dbg
     return (y, ms.value) if iters else y
 
 

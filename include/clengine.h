@@ -274,12 +274,6 @@ int cl_op_attn_decode(int device, const float* q, const uint16_t* k_cache, const
 /* prefill GEMM on tcgen05: Y[t][n] = sum_k X[t][k] W[n][k]; X,W bf16, Y fp32 */
 int cl_op_gemm_bf16(int device, const uint16_t* x, const uint16_t* w, float* y, int32_t t,
                     int32_t n, int32_t k, int32_t iters, float* ms);
-/* batched-decode projection (gemm_skinny.cu, t <= 32 token columns): split-K units of target_kb k-blocks of 64,
- * dynamic unit scheduling, deterministic last-arriver reduction; plain-store epilogue.  dbg16 (may be NULL)
- * receives 512 int64 globaltimer stamps of the last launch (diagnostics: [0..15] CTA 0 phases, [16+2c] / [17+2c]
- * entry / setup-done of CTA c, [336+c] exit of CTA c). */
-int cl_op_gemm_skinny(int device, const uint16_t* x, const uint16_t* w, float* y, int32_t t, int32_t n, int32_t k,
-                      int32_t target_kb, int32_t iters, float* ms, int64_t* dbg16);
 /* causal prefill attention: q [t][n_heads][d], k,v [t][n_kv][d] bf16 (roped), out bf16-rounded fp32 */
 int cl_op_attn_prefill(int device, const uint16_t* q, const uint16_t* k, const uint16_t* v,
                        int32_t t, int32_t n_heads, int32_t n_kv, int32_t head_dim, float* out);

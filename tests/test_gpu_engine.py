@@ -97,13 +97,11 @@ def _ids_match(ids, ref, margins):
     return k
 
 
-@pytest.mark.parametrize("batch_gemm", ["1", "skinny", "0"])
+@pytest.mark.parametrize("batch_gemm", ["1", "0"])
 def test_batched_decode_matches_single_and_oracle(monkeypatch, batch_gemm):
     """Continuous-batching inner loop: B sequences of different lengths advance together.  CL_BATCH_GEMM=1 is
-    the tensor-core path (tcgen05 split-K projections + glue kernels), "skinny" the fused-epilogue variant
-    (gemm_skinny.cu, CL_BATCH_SKINNY=1), 0 the per-sequence GEMV kernels."""
-    monkeypatch.setenv("CL_BATCH_GEMM", "1" if batch_gemm == "skinny" else batch_gemm)
-    monkeypatch.setenv("CL_BATCH_SKINNY", "1" if batch_gemm == "skinny" else "0")
+    the tensor-core path (tcgen05 split-K projections + glue kernels), 0 the per-sequence GEMV kernels."""
+    monkeypatch.setenv("CL_BATCH_GEMM", batch_gemm)
     monkeypatch.setenv("CL_BATCH_GEMM_MIN", "2")
     cfg = oc.PRESETS["tiny-test"]
     m = oc.Model(cfg, seed=5)
@@ -132,11 +130,8 @@ def test_batched_decode_matches_single_and_oracle(monkeypatch, batch_gemm):
             assert (ids[:, b] == ref).mean() >= 0.9 or margins.min() < MARGIN_TOL
 
 
-@pytest.mark.parametrize("skinny", ["0", "1"])
-def test_batched_decode_llama_shapes(monkeypatch, skinny):
-    """Batched tensor-core step at Llama-3-8B layer shapes (2 layers, split-K 3/4/5/9) vs the oracle, teacher-forced.
-    skinny=1: the fused-epilogue projections of gemm_skinny.cu (dynamic split-K units, owner reduction)."""
-    monkeypatch.setenv("CL_BATCH_SKINNY", skinny)
+def test_batched_decode_llama_shapes():
+    """Batched tensor-core step at Llama-3-8B layer shapes (2 layers, split-K 3/4/5/9) vs the oracle, teacher-forced."""
     cfg = dict(oc.PRESETS["llama3-8b"])
     cfg["n_layers"] = 2
     cfg["max_seq_len"] = 256
