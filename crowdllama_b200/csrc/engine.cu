@@ -329,10 +329,13 @@ int Engine::alloc_state() {
                     max_batch_ <= 32;
   if (use_batch_gemm_) {
     bws_.reset(new BatchWs());
-    const size_t Bm = max_batch_, widest = std::max<size_t>((size_t)qkv_dim_, std::max<size_t>(2 * (size_t)cfg.d_ff, d));
+    const size_t Bm = std::max(max_batch_, 32), widest = std::max<size_t>((size_t)qkv_dim_, std::max<size_t>(2 * (size_t)cfg.d_ff, d));   // 32 rows: the persistent batched kernel's token tile
     DMALLOC(bws_->xn, Bm * d * 2);
     DMALLOC(bws_->attn, Bm * q_dim_ * 2);
     DMALLOC(bws_->act, Bm * (size_t)cfg.d_ff * 2);
+    CL_CUDA_OK(cudaMemsetAsync(bws_->xn, 0, Bm * d * 2, stream_));
+    CL_CUDA_OK(cudaMemsetAsync(bws_->attn, 0, Bm * q_dim_ * 2, stream_));
+    CL_CUDA_OK(cudaMemsetAsync(bws_->act, 0, Bm * (size_t)cfg.d_ff * 2, stream_));
     // split-K partial workspace of the four projections (pick_splits)
     size_t part_floats = 4 * Bm * widest;
     for (int nk : {0, 1, 2, 3}) {
@@ -341,6 +344,32 @@ int Engine::alloc_state() {
     }
     DMALLOC(bws_->part, part_floats * 4);
     DMALLOC(bws_->logits, Bm * (size_t)cfg.vocab_size * 4);
+    // persistent batched step: tensor maps of every weight matrix (device array) and of the three token operands
+    use_batch_mega_ = env_int("CL_BATCH_MEGA", 0) != 0 && cfg.head_dim == 128 && page_size_ == 32 &&
+                      batch_mega_supported(cfg.d_model, cfg.d_ff, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads, page_size_, cfg.vocab_size);
+    if (use_batch_mega_) {
+      std::vector<CUtensorMap> wm((size_t)cfg.n_layers * 4 + 1);
+      std::vector<BatchMegaLayer> bl(cfg.n_layers);
+      bool ok = batch_mega_prepare_device();
+      for (int l = 0; l < cfg.n_layers && ok; ++l) {
+        const auto& L = layers_[l];
+        ok = make_wmap(&wm[(size_t)l * 4 + 0], L.wqkv, qkv_dim_, cfg.d_model) && make_wmap(&wm[(size_t)l * 4 + 1], L.wo, cfg.d_model, q_dim_) &&
+             make_wmap(&wm[(size_t)l * 4 + 2], L.wgu, 2 * cfg.d_ff, cfg.d_model) && make_wmap(&wm[(size_t)l * 4 + 3], L.wdown, cfg.d_model, cfg.d_ff);
+        bl[l] = BatchMegaLayer{L.attn_norm, L.ffn_norm, kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_};
+      }
+      ok = ok && make_wmap(&wm[(size_t)cfg.n_layers * 4], lm_head_, cfg.vocab_size, cfg.d_model) &&
+           make_tmap_2d_bf16(&bm_map_xn_, bws_->xn, 32, cfg.d_model, 64, 32) && make_tmap_2d_bf16(&bm_map_attn_, bws_->attn, 32, q_dim_, 64, 32) &&
+           make_tmap_2d_bf16(&bm_map_act_, bws_->act, 32, cfg.d_ff, 64, 32);
+      if (ok) {
+        DMALLOC(d_bm_wmaps_, wm.size() * sizeof(CUtensorMap));
+        DMALLOC(d_bm_layers_, bl.size() * sizeof(BatchMegaLayer));
+        CL_CUDA_OK(cudaMemcpy(d_bm_wmaps_, wm.data(), wm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        CL_CUDA_OK(cudaMemcpy(d_bm_layers_, bl.data(), bl.size() * sizeof(BatchMegaLayer), cudaMemcpyHostToDevice));
+      } else {
+        fprintf(stderr, "[clengine] persistent batched decode kernel unavailable on this device / shape: using the per-kernel batched step\n");
+        use_batch_mega_ = false;
+      }
+    }
   }
   prompt_cap_ = cfg.max_seq_len;
   DMALLOC(d_prompt_, (size_t)prompt_cap_ * 4);
@@ -389,6 +418,7 @@ int Engine::ensure_capacity(cl_seq_t s, int n_tokens) {
 
 // ---- one token step for the sequences listed in d_slots_[0..B) -----------------------------------
 int Engine::enqueue_step(int B, bool tail) {
+  if (B >= 2 && tail && use_batch_mega_ && have_kv_maps_ && bws_) return enqueue_step_batch_mega(B);
   if (B >= batch_gemm_min_ && tail && use_batch_gemm_ && bws_) return enqueue_step_batched(B);   // B = 2 is faster on the GEMV kernels (measured)
   const int d = cfg.d_model, F = cfg.d_ff, L_ = cfg.n_layers;
   int n = 0, r;
@@ -508,6 +538,33 @@ static int pick_splits(int n_rows, int K) {
   for (int s = 1; s <= 16; ++s)
     if (cost_of[s] >= 0 && cost_of[s] * 10 <= best_cost * 11) return s;
   return 1;
+}
+
+// ---- batched token step as ONE persistent kernel (decode_mega_batch.cu): embed -> kernel (all layers + LM head) -> tail
+int Engine::enqueue_step_batch_mega(int B) {
+  int n = 0, r;
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; } while (0)
+  const int d = cfg.d_model, F = cfg.d_ff, V = cfg.vocab_size;
+  CL_LAUNCH(launch_embed(embed_, d, d_tok_, d_h_, d, d_slots_, B, stream_));
+  BatchMegaArgs m;
+  m.layers = d_bm_layers_; m.wmaps = d_bm_wmaps_; m.n_layers = cfg.n_layers; m.B = B; m.n_kv = cfg.n_kv_heads;
+  m.nsplit = std::max(1, std::min(std::min(nsplit_, 32), sm_count() / (cfg.n_kv_heads * B)));
+  m.q_dim = q_dim_; m.qkv_dim = qkv_dim_; m.vocab = V;
+  m.s_qkv = pick_splits(qkv_dim_, d); m.s_o = pick_splits(d, q_dim_); m.s_gu = pick_splits(2 * F, d); m.s_dn = pick_splits(d, F);
+  m.eps = cfg.rms_eps; m.rope = rope_; m.pos = d_pos_; m.block_tables = d_bt_; m.bt_stride = max_pages_per_seq_; m.slots = d_slots_;
+  m.h = d_h_; m.xn = bws_->xn; m.attn = bws_->attn; m.act = bws_->act; m.part = bws_->part; m.att_part = d_attn_part_; m.att_cnt = d_attn_cnt_;
+  m.logits = d_logits_; m.final_norm = final_norm_; m.bars = d_sync_;
+  m.kv_layer_rows = (long long)n_pages_ * cfg.n_kv_heads * page_size_;
+  m.map_xn = bm_map_xn_; m.map_attn = bm_map_attn_; m.map_act = bm_map_act_; m.kmap = kmap_; m.vmap = vmap_;
+  CL_LAUNCH(launch_decode_mega_batch(m, stream_));
+  StepTailArgs t;
+  t.logits = d_logits_; t.vocab = V; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
+  t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
+  t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = B;
+  t.sync_counters = d_sync_; t.n_sync_counters = n_sync_;
+  CL_LAUNCH(launch_step_tail(t, stream_));
+#undef CL_LAUNCH
+  return n;
 }
 
 int Engine::enqueue_step_batched(int B) {

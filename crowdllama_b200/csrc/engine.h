@@ -237,6 +237,12 @@ class Engine {
   struct BatchWs { __nv_bfloat16* xn = nullptr; __nv_bfloat16* attn = nullptr; __nv_bfloat16* act = nullptr; float* part = nullptr; float* logits = nullptr; };
   std::unique_ptr<BatchWs> bws_;
   bool use_batch_gemm_ = false;
+  // persistent batched step (decode_mega_batch.cu)
+  bool use_batch_mega_ = false;
+  BatchMegaLayer* d_bm_layers_ = nullptr;
+  CUtensorMap* d_bm_wmaps_ = nullptr;
+  CUtensorMap bm_map_xn_{}, bm_map_attn_{}, bm_map_act_{};
+  int enqueue_step_batch_mega(int B);
   int batch_gemm_min_ = 3;
   int prefill_chunk_tokens_ = 4096;
 

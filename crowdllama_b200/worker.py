@@ -23,6 +23,7 @@ from .router import resource_from_engine
 INFERENCE_PROTOCOL = "/crowdllama/inference/1.0.0"     # pkg/crowdllama/types.go:20
 METADATA_PROTOCOL = "/crowdllama/metadata/1.0.0"       # pkg/crowdllama/types.go:16
 STOP_PROTOCOL = "/crowdllama-b200/bench-stop/1.0.0"    # harness only: the load generator tells the worker peers it is done
+STATS_PROTOCOL = "/crowdllama-b200/bench-stats/1.0.0"  # harness only: raw cl_engine_stats as JSON (preemptions, KV pages ...)
 
 
 class _Stream:
@@ -62,6 +63,9 @@ class _Conn(socketserver.BaseRequestHandler):
             s.write(resource_from_engine(srv.peer_id, srv.engine).to_json())
         elif proto == STOP_PROTOCOL:
             srv.stop_event.set()
+        elif proto == STATS_PROTOCOL:
+            import json
+            s.write(json.dumps(srv.engine.stats()).encode())
         elif proto == INFERENCE_PROTOCOL:
             if H.handle_inference_stream(srv.api_handler, s, worker_mode=True):
                 with srv._lock:
