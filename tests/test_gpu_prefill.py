@@ -125,3 +125,37 @@ def test_prefill_paths_agree_on_llama_shapes():
             b = e.prefill(s2, p[i:i + 10])
         assert np.abs(a - b).max() < 0.125
         assert int(a.argmax()) == int(b.argmax()) or np.sort(b)[-1] - np.sort(b)[-2] < 2e-2
+
+
+@pytest.mark.parametrize("t2", [150, 300])
+def test_prefill_continuation_at_an_unaligned_position_llama_shapes(t2):
+    """Multi-turn / chunked prompts: a second prefill appended at a position that is no multiple of the 128-token KV
+    block (pos0 = 105) — the tcgen05 attention's diagonal then cuts through blocks, and keys come from pages written
+    by an earlier prefill and by decode steps.  t2 = 150 takes the short-prompt path, 300 the full-tile path."""
+    cfg = dict(oc.PRESETS["llama3-8b"])
+    cfg["n_layers"] = 2
+    cfg["max_seq_len"] = 512
+    m = oc.Model(cfg, seed=4321)
+    V = cfg["vocab_size"]
+    with eng.Engine(model=cfg, seed=4321, max_batch=1) as e:
+        so = m.new_seq()
+        s = e.seq_create()
+        p1 = _prompt(100, V, salt=1)
+        lo = so.prefill_block(p1)
+        lg = e.prefill(s, p1)
+        assert np.abs(lg - lo).max() < 0.125
+        tok = int(lo.argmax())
+        for _ in range(5):
+            lo = so.forward([tok]); lg, _ = e.decode_step(s, tok)
+            tok = int(lo.argmax())
+        p2 = _prompt(t2, V, salt=9)
+        lo = so.prefill_block(p2)
+        lg = e.prefill(s, p2)
+        err = float(np.abs(lg - lo).max())
+        assert err < 0.125, err
+        tok = int(lo.argmax())
+        for _ in range(4):
+            lo = so.forward([tok]); lg, _ = e.decode_step(s, tok)
+            assert np.abs(lg - lo).max() < 0.125
+            tok = int(lo.argmax())
+        assert e.seq_len(s) == 100 + 5 + t2 + 4
