@@ -178,8 +178,11 @@ int Engine::init(const cl_engine_config& c) {
                           (double)cfg.vocab_size * cfg.d_model;
     tok_per_sec_ewma_ = 0.7 * 6.5e12 / (2.0 * params) * (double)max_batch_;
   }
-  sched_prefill_chunk_ = std::max(16, env_int("CL_SCHED_PREFILL_CHUNK", 1024));
-  prefill_small_max_ = std::min(256, env_int("CL_PREFILL_SMALL_MAX", 256));
+  // defaults of the round-2 features: see kDefault* in engine.h (flipped on once a GPU run has validated them)
+  sched_prefill_chunk_ = env_int("CL_SCHED_PREFILL_CHUNK", kDefaultSchedPrefillChunk);
+  if (sched_prefill_chunk_ > 0 && sched_prefill_chunk_ < 16) sched_prefill_chunk_ = 16;
+  prefill_small_max_ = std::min(256, env_int("CL_PREFILL_SMALL_MAX", kDefaultPrefillSmallMax));
+  prefill_fused_ = env_int("CL_PREFILL_FUSED", kDefaultPrefillFused) != 0;
   if (c.start_scheduler) start_scheduler();
   return CL_OK;
 }
@@ -345,7 +348,7 @@ int Engine::alloc_state() {
     DMALLOC(bws_->part, part_floats * 4);
     DMALLOC(bws_->logits, Bm * (size_t)cfg.vocab_size * 4);
     // persistent batched step: tensor maps of every weight matrix (device array) and of the three token operands
-    use_batch_mega_ = env_int("CL_BATCH_MEGA", 0) != 0 && cfg.head_dim == 128 && page_size_ == 32 &&
+    use_batch_mega_ = env_int("CL_BATCH_MEGA", kDefaultBatchMega) != 0 && cfg.head_dim == 128 && page_size_ == 32 &&
                       batch_mega_supported(cfg.d_model, cfg.d_ff, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads, page_size_, cfg.vocab_size);
     if (use_batch_mega_) {
       std::vector<CUtensorMap> wm((size_t)cfg.n_layers * 4 + 1);

@@ -18,6 +18,13 @@
 
 namespace cl {
 
+// Defaults of the features added in round 2.  Each has an environment switch; the default is turned on only after a GPU run
+// of the parity tests and the benchmark with it (profiles/README.md records the run).
+constexpr int kDefaultSchedPrefillChunk = 0;    // CL_SCHED_PREFILL_CHUNK: admission token budget per scheduler iteration (0 = whole prompts)
+constexpr int kDefaultPrefillSmallMax = 0;      // CL_PREFILL_SMALL_MAX: prompts up to this many tokens take the split-K path (0 = off)
+constexpr int kDefaultPrefillFused = 0;         // CL_PREFILL_FUSED: RoPE / SiLU fused into the prefill GEMM epilogues
+constexpr int kDefaultBatchMega = 0;            // CL_BATCH_MEGA: persistent batched decode kernel for B >= 2
+
 void set_last_error(const std::string& s);
 const char* get_last_error();
 
@@ -233,7 +240,8 @@ class Engine {
   struct SmallPrefillWs { float* part = nullptr; __nv_bfloat16* xn = nullptr; __nv_bfloat16* q = nullptr; __nv_bfloat16* attn = nullptr;
                           float* h = nullptr; __nv_bfloat16* act = nullptr; int* iota = nullptr; };
   std::unique_ptr<SmallPrefillWs> sws_;
-  int prefill_small_max_ = 256;       // prompts up to this many tokens take the split-K path (CL_PREFILL_SMALL_MAX, 0 = off)
+  bool prefill_fused_ = false;        // RoPE + cache scatter / SiLU*mul in the prefill GEMM epilogues (CL_PREFILL_FUSED)
+  int prefill_small_max_ = 0;         // prompts up to this many tokens take the split-K path (CL_PREFILL_SMALL_MAX, 0 = off)
   struct BatchWs { __nv_bfloat16* xn = nullptr; __nv_bfloat16* attn = nullptr; __nv_bfloat16* act = nullptr; float* part = nullptr; float* logits = nullptr; };
   std::unique_ptr<BatchWs> bws_;
   bool use_batch_gemm_ = false;
@@ -270,7 +278,7 @@ class Engine {
   std::deque<std::shared_ptr<Request>> queue_;
   std::vector<std::shared_ptr<Request>> active_;
   std::shared_ptr<Request> prefilling_;   // the one request whose prompt is being prefilled chunk by chunk (scheduler.cpp)
-  int sched_prefill_chunk_ = 1024;        // tokens per admission chunk while other sequences are decoding (CL_SCHED_PREFILL_CHUNK)
+  int sched_prefill_chunk_ = 0;           // admission token budget per iteration while other sequences are decoding (CL_SCHED_PREFILL_CHUNK; 0 = unlimited)
   std::atomic<bool> stop_{false};
   bool sched_started_ = false;
   friend struct Request;

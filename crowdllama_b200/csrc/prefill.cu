@@ -142,7 +142,7 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
     pws_->cap_tokens = (int)T;
   }
   PrefillWs& w = *pws_;
-  static const bool fused = !(getenv("CL_PREFILL_FUSED") && atoi(getenv("CL_PREFILL_FUSED")) == 0);   // 0: separate RoPE / SiLU kernels
+  const bool fused = prefill_fused_;    // CL_PREFILL_FUSED; 0: separate RoPE / SiLU kernels
   CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
   const int* bt = d_bt_ + (size_t)s * max_pages_per_seq_;
   int launches = 0, r;

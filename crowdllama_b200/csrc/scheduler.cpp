@@ -217,7 +217,7 @@ void Engine::scheduler_main() {
     // chunk (a 4096-token prompt used to hold every running request for the whole ~85 ms prefill).
     // Several short prompts may be admitted in one iteration as long as their tokens fit the same budget (a burst of
     // 128-token chats fills the batch in a few iterations instead of one request per decode step).
-    int budget = sched_prefill_chunk_;
+    int budget = sched_prefill_chunk_ > 0 ? sched_prefill_chunk_ : (1 << 30);   // 0: unlimited = whole prompts, as in round 1
     while (budget > 0) {
       if (!prefilling_ && (int)active_.size() < max_batch_) {
         std::shared_ptr<Request> r;

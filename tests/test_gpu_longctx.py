@@ -246,11 +246,13 @@ def test_mistral_7b_full_8k_context():
 
 
 # ---- the 4096-token prefill, checked at every position ---------------------------------------------------------------
-def test_prefill_4096_tokens_matches_oracle_at_every_position():
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_prefill_4096_tokens_matches_oracle_at_every_position(monkeypatch, fused):
     """A 4096-token prompt (one tcgen05 chunk) plus a 300-token continuation (attention over cached pages + the new
     chunk) at Llama-3-8B width, 2 layers, against the oracle's layer-major prefill: last-position logits, and the cached
     K/V of layer 1 at EVERY position — they depend on layer 0's attention output at that position, so the whole causal
     attention matrix is covered.  Then 4 teacher-forced decode steps on top."""
+    monkeypatch.setenv("CL_PREFILL_FUSED", fused)      # 1: RoPE + cache scatter / SiLU in the GEMM epilogues
     cfg = _cfg("llama3-8b", n_layers=2, max_seq_len=4096 + 512)
     m = _Cache.model("pf", cfg, 7)
     T0, T1 = 4096, 300
@@ -290,7 +292,8 @@ def test_prefill_4096_tokens_matches_oracle_at_every_position():
         assert max(errs) < tol
         print(f"prefill 4096+300 @ llama3-8b width x 2 layers: logits err {e0:.4f} / {e1:.4f}, decode after {max(errs):.4f} "
               f"(tolerance {tol:.3f}); layer-1 cache at all {T0 + T1} positions: {stats}")
-        _record("llama3-8b/2L/prefill4096+300", logits_err=[round(e0, 5), round(e1, 5)], decode_err=round(max(errs), 5), tol=round(tol, 4),
+        _record(f"llama3-8b/2L/prefill4096+300/fused{fused}", logits_err=[round(e0, 5), round(e1, 5)], decode_err=round(max(errs), 5), tol=round(tol, 4),
                 kv=stats)
     so.close()
-    _Cache.drop("pf")
+    if fused == "0":
+        _Cache.drop("pf")

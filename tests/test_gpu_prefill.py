@@ -64,12 +64,14 @@ def _prompt(n, vocab, salt=0):
     return np.array([(i * 7919 + 13 + salt) % vocab for i in range(n)], np.int32)
 
 
-@pytest.mark.parametrize("small_max", ["256", "0"])
+@pytest.mark.parametrize("path", ["small", "tiles-fused", "tiles"])
 @pytest.mark.parametrize("n_prompt", [16, 40, 97, 200])
-def test_engine_chunked_prefill_matches_oracle(monkeypatch, n_prompt, small_max):
-    """Both tensor-core prefill paths against the oracle: short prompts (<= 256 tokens) on the split-K projections
-    (prefill_small), and — CL_PREFILL_SMALL_MAX=0 — the same prompts on the full-tile path with its fused epilogues."""
-    monkeypatch.setenv("CL_PREFILL_SMALL_MAX", small_max)
+def test_engine_chunked_prefill_matches_oracle(monkeypatch, n_prompt, path):
+    """The tensor-core prefill paths against the oracle: "small" = short prompts (<= 256 tokens) on split-K projections
+    (prefill_small, CL_PREFILL_SMALL_MAX=256); "tiles-fused" = full tiles with the fused GEMM epilogues
+    (CL_PREFILL_FUSED=1; the tiny model has head_dim 64, so only the SiLU epilogue applies); "tiles" = separate kernels."""
+    monkeypatch.setenv("CL_PREFILL_SMALL_MAX", "256" if path == "small" else "0")
+    monkeypatch.setenv("CL_PREFILL_FUSED", "1" if path == "tiles-fused" else "0")
     cfg = oc.PRESETS["tiny-test"]
     m = oc.Model(cfg, seed=1234)
     with eng.Engine(preset="tiny-test", seed=1234) as e:
@@ -94,10 +96,13 @@ def test_engine_chunked_prefill_matches_oracle(monkeypatch, n_prompt, small_max)
         assert e.seq_len(s) == n_prompt + 8 + 33
 
 
-def test_prefill_paths_agree_on_llama_shapes():
-    """Token-wise (decode kernels), full-tile (tcgen05, fused epilogues) and short-prompt (split-K) prefill of the same
-    prompts give the same logits within tolerance at Llama-3-8B layer shapes (2 layers); the short-prompt path is also
-    compared with the oracle directly."""
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_prefill_paths_agree_on_llama_shapes(monkeypatch, fused):
+    """Token-wise (decode kernels), full-tile (tcgen05; fused = RoPE / SiLU in the GEMM epilogues) and short-prompt
+    (split-K) prefill of the same prompts give the same logits within tolerance at Llama-3-8B layer shapes (2 layers);
+    the short-prompt path is also compared with the oracle directly."""
+    monkeypatch.setenv("CL_PREFILL_SMALL_MAX", "256")
+    monkeypatch.setenv("CL_PREFILL_FUSED", fused)
     cfg = dict(oc.PRESETS["llama3-8b"])
     cfg["n_layers"] = 2
     cfg["max_seq_len"] = 512
@@ -128,10 +133,12 @@ def test_prefill_paths_agree_on_llama_shapes():
 
 
 @pytest.mark.parametrize("t2", [150, 300])
-def test_prefill_continuation_at_an_unaligned_position_llama_shapes(t2):
+def test_prefill_continuation_at_an_unaligned_position_llama_shapes(monkeypatch, t2):
     """Multi-turn / chunked prompts: a second prefill appended at a position that is no multiple of the 128-token KV
     block (pos0 = 105) — the tcgen05 attention's diagonal then cuts through blocks, and keys come from pages written
     by an earlier prefill and by decode steps.  t2 = 150 takes the short-prompt path, 300 the full-tile path."""
+    monkeypatch.setenv("CL_PREFILL_SMALL_MAX", "256")
+    monkeypatch.setenv("CL_PREFILL_FUSED", "1")
     cfg = dict(oc.PRESETS["llama3-8b"])
     cfg["n_layers"] = 2
     cfg["max_seq_len"] = 512
