@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
 
   if (warp == 0) {
     // =============================================== producer ===============================================
-    if (lane != 0) return;
+    if (lane == 0) {
     prefetch_tmap(&a.map_xn); prefetch_tmap(&a.map_attn); prefetch_tmap(&a.map_act); prefetch_tmap(&a.kmap); prefetch_tmap(&a.vmap);
     uint32_t wit = 0, xit = 0, att_n = 0;           // ring items issued; attention units issued (kv_ready phases)
     auto w_acquire = [&]() -> int {
@@ -244,10 +244,8 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
       gemm_items(l, 3);
     }
     gemm_items(a.n_layers, 0);                      // LM head
-    return;
-  }
-
-  if (warp == 1) {
+    }
+  } else if (warp == 1) {
     // =============================================== MMA issuer ===============================================
     uint32_t wit = 0, xit = 0, tn = 0;              // ring items consumed; units issued (accumulator = tn % NACC)
     auto gemm_units = [&](int l, int j) {
