@@ -359,16 +359,23 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
       }
     };
 
+    const bool stamp = a.tl != nullptr && blockIdx.x == 0 && ctid == 0;
+#define CL_STAMP(k) do { if (stamp) a.tl[(size_t)l * 16 + (k)] = gtime_ns(); } while (0)
     for (int l = 0; l < a.n_layers; ++l) {
       const BatchMegaLayer& L = a.layers[l];
       unsigned* bars_l = a.bars + (size_t)l * 8;
       // ------------------------------------------------------------------ R0
       if (l > 0) grid_barrier(a.bars + (size_t)(l - 1) * 8 + 7, ctid);      // previous layer's down partials complete
+      CL_STAMP(15);
       resid_norm(L.attn_norm, l > 0 ? a.s_dn : 0);
+      CL_STAMP(0);
       grid_barrier(bars_l + 0, ctid);
+      CL_STAMP(1);
       // ------------------------------------------------------------------ G0: q|k|v partials
       gemm_epilogue(l, 0);
+      CL_STAMP(2);
       grid_barrier(bars_l + 1, ctid);
+      CL_STAMP(3);
       // ------------------------------------------------------------------ AT
       {
         AttUnit u;
@@ -576,16 +583,24 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
           bar_consumers();                            // qs / red_* / flag_s are reused by the next unit
         }
       }
+      CL_STAMP(4);
       grid_barrier(bars_l + 2, ctid);
+      CL_STAMP(5);
       // ------------------------------------------------------------------ G1: o partials
       gemm_epilogue(l, 1);
+      CL_STAMP(6);
       grid_barrier(bars_l + 3, ctid);
+      CL_STAMP(7);
       // ------------------------------------------------------------------ R1
       resid_norm(L.ffn_norm, a.s_o);
+      CL_STAMP(8);
       grid_barrier(bars_l + 4, ctid);
+      CL_STAMP(9);
       // ------------------------------------------------------------------ G2: gate|up partials
       gemm_epilogue(l, 2);
+      CL_STAMP(10);
       grid_barrier(bars_l + 5, ctid);
+      CL_STAMP(11);
       // ------------------------------------------------------------------ R2: act = bf16(SiLU(g) * u)
       {
         const int total = a.B * F;
@@ -599,15 +614,19 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
           a.act[(size_t)b * F + i] = __float2bfloat16_rn(gt / (1.0f + __expf(-gt)) * up);
         }
       }
+      CL_STAMP(12);
       grid_barrier(bars_l + 6, ctid);
+      CL_STAMP(13);
       // ------------------------------------------------------------------ G3: down partials
       gemm_epilogue(l, 3);
+      CL_STAMP(14);
       // its barrier (bars_l + 7) is taken at the top of the next layer / before the final norm
     }
     grid_barrier(a.bars + (size_t)(a.n_layers - 1) * 8 + 7, ctid);
     resid_norm(a.final_norm, a.s_dn);
     grid_barrier(a.bars + (size_t)a.n_layers * 8, ctid);
     gemm_epilogue(a.n_layers, 0);                     // LM head -> logits[slot][n]
+#undef CL_STAMP
   }
   tc_fence_before();
   __syncthreads();

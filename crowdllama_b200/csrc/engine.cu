@@ -558,6 +558,7 @@ int Engine::enqueue_step_batch_mega(int B) {
   m.h = d_h_; m.xn = bws_->xn; m.attn = bws_->attn; m.act = bws_->act; m.part = bws_->part; m.att_part = d_attn_part_; m.att_cnt = d_attn_cnt_;
   m.logits = d_logits_; m.final_norm = final_norm_; m.bars = d_sync_;
   m.kv_layer_rows = (long long)n_pages_ * cfg.n_kv_heads * page_size_;
+  m.tl = d_timeline_;
   m.map_xn = bm_map_xn_; m.map_attn = bm_map_attn_; m.map_act = bm_map_act_; m.kmap = kmap_; m.vmap = vmap_;
   CL_LAUNCH(launch_decode_mega_batch(m, stream_));
   StepTailArgs t;
@@ -575,7 +576,7 @@ int Engine::enqueue_step_batched(int B) {
   int n = 0, r;
   // CL_STEP_PROFILE=1 (eager launches only, CL_GRAPH=0): a CUDA event after every launch; per-kernel-class device time of
   // the step — gap before the kernel included — goes to stderr
-  static const bool prof_env = env_int("CL_STEP_PROFILE", 0) != 0;
+  const bool prof_env = env_int("CL_STEP_PROFILE", 0) != 0;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(stream_, &cap);
   const bool prof = prof_env && cap == cudaStreamCaptureStatusNone;

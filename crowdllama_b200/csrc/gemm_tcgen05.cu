@@ -159,13 +159,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           tmem_ld_wait();
           if constexpr (EPI == EPI_F32) {
             if (n < p.N) {
+              if (p.accumulate_into_y) {
+                // residual add in place: ALL 32 loads first, then the stores.  (A load-add-store per token serialises
+                // on the load latency — the compiler cannot reorder the next load above a store it cannot prove
+                // disjoint — and made the o / down projections epilogue-bound: 564 us instead of 114 us per launch.)
+                float y[32];
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const int t = t0 + c0 + c;
-                if (t < p.T) {
-                  float* dst = Yb + (size_t)t * p.ldy + n;
-                  const float r = __uint_as_float(v[c]);
-                  *dst = p.accumulate_into_y ? (*dst + r) : r;
+                for (int c = 0; c < 32; ++c) {
+                  const int t = t0 + c0 + c;
+                  y[c] = t < p.T ? __ldcg(Yb + (size_t)t * p.ldy + n) : 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const int t = t0 + c0 + c;
+                  if (t < p.T) Yb[(size_t)t * p.ldy + n] = y[c] + __uint_as_float(v[c]);
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const int t = t0 + c0 + c;
+                  if (t < p.T) Yb[(size_t)t * p.ldy + n] = __uint_as_float(v[c]);
                 }
               }
             }
@@ -188,26 +201,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
             const int head = (n0 + m * BM) >> 7, w = n & 127, j = w >> 1;
             const int dim = (lane & 1) ? j + 64 : j;
             const GemmEpi& e = p.epi;
-#pragma unroll 4
+            const bool rot = head < e.n_heads + e.n_kv, isq = head < e.n_heads;
+            // table entries of the 32 tokens first (independent loads in flight), then rotate / round / store
+            float2 cs[32];
+            int pg[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int t = t0 + c0 + c, pos = e.pos0 + (t < p.T ? t : 0);
+              cs[c] = rot ? __ldg(e.rope + (size_t)pos * 64 + j) : make_float2(1.f, 0.f);
+              pg[c] = isq ? 0 : __ldg(e.block_table + pos / e.page_size);
+            }
+            const int g = rot ? head - e.n_heads : head - e.n_heads - e.n_kv;
+            __nv_bfloat16* pool = rot ? e.kpool : e.vpool;
+#pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float mine = __uint_as_float(v[c]);
               const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
               const int t = t0 + c0 + c;
-              if (t >= p.T || n >= p.N) continue;
-              const int pos = e.pos0 + t;
-              float val = mine;
-              if (head < e.n_heads + e.n_kv) {
-                const float2 cs = __ldg(e.rope + (size_t)pos * 64 + j);
-                // even lane: v0 = mine (dim j), v1 = other -> v0 cos - v1 sin; odd lane: v1 = mine (dim j + 64) -> v1 cos + v0 sin
-                val = (lane & 1) ? mine * cs.x + other * cs.y : mine * cs.x - other * cs.y;
-              }
-              if (head < e.n_heads) {
-                e.q_out[(size_t)t * e.q_dim + head * 128 + dim] = __float2bfloat16_rn(val);
-              } else {
-                const int g = head < e.n_heads + e.n_kv ? head - e.n_heads : head - e.n_heads - e.n_kv;
-                __nv_bfloat16* pool = head < e.n_heads + e.n_kv ? e.kpool : e.vpool;
-                const int page = __ldg(e.block_table + pos / e.page_size), off = pos % e.page_size;
-                pool[(((size_t)page * e.n_kv + g) * e.page_size + off) * 128 + dim] = __float2bfloat16_rn(val);
+              // even lane: v0 = mine (dim j), v1 = other -> v0 cos - v1 sin; odd lane: v1 = mine (dim j + 64) -> v1 cos + v0 sin
+              const float val = (lane & 1) ? mine * cs[c].x + other * cs[c].y : mine * cs[c].x - other * cs[c].y;
+              if (t < p.T && n < p.N) {
+                if (isq) {
+                  e.q_out[(size_t)t * e.q_dim + head * 128 + dim] = __float2bfloat16_rn(val);
+                } else {
+                  const int off = (e.pos0 + t) % e.page_size;
+                  pool[(((size_t)pg[c] * e.n_kv + g) * e.page_size + off) * 128 + dim] = __float2bfloat16_rn(val);
+                }
               }
             }
           }

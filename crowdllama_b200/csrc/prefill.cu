@@ -227,6 +227,7 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
       cudaEventElapsedTime(&ms, pev[i - 1], pev[i]);
       std::string key(pname[i]);
       key = key.substr(0, key.find('('));
+      if (key == "launch_gemm_bf16_epi") key += std::string(pname[i]).find("L.wqkv") != std::string::npos ? ":qkv+rope" : ":gate|up+silu";
       if (key == "launch_gemm_bf16") {   // split by projection: the 3rd argument names the output buffer
         const std::string full(pname[i]);
         key += full.find("L.wqkv") != std::string::npos ? ":qkv" : full.find("L.wo") != std::string::npos ? ":o" : full.find("L.wgu") != std::string::npos ? ":gate|up" : ":down";
