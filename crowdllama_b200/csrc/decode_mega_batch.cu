@@ -56,19 +56,33 @@ struct Proj {                                // one projection of one layer
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // grid-wide barrier among the consumer warps of all CTAs (producer / MMA warps do not take part)
-__device__ __forceinline__ void grid_barrier(unsigned* cnt, int ctid) {
+// pause: while this CTA's consumers sit in the barrier its producer issues no new bulk copy — the barrier's red / poll round
+// trips queue behind bulk traffic in front of the L2 slices (tools/bench_barrier.cu: 1.2 us idle, 3.1 us with 2 x 32 KB in
+// flight per SM, 12 us with 6)
+// pause[1] counts the barriers this CTA has left: its producer waits for "barrier n passed" on that shared-memory word
+// instead of adding 148 more pollers to the global counter.
+__device__ __forceinline__ void grid_barrier(unsigned* cnt, int ctid, volatile int* pause) {
   bar_consumers();
   if (ctid == 0) {
+    pause[0] = 1;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
     const long long t0 = clock64();
     while (ld_acquire_u32(cnt) < gridDim.x) {
       if (clock64() - t0 > (1ll << 31)) __trap();
     }
+    pause[0] = 0;
+    __threadfence_block();
+    pause[1] = pause[1] + 1;
   }
   bar_consumers();
 }
-__device__ __forceinline__ void wait_counter(const unsigned* cnt) {       // one thread: phase published?
+// producer thread: has this CTA's consumer side left its n-th grid barrier (counted in shared memory)?  Then one acquire
+// load of the global counter (already complete) orders the other CTAs' writes before this thread's TMA loads.
+__device__ __forceinline__ void wait_counter(const unsigned* cnt, volatile int* done, int n) {
   const long long t0 = clock64();
+  while (*done < n) {
+    if (clock64() - t0 > (1ll << 31)) __trap();
+  }
   while (ld_acquire_u32(cnt) < gridDim.x) {
     if (clock64() - t0 > (1ll << 31)) __trap();
   }
@@ -116,6 +130,7 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
   float* cL_s = cw_s + MAXS * REP;                           // [REP]
   float* ssw = cL_s + REP;                                   // [NC]
   int* flag_s = reinterpret_cast<int*>(ssw + NC);
+  volatile int* pause_s = flag_s + 1;                        // consumers are inside a grid barrier
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = (int)gridDim.x;
@@ -124,6 +139,7 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
     for (int i = 0; i < NSX; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     mbar_init(kv_ready, 1);
+    pause_s[0] = 0; pause_s[1] = 0;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -164,9 +180,19 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
     if (lane == 0) {
     prefetch_tmap(&a.map_xn); prefetch_tmap(&a.map_attn); prefetch_tmap(&a.map_act); prefetch_tmap(&a.kmap); prefetch_tmap(&a.vmap);
     uint32_t wit = 0, xit = 0, att_n = 0;           // ring items issued; attention units issued (kv_ready phases)
+    uint32_t wtail = 0;                             // oldest ring item not yet known to have landed
+    const int max_flight = a.max_flight > 0 ? a.max_flight : NSW;
+    // a free slot, at most max_flight 16 KB copies in flight (the ring still fills all NSW slots over time), and no new
+    // copy while the consumers are inside a grid barrier
     auto w_acquire = [&]() -> int {
       const int s = (int)(wit % NSW);
       mbar_wait(&w_empty[s], ((wit / NSW) & 1u) ^ 1u);
+      for (uint32_t spins = 0; (int)(wit - wtail) >= max_flight; ++spins) {
+        if (mbar_try_wait(&w_full[wtail % NSW], (wtail / NSW) & 1u)) ++wtail;
+        if (spins > (1u << 24)) __trap();
+      }
+      if (a.pause_in_barrier)
+        for (uint32_t spins = 0; *pause_s; ++spins) if (spins > (1u << 26)) __trap();
       return s;
     };
     auto gemm_items = [&](int l, int j) {
@@ -193,7 +219,7 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
           ++wit; ++primed; ++kb;
         }
       }
-      wait_counter(xready(l, j));
+      wait_counter(xready(l, j), pause_s + 1, l * 8 + 2 * j + 1);
       fence_proxy_async_all();                       // X was written with generic-proxy stores by other CTAs
       int i = 0;
       for (int u = blockIdx.x; u < RT * pr.S; u += G) {
@@ -329,14 +355,24 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
         float4 v[4];
         float ss = 0.f;
 #pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = *reinterpret_cast<const float4*>(hr + (ctid + r * 256) * 4);
+        // partials in groups of 4 splits: 16 independent loads in flight per thread, added in fixed order
+        for (int s0 = 0; s0 < n_split; s0 += 4) {
+          float4 y[4][4];
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              y[s][r] = s0 + s < n_split ? __ldcg(reinterpret_cast<const float4*>(a.part + ((size_t)(s0 + s) * BT + b) * D + (ctid + r * 256) * 4))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { v[r].x += y[s][r].x; v[r].y += y[s][r].y; v[r].z += y[s][r].z; v[r].w += y[s][r].w; }
+        }
+#pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const int i = (ctid + r * 256) * 4;
-          v[r] = *reinterpret_cast<const float4*>(hr + i);
-          for (int s = 0; s < n_split; ++s) {
-            const float4 y = __ldcg(reinterpret_cast<const float4*>(a.part + ((size_t)s * BT + b) * D + i));
-            v[r].x += y.x; v[r].y += y.y; v[r].z += y.z; v[r].w += y.w;
-          }
-          if (n_split > 0) *reinterpret_cast<float4*>(hr + i) = v[r];
+          if (n_split > 0) *reinterpret_cast<float4*>(hr + (ctid + r * 256) * 4) = v[r];
           ss = fmaf(v[r].x, v[r].x, ss); ss = fmaf(v[r].y, v[r].y, ss); ss = fmaf(v[r].z, v[r].z, ss); ss = fmaf(v[r].w, v[r].w, ss);
         }
         ss = warp_sum(ss);
@@ -365,16 +401,16 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
       const BatchMegaLayer& L = a.layers[l];
       unsigned* bars_l = a.bars + (size_t)l * 8;
       // ------------------------------------------------------------------ R0
-      if (l > 0) grid_barrier(a.bars + (size_t)(l - 1) * 8 + 7, ctid);      // previous layer's down partials complete
+      if (l > 0) grid_barrier(a.bars + (size_t)(l - 1) * 8 + 7, ctid, pause_s);      // previous layer's down partials complete
       CL_STAMP(15);
       resid_norm(L.attn_norm, l > 0 ? a.s_dn : 0);
       CL_STAMP(0);
-      grid_barrier(bars_l + 0, ctid);
+      grid_barrier(bars_l + 0, ctid, pause_s);
       CL_STAMP(1);
       // ------------------------------------------------------------------ G0: q|k|v partials
       gemm_epilogue(l, 0);
       CL_STAMP(2);
-      grid_barrier(bars_l + 1, ctid);
+      grid_barrier(bars_l + 1, ctid, pause_s);
       CL_STAMP(3);
       // ------------------------------------------------------------------ AT
       {
@@ -433,9 +469,10 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
           float mrow = -INFINITY, lrow = 0.f;
           const int npg = u.pg1 - u.pg0;
           for (int it = 0; it < npg; ++it, ++wit) {
+            if ((it & (NC - 1)) != cw) continue;     // page -> warp (round robin): only the owner touches (and frees) the slot
             const int s = (int)(wit % NSW);
             mbar_wait(&w_full[s], (wit / NSW) & 1u);
-            if ((it & (NC - 1)) == cw) {             // page -> warp (round robin)
+            {
               const uint32_t kb = smem_u32(wring + (size_t)s * WSLOT), vb = kb + 8192;
               const int tok0 = (u.pg0 + it) * P;
               float sacc[4][4];
@@ -499,8 +536,8 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
                 }
               }
             }
-            bar_consumers();                          // every warp is done with (or skipped) this slot
-            if (ctid == 0) mbar_arrive(&w_empty[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&w_empty[s]);
           }
           lrow += __shfl_xor_sync(0xffffffffu, lrow, 1);
           lrow += __shfl_xor_sync(0xffffffffu, lrow, 2);
@@ -584,22 +621,22 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
         }
       }
       CL_STAMP(4);
-      grid_barrier(bars_l + 2, ctid);
+      grid_barrier(bars_l + 2, ctid, pause_s);
       CL_STAMP(5);
       // ------------------------------------------------------------------ G1: o partials
       gemm_epilogue(l, 1);
       CL_STAMP(6);
-      grid_barrier(bars_l + 3, ctid);
+      grid_barrier(bars_l + 3, ctid, pause_s);
       CL_STAMP(7);
       // ------------------------------------------------------------------ R1
       resid_norm(L.ffn_norm, a.s_o);
       CL_STAMP(8);
-      grid_barrier(bars_l + 4, ctid);
+      grid_barrier(bars_l + 4, ctid, pause_s);
       CL_STAMP(9);
       // ------------------------------------------------------------------ G2: gate|up partials
       gemm_epilogue(l, 2);
       CL_STAMP(10);
-      grid_barrier(bars_l + 5, ctid);
+      grid_barrier(bars_l + 5, ctid, pause_s);
       CL_STAMP(11);
       // ------------------------------------------------------------------ R2: act = bf16(SiLU(g) * u)
       {
@@ -615,16 +652,16 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
         }
       }
       CL_STAMP(12);
-      grid_barrier(bars_l + 6, ctid);
+      grid_barrier(bars_l + 6, ctid, pause_s);
       CL_STAMP(13);
       // ------------------------------------------------------------------ G3: down partials
       gemm_epilogue(l, 3);
       CL_STAMP(14);
       // its barrier (bars_l + 7) is taken at the top of the next layer / before the final norm
     }
-    grid_barrier(a.bars + (size_t)(a.n_layers - 1) * 8 + 7, ctid);
+    grid_barrier(a.bars + (size_t)(a.n_layers - 1) * 8 + 7, ctid, pause_s);
     resid_norm(a.final_norm, a.s_dn);
-    grid_barrier(a.bars + (size_t)a.n_layers * 8, ctid);
+    grid_barrier(a.bars + (size_t)a.n_layers * 8, ctid, pause_s);
     gemm_epilogue(a.n_layers, 0);                     // LM head -> logits[slot][n]
 #undef CL_STAMP
   }
@@ -637,7 +674,7 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
 }
 
 constexpr size_t kSmem = (size_t)NSW * WSLOT + (size_t)NSX * XSLOT + (2 * NSW + 2 * NSX + 2 * NACC + 1) * 8 + 8 +
-                         (2 * NC * REP + NC * REP * HD + REP * HD + 2 * MAXS * REP + REP + NC + 4) * 4 + 1024 + 64;
+                         (2 * NC * REP + NC * REP * HD + REP * HD + 2 * MAXS * REP + REP + NC + 8) * 4 + 1024 + 64;
 
 bool g_ready[64] = {false}, g_ok[64] = {false};
 

@@ -182,7 +182,7 @@ int Engine::init(const cl_engine_config& c) {
   sched_prefill_chunk_ = env_int("CL_SCHED_PREFILL_CHUNK", kDefaultSchedPrefillChunk);
   if (sched_prefill_chunk_ > 0 && sched_prefill_chunk_ < 16) sched_prefill_chunk_ = 16;
   prefill_small_max_ = std::min(256, env_int("CL_PREFILL_SMALL_MAX", kDefaultPrefillSmallMax));
-  prefill_fused_ = env_int("CL_PREFILL_FUSED", kDefaultPrefillFused) != 0;
+  prefill_fused_ = env_int("CL_PREFILL_FUSED", kDefaultPrefillFused);
   if (c.start_scheduler) start_scheduler();
   return CL_OK;
 }
@@ -559,6 +559,7 @@ int Engine::enqueue_step_batch_mega(int B) {
   m.logits = d_logits_; m.final_norm = final_norm_; m.bars = d_sync_;
   m.kv_layer_rows = (long long)n_pages_ * cfg.n_kv_heads * page_size_;
   m.tl = d_timeline_;
+  m.max_flight = env_int("CL_BMEGA_MAX_FLIGHT", 4); m.pause_in_barrier = env_int("CL_BMEGA_PAUSE", 1);
   m.map_xn = bm_map_xn_; m.map_attn = bm_map_attn_; m.map_act = bm_map_act_; m.kmap = kmap_; m.vmap = vmap_;
   CL_LAUNCH(launch_decode_mega_batch(m, stream_));
   StepTailArgs t;

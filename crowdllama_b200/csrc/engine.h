@@ -20,9 +20,9 @@ namespace cl {
 
 // Defaults of the features added in round 2.  Each has an environment switch; the default is turned on only after a GPU run
 // of the parity tests and the benchmark with it (profiles/README.md records the run).
-constexpr int kDefaultSchedPrefillChunk = 0;    // CL_SCHED_PREFILL_CHUNK: admission token budget per scheduler iteration (0 = whole prompts)
-constexpr int kDefaultPrefillSmallMax = 0;      // CL_PREFILL_SMALL_MAX: prompts up to this many tokens take the split-K path (0 = off)
-constexpr int kDefaultPrefillFused = 0;         // CL_PREFILL_FUSED: RoPE / SiLU fused into the prefill GEMM epilogues
+constexpr int kDefaultSchedPrefillChunk = 1024; // CL_SCHED_PREFILL_CHUNK: admission token budget per scheduler iteration (0 = whole prompts); validated r2e
+constexpr int kDefaultPrefillSmallMax = 256;    // CL_PREFILL_SMALL_MAX: prompts up to this many tokens take the split-K path (0 = off); validated r2e (128 tokens: 12.1 -> 6.3 ms)
+constexpr int kDefaultPrefillFused = 0;         // CL_PREFILL_FUSED bit mask: 1 = SiLU*mul, 2 = RoPE + cache scatter fused into the prefill GEMM epilogues
 constexpr int kDefaultBatchMega = 0;            // CL_BATCH_MEGA: persistent batched decode kernel for B >= 2
 
 void set_last_error(const std::string& s);
@@ -240,7 +240,7 @@ class Engine {
   struct SmallPrefillWs { float* part = nullptr; __nv_bfloat16* xn = nullptr; __nv_bfloat16* q = nullptr; __nv_bfloat16* attn = nullptr;
                           float* h = nullptr; __nv_bfloat16* act = nullptr; int* iota = nullptr; };
   std::unique_ptr<SmallPrefillWs> sws_;
-  bool prefill_fused_ = false;        // RoPE + cache scatter / SiLU*mul in the prefill GEMM epilogues (CL_PREFILL_FUSED)
+  int prefill_fused_ = 0;             // bit 0: SiLU*mul, bit 1: RoPE + cache scatter in the prefill GEMM epilogues (CL_PREFILL_FUSED)
   int prefill_small_max_ = 0;         // prompts up to this many tokens take the split-K path (CL_PREFILL_SMALL_MAX, 0 = off)
   struct BatchWs { __nv_bfloat16* xn = nullptr; __nv_bfloat16* attn = nullptr; __nv_bfloat16* act = nullptr; float* part = nullptr; float* logits = nullptr; };
   std::unique_ptr<BatchWs> bws_;

@@ -184,15 +184,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
             }
           } else if constexpr (EPI == EPI_SILU) {
             // rows are interleaved (2i = gate_i, 2i+1 = up_i): the lane pair (2j, 2j+1) holds one SwiGLU input pair per
-            // token; the even lane writes act[t][i] — 16 lanes x bf16 = one full 32-byte sector per token and warp
-            const int i = n >> 1;
+            // token.  Two tokens per iteration so that EVERY lane does useful work: the even lane finishes token c (it
+            // owns g, receives u), the odd lane token c + 1 (owns u, receives g) — one shuffle, one SiLU, one store per
+            // lane and pair of tokens; per token the 16 lanes of one parity write 16 consecutive bf16 = a full 32-byte
+            // sector.  (One token per iteration with the odd lanes idle made this epilogue longer than the tile's MMAs.)
+            const int i = n >> 1, odd = lane & 1;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float mine = __uint_as_float(v[c]);
-              const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-              const int t = t0 + c0 + c;
-              if (!(lane & 1) && n < p.N && t < p.T)
-                p.epi.act[(size_t)t * p.epi.ld_act + i] = __float2bfloat16_rn(mine / (1.0f + __expf(-mine)) * other);
+            for (int c = 0; c < 32; c += 2) {
+              const float a0 = __uint_as_float(v[c]), a1 = __uint_as_float(v[c + 1]);
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);   // odd sends u[c], even sends g[c + 1]
+              const float gt = odd ? recv : a0, up = odd ? a1 : recv;
+              const int t = t0 + c0 + c + odd;
+              if (n < p.N && t < p.T)
+                p.epi.act[(size_t)t * p.epi.ld_act + i] = __float2bfloat16_rn(__fdividef(gt, 1.0f + __expf(-gt)) * up);
             }
           } else {
             // q|k|v rows are rope-pair-interleaved per head (row 2j = dim j, row 2j+1 = dim j + 64; BM = head_dim = 128, so

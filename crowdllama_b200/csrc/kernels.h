@@ -185,6 +185,8 @@ struct BatchMegaArgs {
   const float* final_norm = nullptr;
   unsigned* bars = nullptr;                // [n_layers * 8 + 1] grid-barrier counters, zero at kernel start
   long long kv_layer_rows = 0;
+  int max_flight = 4;                      // 16 KB bulk copies in flight per CTA (<= ring slots); 0 = no cap
+  int pause_in_barrier = 1;                // no new copy while this CTA's consumers sit in a grid barrier
   long long* tl = nullptr;                 // debug (CL_TIMELINE=1): [n_layers][16] globaltimer stamps of CTA 0 at phase ends / barrier exits
   alignas(64) CUtensorMap map_xn;          // [32][d] box {64, 32}
   alignas(64) CUtensorMap map_attn;

@@ -142,7 +142,7 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
     pws_->cap_tokens = (int)T;
   }
   PrefillWs& w = *pws_;
-  const bool fused = prefill_fused_;    // CL_PREFILL_FUSED; 0: separate RoPE / SiLU kernels
+  const bool fused_silu = (prefill_fused_ & 1) != 0, fused_rope = (prefill_fused_ & 2) != 0;   // CL_PREFILL_FUSED bit mask
   CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
   const int* bt = d_bt_ + (size_t)s * max_pages_per_seq_;
   int launches = 0, r;
@@ -168,7 +168,7 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
     for (int l = 0; l < cfg.n_layers; ++l) {
       const auto& L = layers_[l];
       CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.attn_norm, cfg.rms_eps, w.xn, T, d, stream_));
-      if (fused && cfg.head_dim == 128) {   // RoPE + bf16 + q / paged-cache scatter in the GEMM epilogue
+      if (fused_rope && cfg.head_dim == 128) {   // RoPE + bf16 + q / paged-cache scatter in the GEMM epilogue
         GemmEpi eq;
         eq.kind = 2; eq.rope = rope_; eq.pos0 = pos0; eq.q_out = w.q; eq.q_dim = q_dim_;
         eq.kpool = kpool_ + (size_t)l * kv_layer_elems_; eq.vpool = vpool_ + (size_t)l * kv_layer_elems_;
@@ -188,7 +188,7 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
         CL_LAUNCH(launch_attn_prefill(aa, stream_));
       CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.h, w.h, T, d, q_dim_, stream_));
       CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.ffn_norm, cfg.rms_eps, w.xn, T, d, stream_));
-      if (fused) {                          // SiLU(g) * u -> bf16 in the GEMM epilogue
+      if (fused_silu) {                     // SiLU(g) * u -> bf16 in the GEMM epilogue
         GemmEpi eg;
         eg.kind = 1; eg.act = w.act; eg.ld_act = F;
         CL_LAUNCH(launch_gemm_bf16_epi(w.xn, L.wgu, T, 2 * F, d, eg, stream_));

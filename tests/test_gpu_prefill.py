@@ -71,7 +71,7 @@ def test_engine_chunked_prefill_matches_oracle(monkeypatch, n_prompt, path):
     (prefill_small, CL_PREFILL_SMALL_MAX=256); "tiles-fused" = full tiles with the fused GEMM epilogues
     (CL_PREFILL_FUSED=1; the tiny model has head_dim 64, so only the SiLU epilogue applies); "tiles" = separate kernels."""
     monkeypatch.setenv("CL_PREFILL_SMALL_MAX", "256" if path == "small" else "0")
-    monkeypatch.setenv("CL_PREFILL_FUSED", "1" if path == "tiles-fused" else "0")
+    monkeypatch.setenv("CL_PREFILL_FUSED", "3" if path == "tiles-fused" else "0")
     cfg = oc.PRESETS["tiny-test"]
     m = oc.Model(cfg, seed=1234)
     with eng.Engine(preset="tiny-test", seed=1234) as e:
@@ -96,7 +96,7 @@ def test_engine_chunked_prefill_matches_oracle(monkeypatch, n_prompt, path):
         assert e.seq_len(s) == n_prompt + 8 + 33
 
 
-@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("fused", ["3", "0"])
 def test_prefill_paths_agree_on_llama_shapes(monkeypatch, fused):
     """Token-wise (decode kernels), full-tile (tcgen05; fused = RoPE / SiLU in the GEMM epilogues) and short-prompt
     (split-K) prefill of the same prompts give the same logits within tolerance at Llama-3-8B layer shapes (2 layers);
@@ -138,7 +138,7 @@ def test_prefill_continuation_at_an_unaligned_position_llama_shapes(monkeypatch,
     block (pos0 = 105) — the tcgen05 attention's diagonal then cuts through blocks, and keys come from pages written
     by an earlier prefill and by decode steps.  t2 = 150 takes the short-prompt path, 300 the full-tile path."""
     monkeypatch.setenv("CL_PREFILL_SMALL_MAX", "256")
-    monkeypatch.setenv("CL_PREFILL_FUSED", "1")
+    monkeypatch.setenv("CL_PREFILL_FUSED", "3")
     cfg = dict(oc.PRESETS["llama3-8b"])
     cfg["n_layers"] = 2
     cfg["max_seq_len"] = 512
