@@ -339,6 +339,7 @@ def run_ours(args):
     lg = e.prefill(s, ids)
     prefill_ms_first = (time.time() - t0) * 1e3
     first = int(lg.argmax())
+    time.sleep(1.0)   # let the board's power state settle after the prefill burst (r2h: sw_power_cap right after a 58 ms prefill cost 1.7 %)
     # ---- warm-up decode steps (also captures the CUDA graph)
     wids, _ = e.decode_greedy(s, first, W)
     nxt = int(wids[-1])

@@ -2,7 +2,8 @@
 // persistent kernel: the continuous-batching inner loop of the worker (scheduler.cpp) without ~10 kernel launches per
 // layer.  Same idea as decode_mega.cu (B = 1), with the projections on the 5th-gen tensor cores:
 //
-//   grid = one CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = tcgen05 MMA issuer, warps 2-9 = consumers
+//   grid = one CTA per SM, 352 threads: warp 0 = TMA producer of W / KV tiles, warp 10 = TMA producer of the token operand,
+//   warp 1 = tcgen05 MMA issuer, warps 2-9 = consumers
 //   (GEMM epilogues: TMEM -> fp32 split-K partials; paged tensor-core attention; per-token reductions).
 //   Projections are Y[n][b] = sum_k W[n][k] X[b][k] with W tile [128 rows x 64 k] = UMMA A (16 KB, 2-D TMA, 128B
 //   swizzle), the B <= 32 token columns [32 x 64 k] = UMMA B (4 KB), accumulators [128 lanes x 32 columns] in TMEM.
@@ -107,7 +108,7 @@ __device__ __forceinline__ bool att_unit(const BatchMegaArgs& a, int u, AttUnit*
   return true;
 }
 
-__global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_constant__ BatchMegaArgs a) {
+__global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_constant__ BatchMegaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wring = base;                                            // [NSW][16 KB]
@@ -179,63 +180,40 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
     // =============================================== producer ===============================================
     if (lane == 0) {
     prefetch_tmap(&a.map_xn); prefetch_tmap(&a.map_attn); prefetch_tmap(&a.map_act); prefetch_tmap(&a.kmap); prefetch_tmap(&a.vmap);
-    uint32_t wit = 0, xit = 0, att_n = 0;           // ring items issued; attention units issued (kv_ready phases)
+    uint32_t wit = 0, att_n = 0;                    // ring items issued; attention units issued (kv_ready phases)
     uint32_t wtail = 0;                             // oldest ring item not yet known to have landed
+    long long c_empty = 0, c_flight = 0, c_kv = 0;   // diagnostics: cycles blocked (CL_TIMELINE)
+    const long long c_start = clock64();
     const int max_flight = a.max_flight > 0 ? a.max_flight : NSW;
     // a free slot, at most max_flight 16 KB copies in flight (the ring still fills all NSW slots over time), and no new
     // copy while the consumers are inside a grid barrier
     auto w_acquire = [&]() -> int {
       const int s = (int)(wit % NSW);
+      long long t0 = clock64();
       mbar_wait(&w_empty[s], ((wit / NSW) & 1u) ^ 1u);
+      long long t1 = clock64();
+      c_empty += t1 - t0;
       for (uint32_t spins = 0; (int)(wit - wtail) >= max_flight; ++spins) {
         if (mbar_try_wait(&w_full[wtail % NSW], (wtail / NSW) & 1u)) ++wtail;
         if (spins > (1u << 24)) __trap();
       }
       if (a.pause_in_barrier)
         for (uint32_t spins = 0; *pause_s; ++spins) if (spins > (1u << 26)) __trap();
+      c_flight += clock64() - t1;
       return s;
     };
+    // W k-blocks of this CTA's units of projection j of layer l, in unit order.  No dependency on activations: the
+    // weight stream runs ahead of the phases by the depth of the ring (the token operand has its own producer, warp 10).
     auto gemm_items = [&](int l, int j) {
       const Proj pr = proj(l, j);
       const int RT = (pr.N + BM - 1) / BM, nkb = pr.K / BK, kbp = (nkb + pr.S - 1) / pr.S;
-      const CUtensorMap* xm = xmap(l, j);
-      // this CTA's k-blocks of the phase, in unit order
-      int total = 0;
-      for (int u = blockIdx.x; u < RT * pr.S; u += G) { const int ks = u / RT; total += min(nkb, (ks + 1) * kbp) - ks * kbp; }
-      // prime: weights first (no dependency), as many k-blocks as the ring takes without blocking on consumers that
-      // are themselves waiting for this phase's X tiles
-      int primed = 0;
-      {
-        int u = blockIdx.x, kb = -1, kb1 = 0, rt = 0;
-        while (primed < total && primed < NSW) {
-          if (kb < 0 || kb >= kb1) {
-            if (kb >= 0) u += G;
-            const int ks = u / RT;
-            rt = u % RT; kb = ks * kbp; kb1 = min(nkb, (ks + 1) * kbp);
-          }
+      for (int u = blockIdx.x; u < RT * pr.S; u += G) {
+        const int ks = u / RT, rt = u % RT;
+        for (int kb = ks * kbp; kb < min(nkb, (ks + 1) * kbp); ++kb) {
           const int s = w_acquire();
           mbar_arrive_expect_tx(&w_full[s], WSLOT);
           tma_load_2d(wring + (size_t)s * WSLOT, pr.wmap, kb * BK, rt * BM, &w_full[s]);
-          ++wit; ++primed; ++kb;
-        }
-      }
-      wait_counter(xready(l, j), pause_s + 1, l * 8 + 2 * j + 1);
-      fence_proxy_async_all();                       // X was written with generic-proxy stores by other CTAs
-      int i = 0;
-      for (int u = blockIdx.x; u < RT * pr.S; u += G) {
-        const int ks = u / RT, rt = u % RT;
-        for (int kb = ks * kbp; kb < min(nkb, (ks + 1) * kbp); ++kb, ++i) {
-          if (i >= primed) {
-            const int s = w_acquire();
-            mbar_arrive_expect_tx(&w_full[s], WSLOT);
-            tma_load_2d(wring + (size_t)s * WSLOT, pr.wmap, kb * BK, rt * BM, &w_full[s]);
-            ++wit;
-          }
-          const int xs = (int)(xit % NSX);
-          mbar_wait(&x_empty[xs], ((xit / NSX) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&x_full[xs], XSLOT);
-          tma_load_2d(xring + (size_t)xs * XSLOT, xm, kb * BK, 0, &x_full[xs]);
-          ++xit;
+          ++wit;
         }
       }
     };
@@ -249,7 +227,9 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
         for (int pg = u.pg0; pg < u.pg1; ++pg) {
           const int s = w_acquire();
           if (pg == cur) {                          // this page receives the current token's K/V from THIS unit's prologue
+            const long long t0 = clock64();
             mbar_wait(kv_ready, att_n & 1u);
+            c_kv += clock64() - t0;
             fence_proxy_async_all();
           }
           const long long row = (long long)l * a.kv_layer_rows + ((long long)bt[pg] * a.n_kv + u.g) * P;
@@ -270,10 +250,47 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
       gemm_items(l, 3);
     }
     gemm_items(a.n_layers, 0);                      // LM head
+    if (a.tl != nullptr && blockIdx.x == 0) {
+      long long* dbg = a.tl + (size_t)a.n_layers * 16;
+      dbg[0] = clock64() - c_start; dbg[1] = c_empty; dbg[2] = c_flight; dbg[5] = c_kv;
+    }
+    }
+  } else if (warp == 10) {
+    // =============================================== X producer ===============================================
+    // token-operand tiles [32 x 64 k] (4 KB, L2-resident) of every GEMM k-block, gated only by the grid barrier that
+    // publishes the operand
+    if (lane == 0) {
+      uint32_t xit = 0;
+      long long c_xempty = 0, c_phase = 0;
+      auto x_items = [&](int l, int j) {
+        const Proj pr = proj(l, j);
+        const int RT = (pr.N + BM - 1) / BM, nkb = pr.K / BK, kbp = (nkb + pr.S - 1) / pr.S;
+        const CUtensorMap* xm = xmap(l, j);
+        { const long long t0 = clock64(); wait_counter(xready(l, j), pause_s + 1, l * 8 + 2 * j + 1); c_phase += clock64() - t0; }
+        fence_proxy_async_all();                     // X was written with generic-proxy stores by other CTAs
+        for (int u = blockIdx.x; u < RT * pr.S; u += G) {
+          const int ks = u / RT;
+          for (int kb = ks * kbp; kb < min(nkb, (ks + 1) * kbp); ++kb) {
+            const int xs = (int)(xit % NSX);
+            { const long long t0 = clock64(); mbar_wait(&x_empty[xs], ((xit / NSX) & 1u) ^ 1u); c_xempty += clock64() - t0; }
+            mbar_arrive_expect_tx(&x_full[xs], XSLOT);
+            tma_load_2d(xring + (size_t)xs * XSLOT, xm, kb * BK, 0, &x_full[xs]);
+            ++xit;
+          }
+        }
+      };
+      for (int l = 0; l < a.n_layers; ++l)
+        for (int j = 0; j < 4; ++j) x_items(l, j);
+      x_items(a.n_layers, 0);
+      if (a.tl != nullptr && blockIdx.x == 0) {
+        long long* dbg = a.tl + (size_t)a.n_layers * 16;
+        dbg[3] = c_xempty; dbg[4] = c_phase;
+      }
     }
   } else if (warp == 1) {
     // =============================================== MMA issuer ===============================================
     uint32_t wit = 0, xit = 0, tn = 0;              // ring items consumed; units issued (accumulator = tn % NACC)
+    long long m_w = 0, m_x = 0, m_t = 0;            // diagnostics: cycles blocked on W tiles / X tiles / a free accumulator
     auto gemm_units = [&](int l, int j) {
       const Proj pr = proj(l, j);
       const int RT = (pr.N + BM - 1) / BM, nkb = pr.K / BK, kbp = (nkb + pr.S - 1) / pr.S;
@@ -281,13 +298,16 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
         const int ks = u / RT;
         const int nk = min(nkb, (ks + 1) * kbp) - ks * kbp;
         const int acc = (int)(tn % NACC);
-        mbar_wait(&t_empty[acc], ((tn / NACC) & 1u) ^ 1u);
+        { const long long t0 = clock64(); mbar_wait(&t_empty[acc], ((tn / NACC) & 1u) ^ 1u); m_t += clock64() - t0; }
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)(acc * BT);
         for (int kb = 0; kb < nk; ++kb) {
           const int s = (int)(wit % NSW), xs = (int)(xit % NSX);
+          const long long t0 = clock64();
           mbar_wait(&w_full[s], (wit / NSW) & 1u);
+          const long long t1 = clock64();
           mbar_wait(&x_full[xs], (xit / NSX) & 1u);
+          m_w += t1 - t0; m_x += clock64() - t1;
           tc_fence_after();
           if (lane == 0) {
             const uint64_t adesc = make_smem_desc(smem_u32(wring + (size_t)s * WSLOT));
@@ -311,7 +331,11 @@ __global__ void __launch_bounds__(320, 1) decode_mega_batch_kernel(const __grid_
       gemm_units(l, 3);
     }
     gemm_units(a.n_layers, 0);
-  } else {
+    if (a.tl != nullptr && blockIdx.x == 0 && lane == 0) {
+      long long* dbg = a.tl + (size_t)a.n_layers * 16 + 8;
+      dbg[0] = m_w; dbg[1] = m_x; dbg[2] = m_t;
+    }
+  } else if (warp >= 2 && warp < 2 + NC) {
     // =============================================== consumers ===============================================
     const int cw = warp - 2, ctid = cw * 32 + lane;          // consumer warp 0..7, consumer thread 0..255
     uint32_t wit = 0, tn = 0, att_n = 0;
@@ -692,7 +716,7 @@ bool batch_mega_prepare_device() {
     g_ready[dev] = true;
     int nb = 0;
     g_ok[dev] = cudaFuncSetAttribute(decode_mega_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) == cudaSuccess &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_mega_batch_kernel, 320, kSmem) == cudaSuccess && nb >= 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_mega_batch_kernel, 352, kSmem) == cudaSuccess && nb >= 1;
     if (!g_ok[dev]) cudaGetLastError();
   }
   return g_ok[dev];
@@ -704,7 +728,7 @@ bool make_wmap(CUtensorMap* map, const void* W, int N, int K) { return make_tmap
 int launch_decode_mega_batch(const BatchMegaArgs& a, cudaStream_t st) {
   if (!batch_mega_prepare_device() || a.B < 1 || a.B > BT || a.nsplit < 1 || a.nsplit > MAXS) return -1;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(sm_count()); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = kSmem; cfg.stream = st;
+  cfg.gridDim = dim3(sm_count()); cfg.blockDim = dim3(352); cfg.dynamicSmemBytes = kSmem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeCooperative;        // all CTAs co-resident (grid barriers), or the launch fails
   at[0].val.cooperative = 1;

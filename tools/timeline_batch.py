@@ -21,7 +21,12 @@ with eng.Engine(preset="llama3-8b", seed=1234, max_batch=B) as e:
     e.decode_greedy_batch(seqs, [17 + b for b in range(B)], 4)
     _, ms = e.decode_greedy_batch(seqs, [17 + b for b in range(B)], 8)
     L = e.cfg["n_layers"]
-    tl = e.debug_timeline().reshape(-1)[: L * 16].reshape(L, 16).astype(np.float64) / 1e3       # us
+    raw = e.debug_timeline().reshape(-1)
+    tl = raw[: L * 16].reshape(L, 16).astype(np.float64) / 1e3       # us
+    dbg = raw[L * 16: L * 16 + 16].astype(np.float64) / 1965.0       # cycles -> us at 1965 MHz
+    print(f"CTA 0 producer (whole step, us): total {dbg[0]:.0f}, blocked on: free slot {dbg[1]:.0f}, flight cap / pause {dbg[2]:.0f}, "
+          f"X slot {dbg[3]:.0f}, phase publication {dbg[4]:.0f}, kv_ready {dbg[5]:.0f};  MMA warp blocked on: W tile {dbg[8]:.0f}, X tile {dbg[9]:.0f}, "
+          f"accumulator {dbg[10]:.0f}")
     names = ["R0 resid+norm", "barrier A", "G0 q|k|v epilogue done", "barrier B", "AT attention", "barrier C", "G1 o", "barrier D", "R1 resid+norm",
              "barrier E", "G2 gate|up", "barrier F", "R2 silu", "barrier G", "G3 down"]
     order = [15, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
