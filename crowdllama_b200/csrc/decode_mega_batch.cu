@@ -21,7 +21,7 @@
 //   AT  attention unit (b, kv head, split): q / k / v from the partials (+RoPE, K/V append into the paged cache),
 //       mma.sync m16n8k16 over TMA-swizzled pages (P = hi + lo bf16), the last split to finish combines -> bf16 attn_b
 //   G1  o partials   R1  h_b += ..., xn_b = norm   G2  gate|up partials   R2  act = bf16(SiLU(g) u)   G3  down partials
-// then the final norm and the LM head (one unit per 128 logits rows, epilogue writes logits[slot][n]).
+// then the final norm; the LM head follows as a separate tcgen05 GEMM launch (gemm_tcgen05.cu).
 // Built for the Llama-3-8B / Mistral-7B layer shape (d 4096, d_ff 14336, head_dim 128, 4 q heads per kv head, page 32).
 #include <cuda.h>
 
@@ -39,9 +39,9 @@ using namespace tc;
 
 constexpr int D = 4096, F = 14336, HD = 128, REP = 4, P = 32, HALF = HD / 2;
 constexpr int BT = 32;                       // token columns (UMMA N)
-constexpr int NSW = 10;                      // W / KV ring slots of 16 KB
+constexpr int NSW = 6;                       // W / KV ring slots of 16 KB (at most max_flight of them in flight)
 constexpr uint32_t WSLOT = 16384;
-constexpr int NSX = 8;                       // X ring slots of 4 KB
+constexpr int NSX = 25;                      // resident X tiles of 4 KB: the k range of one split (<= 25 k-blocks)
 constexpr uint32_t XSLOT = 4096;
 constexpr int NACC = 4;                      // TMEM accumulator sets of 32 columns
 constexpr int NC = 8;                        // consumer warps
@@ -108,17 +108,33 @@ __device__ __forceinline__ bool att_unit(const BatchMegaArgs& a, int u, AttUnit*
   return true;
 }
 
+// GEMM work of one projection: (row tile, k split) units.  A CTA keeps ONE split for the whole phase (ks = blockIdx.x mod S),
+// so the token operand of that split (<= 25 tiles of [32 x 64 k]) is loaded once and stays resident in shared memory for
+// all of the CTA's row tiles; row tiles go round-robin over the CTAs that share the split.
+struct GemmPlan { int RT, nkb, kbp, ks, kb0, nk, m, M; };
+__device__ __forceinline__ GemmPlan gemm_plan(const Proj& pr) {
+  GemmPlan g;
+  g.RT = (pr.N + BM - 1) / BM;
+  g.nkb = pr.K / BK;
+  g.kbp = (g.nkb + pr.S - 1) / pr.S;
+  g.ks = (int)blockIdx.x % pr.S;
+  g.m = (int)blockIdx.x / pr.S;
+  g.M = ((int)gridDim.x - g.ks + pr.S - 1) / pr.S;                 // CTAs that work on split ks
+  g.kb0 = g.ks * g.kbp;
+  g.nk = max(0, min(g.nkb, g.kb0 + g.kbp) - g.kb0);
+  return g;
+}
+
 __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_constant__ BatchMegaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wring = base;                                            // [NSW][16 KB]
-  uint8_t* xring = base + (size_t)NSW * WSLOT;                      // [NSX][4 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xring + (size_t)NSX * XSLOT);
+  uint8_t* xres = base + (size_t)NSW * WSLOT;                       // [NSX][4 KB] resident token operand of this CTA's split
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xres + (size_t)NSX * XSLOT);
   uint64_t* w_full = bars;                   // [NSW]
   uint64_t* w_empty = w_full + NSW;          // [NSW]
-  uint64_t* x_full = w_empty + NSW;          // [NSX]
-  uint64_t* x_empty = x_full + NSX;          // [NSX]
-  uint64_t* t_full = x_empty + NSX;          // [NACC]
+  uint64_t* x_full = w_empty + NSW;          // [NSX]  tile i of this GEMM phase's token operand has landed
+  uint64_t* t_full = x_full + NSX;           // [NACC]
   uint64_t* t_empty = t_full + NACC;         // [NACC]
   uint64_t* kv_ready = t_empty + NACC;       // [1]  consumers -> producer: the current token's K/V rows are in the cache
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_ready + 1);
@@ -137,7 +153,7 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
   const int G = (int)gridDim.x;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < NSX; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < NSX; ++i) mbar_init(&x_full[i], 1);
     for (int i = 0; i < NACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     mbar_init(kv_ready, 1);
     pause_s[0] = 0; pause_s[1] = 0;
@@ -206,16 +222,14 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
     // weight stream runs ahead of the phases by the depth of the ring (the token operand has its own producer, warp 10).
     auto gemm_items = [&](int l, int j) {
       const Proj pr = proj(l, j);
-      const int RT = (pr.N + BM - 1) / BM, nkb = pr.K / BK, kbp = (nkb + pr.S - 1) / pr.S;
-      for (int u = blockIdx.x; u < RT * pr.S; u += G) {
-        const int ks = u / RT, rt = u % RT;
-        for (int kb = ks * kbp; kb < min(nkb, (ks + 1) * kbp); ++kb) {
+      const GemmPlan g = gemm_plan(pr);
+      for (int rt = g.m; rt < g.RT && g.nk > 0; rt += g.M)
+        for (int kb = g.kb0; kb < g.kb0 + g.nk; ++kb) {
           const int s = w_acquire();
           mbar_arrive_expect_tx(&w_full[s], WSLOT);
           tma_load_2d(wring + (size_t)s * WSLOT, pr.wmap, kb * BK, rt * BM, &w_full[s]);
           ++wit;
         }
-      }
     };
     for (int l = 0; l < a.n_layers; ++l) {
       gemm_items(l, 0);
@@ -249,7 +263,6 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
       gemm_items(l, 2);
       gemm_items(l, 3);
     }
-    gemm_items(a.n_layers, 0);                      // LM head
     if (a.tl != nullptr && blockIdx.x == 0) {
       long long* dbg = a.tl + (size_t)a.n_layers * 16;
       dbg[0] = clock64() - c_start; dbg[1] = c_empty; dbg[2] = c_flight; dbg[5] = c_kv;
@@ -260,28 +273,28 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
     // token-operand tiles [32 x 64 k] (4 KB, L2-resident) of every GEMM k-block, gated only by the grid barrier that
     // publishes the operand
     if (lane == 0) {
-      uint32_t xit = 0;
+      uint32_t gp = 0;                             // GEMM phases so far: every x_full barrier completes once per phase
       long long c_xempty = 0, c_phase = 0;
       auto x_items = [&](int l, int j) {
         const Proj pr = proj(l, j);
-        const int RT = (pr.N + BM - 1) / BM, nkb = pr.K / BK, kbp = (nkb + pr.S - 1) / pr.S;
+        const GemmPlan g = gemm_plan(pr);
         const CUtensorMap* xm = xmap(l, j);
         { const long long t0 = clock64(); wait_counter(xready(l, j), pause_s + 1, l * 8 + 2 * j + 1); c_phase += clock64() - t0; }
         fence_proxy_async_all();                     // X was written with generic-proxy stores by other CTAs
-        for (int u = blockIdx.x; u < RT * pr.S; u += G) {
-          const int ks = u / RT;
-          for (int kb = ks * kbp; kb < min(nkb, (ks + 1) * kbp); ++kb) {
-            const int xs = (int)(xit % NSX);
-            { const long long t0 = clock64(); mbar_wait(&x_empty[xs], ((xit / NSX) & 1u) ^ 1u); c_xempty += clock64() - t0; }
-            mbar_arrive_expect_tx(&x_full[xs], XSLOT);
-            tma_load_2d(xring + (size_t)xs * XSLOT, xm, kb * BK, 0, &x_full[xs]);
-            ++xit;
+        // The previous phase's MMAs are long complete: this operand only exists after grid barriers that follow them.
+        const bool work = g.m < g.RT && g.nk > 0;
+        for (int i = 0; i < NSX; ++i) {
+          if (work && i < g.nk) {
+            mbar_arrive_expect_tx(&x_full[i], XSLOT);
+            tma_load_2d(xres + (size_t)i * XSLOT, xm, (g.kb0 + i) * BK, 0, &x_full[i]);
+          } else {
+            mbar_arrive(&x_full[i]);                 // unused tile: complete the phase so that parities stay aligned
           }
         }
+        ++gp;
       };
       for (int l = 0; l < a.n_layers; ++l)
         for (int j = 0; j < 4; ++j) x_items(l, j);
-      x_items(a.n_layers, 0);
       if (a.tl != nullptr && blockIdx.x == 0) {
         long long* dbg = a.tl + (size_t)a.n_layers * 16;
         dbg[3] = c_xempty; dbg[4] = c_phase;
@@ -289,39 +302,39 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
     }
   } else if (warp == 1) {
     // =============================================== MMA issuer ===============================================
-    uint32_t wit = 0, xit = 0, tn = 0;              // ring items consumed; units issued (accumulator = tn % NACC)
+    uint32_t wit = 0, gp = 0, tn = 0;               // ring items consumed; GEMM phases; units issued (accumulator = tn % NACC)
     long long m_w = 0, m_x = 0, m_t = 0;            // diagnostics: cycles blocked on W tiles / X tiles / a free accumulator
     auto gemm_units = [&](int l, int j) {
       const Proj pr = proj(l, j);
-      const int RT = (pr.N + BM - 1) / BM, nkb = pr.K / BK, kbp = (nkb + pr.S - 1) / pr.S;
-      for (int u = blockIdx.x; u < RT * pr.S; u += G, ++tn) {
-        const int ks = u / RT;
-        const int nk = min(nkb, (ks + 1) * kbp) - ks * kbp;
+      const GemmPlan g = gemm_plan(pr);
+      bool first = true;                            // the X tiles are waited for once, by the phase's first unit
+      for (int rt = g.m; rt < g.RT && g.nk > 0; rt += g.M, ++tn) {
         const int acc = (int)(tn % NACC);
         { const long long t0 = clock64(); mbar_wait(&t_empty[acc], ((tn / NACC) & 1u) ^ 1u); m_t += clock64() - t0; }
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)(acc * BT);
-        for (int kb = 0; kb < nk; ++kb) {
-          const int s = (int)(wit % NSW), xs = (int)(xit % NSX);
+        for (int kb = 0; kb < g.nk; ++kb) {
+          const int s = (int)(wit % NSW);
           const long long t0 = clock64();
           mbar_wait(&w_full[s], (wit / NSW) & 1u);
           const long long t1 = clock64();
-          mbar_wait(&x_full[xs], (xit / NSX) & 1u);
+          if (first) mbar_wait(&x_full[kb], gp & 1u);
           m_w += t1 - t0; m_x += clock64() - t1;
           tc_fence_after();
           if (lane == 0) {
             const uint64_t adesc = make_smem_desc(smem_u32(wring + (size_t)s * WSLOT));
-            const uint64_t bdesc = make_smem_desc(smem_u32(xring + (size_t)xs * XSLOT));
+            const uint64_t bdesc = make_smem_desc(smem_u32(xres + (size_t)kb * XSLOT));
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) umma_f16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
             umma_commit(&w_empty[s]);
-            umma_commit(&x_empty[xs]);
-            if (kb == nk - 1) umma_commit(&t_full[acc]);
+            if (kb == g.nk - 1) umma_commit(&t_full[acc]);
           }
           __syncwarp();
-          ++wit; ++xit;
+          ++wit;
         }
+        first = false;
       }
+      ++gp;
     };
     for (int l = 0; l < a.n_layers; ++l) {
       gemm_units(l, 0);
@@ -330,7 +343,6 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
       gemm_units(l, 2);
       gemm_units(l, 3);
     }
-    gemm_units(a.n_layers, 0);
     if (a.tl != nullptr && blockIdx.x == 0 && lane == 0) {
       long long* dbg = a.tl + (size_t)a.n_layers * 16 + 8;
       dbg[0] = m_w; dbg[1] = m_x; dbg[2] = m_t;
@@ -342,10 +354,9 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
     // ---- split-K epilogue: warps 2-5 own the TMEM lane quarters (warp % 4); partial[ks][b][n] fp32
     auto gemm_epilogue = [&](int l, int j) {
       const Proj pr = proj(l, j);
-      const int RT = (pr.N + BM - 1) / BM, nkb = pr.K / BK, kbp = (nkb + pr.S - 1) / pr.S;
-      for (int u = blockIdx.x; u < RT * pr.S; u += G, ++tn) {
-        const int ks = u / RT, rt = u % RT;
-        wit += (uint32_t)(min(nkb, (ks + 1) * kbp) - ks * kbp);
+      const GemmPlan g = gemm_plan(pr);
+      for (int rt = g.m; rt < g.RT && g.nk > 0; rt += g.M, ++tn) {
+        wit += (uint32_t)g.nk;
         if (cw >= 4) continue;
         const int acc = (int)(tn % NACC);
         mbar_wait(&t_full[acc], (tn / NACC) & 1u);
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
             for (int b = 0; b < BT; ++b)
               if (b < a.B) a.logits[(size_t)a.slots[b] * a.vocab + n] = __uint_as_float(v[b]);
           } else {
-            float* dst = a.part + (size_t)ks * BT * pr.N + n;
+            float* dst = a.part + (size_t)g.ks * BT * pr.N + n;
 #pragma unroll
             for (int b = 0; b < BT; ++b)
               if (b < a.B) dst[(size_t)b * pr.N] = __uint_as_float(v[b]);
@@ -684,9 +695,8 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
       // its barrier (bars_l + 7) is taken at the top of the next layer / before the final norm
     }
     grid_barrier(a.bars + (size_t)(a.n_layers - 1) * 8 + 7, ctid, pause_s);
-    resid_norm(a.final_norm, a.s_dn);
-    grid_barrier(a.bars + (size_t)a.n_layers * 8, ctid, pause_s);
-    gemm_epilogue(a.n_layers, 0);                     // LM head -> logits[slot][n]
+    resid_norm(a.final_norm, a.s_dn);                 // xn = final norm: the LM head (K = 64 k-blocks, more than the resident
+                                                      // operand holds) runs as a plain tcgen05 GEMM launch after this kernel
 #undef CL_STAMP
   }
   tc_fence_before();
@@ -697,7 +707,7 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
   }
 }
 
-constexpr size_t kSmem = (size_t)NSW * WSLOT + (size_t)NSX * XSLOT + (2 * NSW + 2 * NSX + 2 * NACC + 1) * 8 + 8 +
+constexpr size_t kSmem = (size_t)NSW * WSLOT + (size_t)NSX * XSLOT + (2 * NSW + NSX + 2 * NACC + 1) * 8 + 8 +
                          (2 * NC * REP + NC * REP * HD + REP * HD + 2 * MAXS * REP + REP + NC + 8) * 4 + 1024 + 64;
 
 bool g_ready[64] = {false}, g_ok[64] = {false};

@@ -351,6 +351,11 @@ int Engine::alloc_state() {
     use_batch_mega_ = env_int("CL_BATCH_MEGA", kDefaultBatchMega) != 0 && cfg.head_dim == 128 && page_size_ == 32 &&
                       batch_mega_supported(cfg.d_model, cfg.d_ff, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads, page_size_, cfg.vocab_size);
     if (use_batch_mega_) {
+      auto kbp = [&](int N, int K) { const int nkb = K / 64, sp = pick_splits(N, K); return (nkb + sp - 1) / sp; };
+      if (kbp(qkv_dim_, cfg.d_model) > 25 || kbp(cfg.d_model, q_dim_) > 25 || kbp(2 * cfg.d_ff, cfg.d_model) > 25 || kbp(cfg.d_model, cfg.d_ff) > 25)
+        use_batch_mega_ = false;   // a split's token operand must fit the kernel's 25 resident tiles
+    }
+    if (use_batch_mega_) {
       std::vector<CUtensorMap> wm((size_t)cfg.n_layers * 4 + 1);
       std::vector<BatchMegaLayer> bl(cfg.n_layers);
       bool ok = batch_mega_prepare_device();
@@ -562,6 +567,8 @@ int Engine::enqueue_step_batch_mega(int B) {
   m.max_flight = env_int("CL_BMEGA_MAX_FLIGHT", 4); m.pause_in_barrier = env_int("CL_BMEGA_PAUSE", 1);
   m.map_xn = bm_map_xn_; m.map_attn = bm_map_attn_; m.map_act = bm_map_act_; m.kmap = kmap_; m.vmap = vmap_;
   CL_LAUNCH(launch_decode_mega_batch(m, stream_));
+  CL_LAUNCH(launch_gemm_bf16(bws_->xn, lm_head_, bws_->logits, nullptr, B, V, d, stream_, 1, false));
+  CL_LAUNCH(launch_batch_scatter_rows(bws_->logits, V, d_logits_, V, d_slots_, B, stream_));
   StepTailArgs t;
   t.logits = d_logits_; t.vocab = V; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
   t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
