@@ -338,7 +338,9 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
     };
     for (int l = 0; l < a.n_layers; ++l) {
       gemm_units(l, 0);
-      wit += (uint32_t)att_pages;                   // the attention pages pass through the same ring: skip them
+      // the attention pages pass through the same ring: observe their barriers in order (never skip a phase of a slot
+      // — see the attention loop), without touching the data
+      for (int i = 0; i < att_pages; ++i, ++wit) mbar_wait(&w_full[wit % NSW], (wit / NSW) & 1u);
       gemm_units(l, 1);
       gemm_units(l, 2);
       gemm_units(l, 3);
@@ -504,9 +506,12 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
           float mrow = -INFINITY, lrow = 0.f;
           const int npg = u.pg1 - u.pg0;
           for (int it = 0; it < npg; ++it, ++wit) {
-            if ((it & (NC - 1)) != cw) continue;     // page -> warp (round robin): only the owner touches (and frees) the slot
+            // EVERY warp observes every page's barrier in ring order (a waiter that skipped a phase of the same slot
+            // would see "parity differs" for a page that has not landed: mbarrier waits are only safe one phase at a
+            // time); only the owner warp (round robin) touches the data and frees the slot
             const int s = (int)(wit % NSW);
             mbar_wait(&w_full[s], (wit / NSW) & 1u);
+            if ((it & (NC - 1)) != cw) continue;
             {
               const uint32_t kb = smem_u32(wring + (size_t)s * WSLOT), vb = kb + 8192;
               const int tok0 = (u.pg0 + it) * P;
