@@ -334,6 +334,9 @@ __global__ void __launch_bounds__(352, 1) decode_mega_batch_kernel(const __grid_
         }
         first = false;
       }
+      // observe EVERY x_full barrier in EVERY phase (tiles beyond this split's range, or all of them when this CTA has no
+      // unit in the phase): a warp that skipped a phase of a barrier would pass its next wait on stale parity
+      for (int i = first ? 0 : g.nk; i < NSX; ++i) mbar_wait(&x_full[i], gp & 1u);
       ++gp;
     };
     for (int l = 0; l < a.n_layers; ++l) {
