@@ -168,15 +168,19 @@ int Engine::init(const cl_engine_config& c) {
   }
   CL_CUDA_OK(cudaStreamSynchronize(stream_));
   {
-    // Advertised throughput = CAPACITY: decode steps per second x max_batch, i.e. what this worker delivers with a
-    // full batch at its current step time.  (Advertising the achieved tokens/s instead made FindBestWorker's
-    // score T/(1+L) a positive feedback: the busy worker's T grows with its batch, idle workers keep a
-    // single-stream T, and one worker of four took all 256 requests — profiles/README.md.)  Before anything has
-    // been measured: a model-based estimate (70 % of the HBM roofline of one decode step); FindBestWorker
-    // (manager.go:369-377) never selects a worker whose score is 0.
+    // Advertised throughput = CAPACITY, and load-INDEPENDENT: what this worker can deliver with a full batch, estimated
+    // from the device's memory bandwidth and the model's bytes per token (70 % of the HBM roofline of one decode step x
+    // max_batch).  Round 1 advertised the measured decode steps/s x max_batch; a step at B = 32 takes 1.6x as long as at
+    // B = 1, so busy workers advertised LESS than idle ones, crossed a half-octave bucket, and FindBestWorker's strict
+    // maximum (manager.go:369-377) sent every request of a refresh interval to one idle worker (8 peers, r2k: 96 of 192
+    // requests on one worker).  Identical GPUs now advertise identical numbers and tie, which is what the reference's
+    // constants (peer.go:319-343) did; the measured rate stays available as cl_stats.measured_tokens_per_sec.
     const double params = (double)cfg.n_layers * ((double)qkv_dim_ * cfg.d_model + (double)cfg.d_model * q_dim_ + 3.0 * cfg.d_ff * cfg.d_model) +
                           (double)cfg.vocab_size * cfg.d_model;
-    tok_per_sec_ewma_ = 0.7 * 6.5e12 / (2.0 * params) * (double)max_batch_;
+    double bw = 2.0 * (double)prop.memoryClockRate * 1e3 * (double)prop.memoryBusWidth / 8.0;   // bytes/s (DDR)
+    if (!(bw > 1e11)) bw = 6.5e12;
+    capacity_tok_per_sec_ = 0.7 * bw / (2.0 * params) * (double)max_batch_;
+    tok_per_sec_ewma_ = 0.0;
   }
   // defaults of the round-2 features: see kDefault* in engine.h (flipped on once a GPU run has validated them)
   sched_prefill_chunk_ = env_int("CL_SCHED_PREFILL_CHUNK", kDefaultSchedPrefillChunk);
@@ -982,7 +986,8 @@ int Engine::debug_hidden(float* out, int n) {
 
 int Engine::stats(cl_stats* out) {
   memset(out, 0, sizeof *out);
-  out->tokens_per_sec = tok_per_sec_ewma_;
+  out->tokens_per_sec = capacity_tok_per_sec_;
+  out->measured_tokens_per_sec = tok_per_sec_ewma_;
   int active = 0;
   for (auto& s : seqs_) active += s.live ? 1 : 0;
   out->active_seqs = active;

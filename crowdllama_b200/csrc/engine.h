@@ -267,7 +267,8 @@ class Engine {
 
   // stats
   std::atomic<int64_t> launches_{0}, tokens_generated_{0}, requests_completed_{0}, preemptions_{0};
-  double tok_per_sec_ewma_ = 0.0;
+  double tok_per_sec_ewma_ = 0.0;          // measured: EWMA of decode steps/s x max_batch (diagnostic)
+  double capacity_tok_per_sec_ = 0.0;      // advertised: load-independent capacity estimate (engine.cu init)
   char gpu_name_[64] = {0};
   int vram_gb_ = 0;
 

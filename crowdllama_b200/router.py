@@ -38,10 +38,13 @@ class Resource:
 
 
 def advertised_throughput(tokens_per_sec: float) -> float:
-    """Quantise the measured capacity to half-octave buckets.  FindBestWorker compares scores with a strict '>' and
+    """Quantise the engine's capacity figure to half-octave buckets.  FindBestWorker compares scores with a strict '>' and
     breaks exact ties at random (Go map order, manager.go:369-377); the reference's workers all advertise the constant
-    150, so identical machines tie and share the load.  Raw measured EWMAs never tie: between two metadata refreshes
-    every request would go to the one worker whose EWMA happens to be 1 % higher."""
+    150, so identical machines tie and share the load.  cl_stats.tokens_per_sec is a load-independent estimate (device
+    memory bandwidth / model bytes x max_batch) for the same reason: a MEASURED rate drops as the batch fills (a step
+    at B = 32 takes 1.6x a step at B = 1), so busy workers would advertise less than idle ones and one idle worker
+    would win every request until the next refresh (8 peers: 96 of 192 requests on one worker).  The bucket keeps
+    small differences between boards of one model (memory clock bins) from breaking the tie."""
     if tokens_per_sec <= 0:
         return 0.0
     import math

@@ -173,10 +173,12 @@ func (e *Engine) HandleStream(ctx context.Context, req *llamav1.BaseMessage, emi
 	return emitErr
 }
 
-// AdvertisedThroughput quantises the measured capacity to half-octave buckets, AdvertisedLoad to two levels — the
-// same rule as crowdllama_b200/router.py (advertised_throughput / advertised_load) and INTEGRATION.md "What to
+// AdvertisedThroughput quantises the engine's capacity figure to half-octave buckets, AdvertisedLoad to two levels —
+// the same rule as crowdllama_b200/router.py (advertised_throughput / advertised_load) and INTEGRATION.md "What to
 // advertise": FindBestWorker (pkg/peermanager/manager.go:338-387) takes a strict maximum over metadata that is
-// 10-30 s old, so raw numbers send every request to one worker between two refreshes.
+// 10-30 s old, so numbers that move with the load send every request to one worker between two refreshes.
+// cl_stats.tokens_per_sec is already load-independent (memory bandwidth / model bytes x max_batch); the measured rate
+// is cl_stats.measured_tokens_per_sec and must NOT be advertised.
 func AdvertisedThroughput(tokensPerSec float64) float64 {
 	if tokensPerSec <= 0 {
 		return 0

@@ -114,7 +114,8 @@ typedef struct cl_result {
 } cl_result;
 
 typedef struct cl_stats {
-  double tokens_per_sec;     /* capacity: EWMA of decode steps/s x max_batch -> Resource.TokensThroughput (types.go:33) */
+  double tokens_per_sec;     /* capacity, load-independent: 70 % of the HBM roofline of one decode step x max_batch, from the
+                                device's memory bandwidth and the model's bytes per token -> Resource.TokensThroughput (types.go:33) */
   double load;               /* (active + queued) / max_batch, capped at 1 -> Resource.Load (types.go:35) */
   int32_t queue_depth;
   int32_t active_seqs;
@@ -126,6 +127,7 @@ typedef struct cl_stats {
   int32_t vram_gb;           /* -> Resource.VRAMGB */
   char gpu_model[64];        /* -> Resource.GPUModel */
   int64_t kernel_launches;   /* kernels of this library launched so far (graph nodes counted) */
+  double measured_tokens_per_sec; /* EWMA of decode steps/s x max_batch at the CURRENT batch sizes (diagnostic; not for routing) */
 } cl_stats;
 
 typedef struct cl_engine cl_engine;
