@@ -226,7 +226,7 @@ def run_box_client(args):
     from crowdllama_b200.worker import STOP_PROTOCOL
     addrs = [("127.0.0.1", args.base_port + i) for i in range(args.workers)]
     out = {"workers": args.workers, "gen_tokens": BOX_GEN, "max_batch_per_worker": BOX_MAX_BATCH, "router": "find_best_worker (manager.go:338-387), "
-           "metadata refreshed every 2 s, capacity in half-octave buckets + two-level load (router.py)"}
+           "metadata refreshed every 2 s, load-independent capacity in half-octave buckets + two-level load (router.py)"}
     try:
         for a in addrs:
             if not _wait_port(a, 600):
@@ -270,7 +270,8 @@ def run_box_client(args):
             return {"concurrency": concurrency, "requests": n_req, "ok": ok, "errors": errs[:3], "wall_s": round(dt, 3),
                     "req_per_s": round(ok / dt, 3), "tok_per_s": round(ok * BOX_GEN / dt, 1),
                     "p50_latency_s": round(float(np.median(lat)), 3) if lat else None,
-                    "per_worker_requests": dict(sorted(gw.counts.items()))}
+                    "per_worker_requests": dict(sorted(gw.counts.items())),
+                    "advertised_at_end": {r.peer_id: [r.tokens_throughput, r.load] for r in sorted(gw.table.peers.values(), key=lambda r: r.peer_id)}}
         out["config4"] = scenario(64, 192)                                   # BASELINE.json configs[3]: 64 concurrent chats
         out["saturated"] = scenario(BOX_MAX_BATCH * args.workers, 3 * BOX_MAX_BATCH * args.workers)
         gw.shutdown()
