@@ -223,7 +223,7 @@ def run_box_client(args):
     """Gateway stand-in + closed-loop HTTP clients against already running worker peers.  Prints one JSON object."""
     import urllib.request
     from crowdllama_b200 import gateway
-    from crowdllama_b200.worker import STOP_PROTOCOL
+    from crowdllama_b200.worker import STOP_PROTOCOL, STATS_PROTOCOL
     addrs = [("127.0.0.1", args.base_port + i) for i in range(args.workers)]
     out = {"workers": args.workers, "gen_tokens": BOX_GEN, "max_batch_per_worker": BOX_MAX_BATCH, "router": "find_best_worker (manager.go:338-387), "
            "metadata refreshed every 2 s, load-independent capacity in half-octave buckets + two-level load (router.py)"}
@@ -240,8 +240,20 @@ def run_box_client(args):
             [t.start() for t in th]
             [t.join() for t in th]
 
+        def worker_stats():
+            res = []
+            for a in addrs:
+                with socket.create_connection(a, timeout=5) as sk:
+                    sk.sendall((STATS_PROTOCOL + "\n").encode())
+                    data = b""
+                    while chunk := sk.recv(65536):
+                        data += chunk
+                res.append(json.loads(data))
+            return res
+
         def scenario(concurrency, n_req):
             lat, errs = [], []
+            st0 = worker_stats()
 
             def one(i):
                 body = json.dumps({"model": MODEL_NAME, "messages": [{"role": "user", "content": f"{i:04d} {prompt}"}], "stream": False}).encode()
@@ -267,13 +279,32 @@ def run_box_client(args):
                 th.join()
             dt = time.time() - t0
             ok = len(lat)
-            return {"concurrency": concurrency, "requests": n_req, "ok": ok, "errors": errs[:3], "wall_s": round(dt, 3),
+            st1 = worker_stats()
+            acc = {k: sum(b.get(k, 0) - a.get(k, 0) for a, b in zip(st0, st1)) for k in ("tokens_generated", "requests_completed", "preemptions", "sched_decode_steps",
+                                                                            "sched_decode_ns", "sched_prefill_calls", "sched_prefill_tokens", "sched_prefill_ns")}
+            sched = {"mean_batch": round(acc["tokens_generated"] / max(acc["sched_decode_steps"], 1), 2),
+                     "decode_ms_per_step": round(acc["sched_decode_ns"] / max(acc["sched_decode_steps"], 1) * 1e-6, 3),
+                     "prefill_ms_per_call": round(acc["sched_prefill_ns"] / max(acc["sched_prefill_calls"], 1) * 1e-6, 3),
+                     "prefill_tokens_per_call": round(acc["sched_prefill_tokens"] / max(acc["sched_prefill_calls"], 1), 1),
+                     "decode_s_per_worker": round(acc["sched_decode_ns"] * 1e-9 / len(addrs), 3),
+                     "prefill_s_per_worker": round(acc["sched_prefill_ns"] * 1e-9 / len(addrs), 3), "preemptions": acc["preemptions"]}
+            return {"scheduler": sched, "concurrency": concurrency, "requests": n_req, "ok": ok, "errors": errs[:3], "wall_s": round(dt, 3),
                     "req_per_s": round(ok / dt, 3), "tok_per_s": round(ok * BOX_GEN / dt, 1),
                     "p50_latency_s": round(float(np.median(lat)), 3) if lat else None,
                     "per_worker_requests": dict(sorted(gw.counts.items())),
                     "advertised_at_end": {r.peer_id: [r.tokens_throughput, r.load] for r in sorted(gw.table.peers.values(), key=lambda r: r.peer_id)}}
-        out["config4"] = scenario(64, 192)                                   # BASELINE.json configs[3]: 64 concurrent chats
-        out["saturated"] = scenario(BOX_MAX_BATCH * args.workers, 3 * BOX_MAX_BATCH * args.workers)
+        # BASELINE.json configs[3]: 64 concurrent chats.  Long enough for request-level statistics: >= 6 waves per worker slot.
+        # untimed warm-up THROUGH the gateway (the first scenario otherwise pays for cold HTTP / thread / routing paths and
+        # starts desynchronised: 21.2 req/s first against 25.0 for the same scenario run later, r2o)
+        out["warmup"] = {k: v for k, v in scenario(BOX_MAX_BATCH * args.workers, 2 * BOX_MAX_BATCH * args.workers).items() if k in ("requests", "ok", "wall_s")}
+        for i, tag in enumerate(os.environ.get("CL_BOX_SCENARIOS", "config4,saturated").split(",")):   # the default is the contract
+            key = tag if tag not in out else f"{tag}#{i}"
+            if tag == "config4":
+                out[key] = scenario(64, max(192, 96 * args.workers))
+            elif tag == "saturated":
+                out[key] = scenario(BOX_MAX_BATCH * args.workers, 6 * BOX_MAX_BATCH * args.workers)
+            elif tag.startswith("c"):                                         # c<concurrency>: diagnostics
+                out[key] = scenario(int(tag[1:]), 6 * BOX_MAX_BATCH * args.workers)
         gw.shutdown()
     except Exception as ex:  # noqa: BLE001
         out["error"] = repr(ex)

@@ -181,7 +181,9 @@ class Engine {
   int ensure_capacity(cl_seq_t s, int n_tokens);  // reserve pages + upload block table row
   int enqueue_step(int B, bool tail);              // kernels of one token step for d_slots_[0..B)
   int enqueue_step_batched(int B);                 // B >= 2: tcgen05 projections + per-sequence glue kernels
-  int run_step_graph(int B);                       // graph launch (or eager enqueue)
+  int run_step_graph(int B);
+  bool ensure_graph(int B);
+  void precapture_graphs();                       // graph launch (or eager enqueue)
   int read_logits(int slot, float* out);
   int prefill_tokenwise(cl_seq_t s, const int32_t* ids, int n, float* logits_out);
   int prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits_out);  // tcgen05 path (prefill.cu)
@@ -267,6 +269,8 @@ class Engine {
 
   // stats
   std::atomic<int64_t> launches_{0}, tokens_generated_{0}, requests_completed_{0}, preemptions_{0};
+  // scheduler accounting (cl_stats.sched_*): where the scheduler thread's time goes
+  std::atomic<int64_t> sched_decode_steps_{0}, sched_decode_ns_{0}, sched_prefill_calls_{0}, sched_prefill_tokens_{0}, sched_prefill_ns_{0};
   double tok_per_sec_ewma_ = 0.0;          // measured: EWMA of decode steps/s x max_batch (diagnostic)
   double capacity_tok_per_sec_ = 0.0;      // advertised: load-independent capacity estimate (engine.cu init)
   char gpu_name_[64] = {0};

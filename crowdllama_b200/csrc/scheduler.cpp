@@ -205,6 +205,10 @@ void Engine::scheduler_main() {
   std::vector<int32_t> toks(max_seqs_);
   std::vector<int> slots;
   std::vector<int> last_slots;
+  {
+    std::lock_guard<std::mutex> elk(mu_);
+    precapture_graphs();   // every batch size's step graph up front, not inside the first steps that meet it
+  }
   while (true) {
     {
       std::unique_lock<std::mutex> lk(q_mu_);
@@ -259,7 +263,9 @@ void Engine::scheduler_main() {
       const bool last = chunk == left;
       const int64_t t0 = now_ns();
       const int rc = prefill(r->seq, r->full.data() + r->prefilled, (int)chunk, last ? logits.data() : nullptr);
-      r->prefill_ns += now_ns() - t0;
+      const int64_t pdt = now_ns() - t0;
+      r->prefill_ns += pdt;
+      sched_prefill_calls_++; sched_prefill_tokens_ += (int64_t)chunk; sched_prefill_ns_ += pdt;
       slots_dirty_ = true;                // prefill rewrote d_slots_[0]
       budget -= (int)std::min(chunk, (size_t)budget);
       if (rc) { seq_free(r->seq); r->seq = -1; prefilling_.reset(); complete(r, rc, get_last_error()); continue; }
@@ -361,6 +367,7 @@ void Engine::scheduler_main() {
     const int64_t dt = now_ns() - t0;
     for (auto& r : active_) r->decode_ns += dt;
     tokens_generated_ += B;
+    sched_decode_steps_++; sched_decode_ns_ += dt;
     const double tps = (double)max_batch_ / ((double)dt * 1e-9);   // capacity at the current step time (engine.cu, init)
     tok_per_sec_ewma_ = tok_per_sec_ewma_ == 0.0 ? tps : 0.9 * tok_per_sec_ewma_ + 0.1 * tps;
     // ---- retire finished requests

@@ -57,7 +57,8 @@ class Stats(C.Structure):
                 ("active_seqs", C.c_int32), ("kv_pages_total", C.c_int32), ("kv_pages_used", C.c_int32),
                 ("tokens_generated", C.c_int64), ("requests_completed", C.c_int64), ("preemptions", C.c_int64),
                 ("vram_gb", C.c_int32), ("gpu_model", C.c_char * 64), ("kernel_launches", C.c_int64),
-                ("measured_tokens_per_sec", C.c_double)]
+                ("measured_tokens_per_sec", C.c_double), ("sched_decode_steps", C.c_int64), ("sched_decode_ns", C.c_int64),
+                ("sched_prefill_calls", C.c_int64), ("sched_prefill_tokens", C.c_int64), ("sched_prefill_ns", C.c_int64)]
 
 
 # every symbol include/clengine.h declares (tests check the library exports all of them)

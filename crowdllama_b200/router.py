@@ -51,13 +51,21 @@ def advertised_throughput(tokens_per_sec: float) -> float:
     return float(round(2.0 ** (round(math.log2(tokens_per_sec) * 2.0) / 2.0), 1))
 
 
+LOAD_FLAG_AT = 2.0          # (active + queued) / max_batch at which a worker advertises Load = 1
+
+
 def advertised_load(load: float) -> float:
-    """Two levels only: 0 while the worker has a free batch slot, 1 once it is saturated (every slot busy or requests
-    queued).  The gateway sees metadata that is 2-30 s old (DiscoveryInterval 10 s, MetadataUpdateInterval 30 s,
-    manager.go:99-101); a fine-grained load makes the momentarily least loaded worker win EVERY request until the next
-    refresh (measured: 36 / 100 / 42 / 78 requests over four identical workers).  With two levels all unsaturated
-    workers tie and FindBestWorker's random tie-break spreads the requests, as it does with the reference's constants."""
-    return 1.0 if load >= 1.0 else 0.0
+    """Two levels only: 0 in normal operation, 1 once a whole extra batch is waiting (load >= 2: a new request would sit
+    through a full generation before it gets a slot).  The gateway sees metadata that is 2-30 s old (DiscoveryInterval
+    10 s, MetadataUpdateInterval 30 s, manager.go:99-101) while a chat lasts about a second, so the advertised Load
+    describes the past: a fine-grained load makes the momentarily least loaded worker win EVERY request until the next
+    refresh (measured: 36 / 100 / 42 / 78 requests over four identical workers), and even a flag at load >= 1 shuns
+    every worker that happened to be full at refresh time (8 peers, 256 clients: 60 ... 138 requests per worker, 0.63
+    of 8x one worker; tools/route_sim.py reproduces it: 0.77 of balanced at a 2 s refresh, 0.56 at 10 s, against 0.92
+    with the flag at 2).  Below the flag all workers tie, FindBestWorker's random tie-break spreads the requests as it
+    does with the reference's constants, and a closed loop balances itself: a worker with fewer running requests
+    completes fewer per second than it receives."""
+    return 1.0 if load >= LOAD_FLAG_AT else 0.0
 
 
 def resource_from_engine(peer_id: str, engine, version: str = "b200") -> Resource:

@@ -186,8 +186,10 @@ func AdvertisedThroughput(tokensPerSec float64) float64 {
 	return math.Round(math.Pow(2, math.Round(math.Log2(tokensPerSec)*2)/2)*10) / 10
 }
 
+// Load = 1 only once a whole extra batch is waiting (cl_stats.load >= 2): the metadata is older than a request lasts,
+// and a flag at load >= 1 shuns every worker that happened to be full at refresh time (tools/route_sim.py).
 func AdvertisedLoad(load float64) float64 {
-	if load >= 1 {
+	if load >= 2 {
 		return 1
 	}
 	return 0

@@ -116,7 +116,8 @@ typedef struct cl_result {
 typedef struct cl_stats {
   double tokens_per_sec;     /* capacity, load-independent: 70 % of the HBM roofline of one decode step x max_batch, from the
                                 device's memory bandwidth and the model's bytes per token -> Resource.TokensThroughput (types.go:33) */
-  double load;               /* (active + queued) / max_batch, capped at 1 -> Resource.Load (types.go:35) */
+  double load;               /* (active + queued) / max_batch; > 1: requests are waiting for a batch slot -> Resource.Load
+                                (types.go:35) through the two-level rule of INTEGRATION.md "What to advertise" */
   int32_t queue_depth;
   int32_t active_seqs;
   int32_t kv_pages_total;
@@ -128,6 +129,10 @@ typedef struct cl_stats {
   char gpu_model[64];        /* -> Resource.GPUModel */
   int64_t kernel_launches;   /* kernels of this library launched so far (graph nodes counted) */
   double measured_tokens_per_sec; /* EWMA of decode steps/s x max_batch at the CURRENT batch sizes (diagnostic; not for routing) */
+  /* scheduler accounting since engine creation: batched decode steps (tokens_generated / sched_decode_steps = mean batch)
+     and admission-time prefill calls, with the scheduler thread's wall time inside each */
+  int64_t sched_decode_steps, sched_decode_ns;
+  int64_t sched_prefill_calls, sched_prefill_tokens, sched_prefill_ns;
 } cl_stats;
 
 typedef struct cl_engine cl_engine;

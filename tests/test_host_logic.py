@@ -423,3 +423,13 @@ def test_checkpoint_validation_is_host_logic(tmp_path):
         eng.checkpoint_info(tmp_path / "garbage.safetensors", cfg)
     with pytest.raises(eng.EngineError):
         eng.checkpoint_info(tmp_path, None)                     # a directory without config.json
+
+
+def test_advertised_metadata_rule():
+    """INTEGRATION.md "What to advertise": capacity in half-octave buckets (identical workers tie), Load flagged only
+    once a whole extra batch waits."""
+    from crowdllama_b200 import router
+    assert router.advertised_throughput(11000.0) == router.advertised_throughput(12500.0)
+    assert router.advertised_throughput(11000.0) != router.advertised_throughput(22000.0)
+    assert router.advertised_throughput(0.0) == 0.0
+    assert [router.advertised_load(x) for x in (0.0, 0.99, 1.0, 1.9, 2.0, 7.5)] == [0.0, 0.0, 0.0, 0.0, 1.0, 1.0]
