@@ -331,7 +331,7 @@ int Engine::alloc_state() {
     DMALLOC(d_timeline_, (size_t)(cfg.n_layers * 5 + 1) * 4 * 8);   // >= n_layers * 16 stamps for the megakernel view
     CL_CUDA_OK(cudaMemsetAsync(d_timeline_, 0, (size_t)(cfg.n_layers * 5 + 1) * 4 * 8, stream_));
   }
-  batch_gemm_min_ = env_int("CL_BATCH_GEMM_MIN", 3);
+  batch_gemm_min_ = env_int("CL_BATCH_GEMM_MIN", 2);
   use_batch_gemm_ = env_int("CL_BATCH_GEMM", 1) != 0 && max_batch_ >= 2 && gemm_tcgen05_supported(max_batch_, cfg.d_model, cfg.d_model) &&
                     max_batch_ <= 32;
   if (use_batch_gemm_) {
@@ -431,7 +431,7 @@ int Engine::ensure_capacity(cl_seq_t s, int n_tokens) {
 // ---- one token step for the sequences listed in d_slots_[0..B) -----------------------------------
 int Engine::enqueue_step(int B, bool tail) {
   if (B >= 2 && tail && use_batch_mega_ && have_kv_maps_ && bws_) return enqueue_step_batch_mega(B);
-  if (B >= batch_gemm_min_ && tail && use_batch_gemm_ && bws_) return enqueue_step_batched(B);   // B = 2 is faster on the GEMV kernels (measured)
+  if (B >= batch_gemm_min_ && tail && use_batch_gemm_ && bws_) return enqueue_step_batched(B);   // from B = 2: 3.58 vs 3.94 ms at ctx 256, 3.72 vs 4.29 at ctx 4096 against two GEMV passes (r2p)
   const int d = cfg.d_model, F = cfg.d_ff, L_ = cfg.n_layers;
   int n = 0, r;
 #define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } n += r; } while (0)

@@ -253,7 +253,7 @@ class Engine {
   CUtensorMap* d_bm_wmaps_ = nullptr;
   CUtensorMap bm_map_xn_{}, bm_map_attn_{}, bm_map_act_{};
   int enqueue_step_batch_mega(int B);
-  int batch_gemm_min_ = 3;
+  int batch_gemm_min_ = 2;
   int prefill_chunk_tokens_ = 4096;
 
   std::unique_ptr<KvPool> pool_;

@@ -41,6 +41,7 @@ struct GemmParams {
   int T, N, K, ldy;
   int accumulate_into_y;  // 1: Y += result (residual add in place)
   int k_splits;           // > 1: split-K; split s writes its partial to Y + s * T * ldy (the consumer sums in fixed order)
+  int pre_stages;         // PDL launches only: W tiles of the first stages requested before griddepcontrol.wait (0 = none)
   GemmEpi epi;            // fused prefill epilogues (EPI template parameter != 0): see kernels.h
 };
 enum { EPI_F32 = 0, EPI_SILU = 1, EPI_ROPE = 2 };
@@ -91,8 +92,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      // X is the previous kernel's output.  (Filling the ring with W tiles BEFORE the wait was tried and lost:
-      // B = 16 step 4.81 -> 5.12 ms — the early bulk stream slows the latency-bound glue kernel it overlaps with.)
+      // X is the previous kernel's output; W is constant: the W halves of the first p.pre_stages ring stages are
+      // requested before griddepcontrol.wait (while the glue kernel in front still runs), their X halves after it.
+      int pre = 0;
+      if (p.pre_stages > 0 && (int)blockIdx.x < num_tiles) {
+        const int tile = blockIdx.x;
+        const int bt_ = tile % (num_t * num_n), ks = tile / (num_t * num_n);
+        const int n0 = (bt_ / num_t) * BMT;
+        const int kb0 = ks * kb_per, kb1 = min(num_kb_all, kb0 + kb_per);
+        pre = min(min(p.pre_stages, NST), kb1 - kb0);
+        for (int i = 0; i < pre; ++i) {            // fresh barriers: every stage is empty
+          mbar_arrive_expect_tx(&full[i], STAGE);
+          tma_load_2d(base + (size_t)i * STAGE, &map_w, (kb0 + i) * BK, n0, &full[i]);
+        }
+      }
       pdl_wait();
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -100,11 +113,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         const int n0 = (bt_ / num_t) * BMT, t0 = (bt_ % num_t) * BT;
         const int kb0 = ks * kb_per, kb1 = min(num_kb_all, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], STAGE);
           uint8_t* sa = base + (size_t)stage * STAGE;
-          tma_load_2d(sa, &map_w, kb * BK, n0, &full[stage]);
-          tma_load_2d(sa + A_BYTES, &map_x, kb * BK, t0, &full[stage]);
+          if (pre > 0) {                           // W of this stage is already on its way
+            --pre;
+            tma_load_2d(sa + A_BYTES, &map_x, kb * BK, t0, &full[stage]);
+          } else {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full[stage], STAGE);
+            tma_load_2d(sa, &map_w, kb * BK, n0, &full[stage]);
+            tma_load_2d(sa + A_BYTES, &map_x, kb * BK, t0, &full[stage]);
+          }
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       }
@@ -335,7 +353,10 @@ int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, c
   if (!make_map(&mw, W, N, K, BM * MT) || !make_map(&mx, X, T, K, BT)) return -1;
   if (k_splits > 1 && (resid || (K + BK - 1) / BK < k_splits)) return -1;   // every split needs >= 1 k-block (an empty split would never signal its epilogue)
   if (k_splits > 1 && ((K + BK - 1) / BK + k_splits - 1) / k_splits * (k_splits - 1) >= (K + BK - 1) / BK) return -1;
-  GemmParams p{Y, T, N, K, N, resid ? 1 : 0, k_splits, GemmEpi()};
+  // measured (r2p / r2q, batched decode step at ctx 1024): B = 8 3.819 ms with no early W, 3.758 / 3.734 / 3.719 with 4 / 6 / 8
+  // stages; B = 32 4.525 -> 4.487.  The whole ring it is (the round-1 loss came from the glue kernels of that time).
+  static const int pre_env = getenv("CL_GEMM_PRE") ? atoi(getenv("CL_GEMM_PRE")) : 8;
+  GemmParams p{Y, T, N, K, N, resid ? 1 : 0, k_splits, pdl ? pre_env : 0, GemmEpi()};
   cudaError_t e;
   switch (BT) {
     case 256: e = MT == 2 ? launch_inst<256, 3, 2>(mw, mx, p, st, pdl) : launch_inst<256, 4>(mw, mx, p, st, pdl); break;
@@ -354,7 +375,7 @@ int launch_gemm_bf16_epi(const __nv_bfloat16* X, const __nv_bfloat16* W, int T, 
   const int BT = T > 128 ? 256 : T > 64 ? 128 : T > 32 ? 64 : 32;
   CUtensorMap mw, mx;
   if (!make_map(&mw, W, N, K, BM) || !make_map(&mx, X, T, K, BT)) return -1;
-  GemmParams p{nullptr, T, N, K, N, 0, 1, epi};
+  GemmParams p{nullptr, T, N, K, N, 0, 1, 0, epi};
   cudaError_t e;
   if (epi.kind == 1) {
     switch (BT) {

@@ -27,6 +27,48 @@ bool Engine::prefill_path_ok() const {
 // split-K rule shared with the batched decode step (engine.cu)
 int pick_splits_public(int n_rows, int K);
 
+// CL_PREFILL_PROFILE=1: a CUDA event after every launch, per-kernel-class device time printed to stderr (in-pipeline
+// times incl. the gap before each kernel; the ncu launch list measures cold, serialised launches instead).
+struct PrefillProfiler {
+  bool on;
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> name;
+  explicit PrefillProfiler(cudaStream_t s) : st(s) {
+    static const bool prof = getenv("CL_PREFILL_PROFILE") && atoi(getenv("CL_PREFILL_PROFILE")) != 0;
+    on = prof;
+  }
+  void mark(const char* n) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    name.push_back(n);
+  }
+  void report(int n_tokens, const char* path) {
+    if (!on || ev.size() < 2) return;
+    cudaStreamSynchronize(st);
+    std::map<std::string, std::pair<double, int>> acc;
+    double total = 0.0;
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      const std::string full(name[i]);
+      std::string key = full.substr(0, full.find('('));
+      if (key == "launch_gemm_bf16_epi") key += full.find("L.wqkv") != std::string::npos ? ":qkv+rope" : ":gate|up+silu";
+      if (key == "launch_gemm_bf16")     // split by projection: the weight argument names it
+        key += full.find("L.wqkv") != std::string::npos ? ":qkv" : full.find("L.wo") != std::string::npos ? ":o" : full.find("L.wgu") != std::string::npos ? ":gate|up" : ":down";
+      acc[key].first += ms; acc[key].second += 1;
+      total += ms;
+    }
+    fprintf(stderr, "[prefill profile] %s path, %d tokens, %zu launches, %.3f ms on the device\n", path, n_tokens, ev.size() - 1, total);
+    for (auto& kv : acc) fprintf(stderr, "[prefill profile]   %-32s n=%4d total %8.3f ms  mean %8.2f us\n", kv.first.c_str(), kv.second.second, kv.second.first, 1e3 * kv.second.first / kv.second.second);
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear(); name.clear();
+  }
+};
+
 // Short prompts (prefill_min_tokens_ <= n <= 256, e.g. a 128-token chat): one token tile per W row tile means only
 // N/128 CTAs stream the weights of a projection (48 for q|k|v, 32 for o and down) — 11 ms for 128 tokens where the
 // weight stream alone needs 2.4.  Same recipe as the batched decode step: split-K so that ~148 CTAs share every
@@ -64,14 +106,20 @@ int Engine::prefill_small(cl_seq_t s, const int32_t* ids, int n, float* logits_o
   CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
   const int* bt = d_bt_ + (size_t)s * max_pages_per_seq_;
   int launches = 0, r;
-#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; } while (0)
+  PrefillProfiler pp(stream_);
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; pp.mark(#call); } while (0)
+  // programmatic dependent launch between the GEMMs and the per-row glue kernels, as in the batched decode step (the two
+  // prefill kernels in between are launched normally and order the stream)
+  static const bool small_pdl = !getenv("CL_SMALL_PDL") || atoi(getenv("CL_SMALL_PDL")) != 0;   // 146 tokens: 6.41 -> 5.90 ms (r2q)
+  const bool bp = small_pdl && use_pdl_;
+  pp.mark("start");
   CL_LAUNCH(launch_embed_rows(embed_, d, d_prompt_, w.h, T, stream_));
   const float* pending = nullptr;   // split-K partials of the previous residual projection, folded in by the next norm
   int pending_s = 0;
   for (int l = 0; l < cfg.n_layers; ++l) {
     const auto& L = layers_[l];
-    CL_LAUNCH(launch_batch_resid_norm(w.h, d, pending, pending_s, T, L.attn_norm, cfg.rms_eps, w.xn, w.iota, stream_));
-    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wqkv, w.part, nullptr, T, qkv_dim_, d, stream_, s_qkv));
+    CL_LAUNCH(launch_batch_resid_norm(w.h, d, pending, pending_s, T, L.attn_norm, cfg.rms_eps, w.xn, w.iota, stream_, bp));
+    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wqkv, w.part, nullptr, T, qkv_dim_, d, stream_, s_qkv, bp));
     RopeScatterArgs ra{w.part, qkv_dim_, rope_, pos0, T, w.q, kpool_ + (size_t)l * kv_layer_elems_, vpool_ + (size_t)l * kv_layer_elems_,
                        bt, page_size_, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim};
     ra.n_split = s_qkv; ra.split_stride = (size_t)T * qkv_dim_;
@@ -82,15 +130,15 @@ int Engine::prefill_small(cl_seq_t s, const int32_t* ids, int n, float* logits_o
       CL_LAUNCH(launch_attn_prefill_tc(aa, kmap_, vmap_, (long long)l * n_pages_ * cfg.n_kv_heads * page_size_, stream_));
     else
       CL_LAUNCH(launch_attn_prefill(aa, stream_));
-    CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.part, nullptr, T, d, q_dim_, stream_, s_o));
-    CL_LAUNCH(launch_batch_resid_norm(w.h, d, w.part, s_o, T, L.ffn_norm, cfg.rms_eps, w.xn, w.iota, stream_));
-    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.part, nullptr, T, 2 * F, d, stream_, s_gu));
-    CL_LAUNCH(launch_batch_silu(w.part, s_gu, T, F, w.act, stream_));
-    CL_LAUNCH(launch_gemm_bf16(w.act, L.wdown, w.part, nullptr, T, d, F, stream_, s_dn));
+    CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.part, nullptr, T, d, q_dim_, stream_, s_o, bp));
+    CL_LAUNCH(launch_batch_resid_norm(w.h, d, w.part, s_o, T, L.ffn_norm, cfg.rms_eps, w.xn, w.iota, stream_, bp));
+    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.part, nullptr, T, 2 * F, d, stream_, s_gu, bp));
+    CL_LAUNCH(launch_batch_silu(w.part, s_gu, T, F, w.act, stream_, bp));
+    CL_LAUNCH(launch_gemm_bf16(w.act, L.wdown, w.part, nullptr, T, d, F, stream_, s_dn, bp));
     pending = w.part; pending_s = s_dn;
   }
   // fold the last down-projection into the residual rows (the normalised copy it also writes is not used), then the shared tail
-  CL_LAUNCH(launch_batch_resid_norm(w.h, d, pending, pending_s, T, final_norm_, cfg.rms_eps, w.xn, w.iota, stream_));
+  CL_LAUNCH(launch_batch_resid_norm(w.h, d, pending, pending_s, T, final_norm_, cfg.rms_eps, w.xn, w.iota, stream_, bp));
   CL_CUDA_OK(cudaMemcpyAsync(d_h_ + (size_t)s * d, w.h + (size_t)(T - 1) * d, (size_t)d * 4, cudaMemcpyDeviceToDevice, stream_));
   const int last_pos = q.len + n - 1;
   CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &last_pos, 4, cudaMemcpyHostToDevice, stream_));
@@ -107,6 +155,7 @@ int Engine::prefill_small(cl_seq_t s, const int32_t* ids, int n, float* logits_o
   t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = 1;
   CL_LAUNCH(launch_step_tail(t, stream_));
 #undef CL_LAUNCH
+  pp.report(n, "short-prompt");
   launches_ += launches;
   q.len += n;
   q.history.insert(q.history.end(), ids, ids + n);
@@ -146,21 +195,9 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
   CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
   const int* bt = d_bt_ + (size_t)s * max_pages_per_seq_;
   int launches = 0, r;
-  // CL_PREFILL_PROFILE=1: a CUDA event after every launch, per-kernel-class device time printed to stderr (in-pipeline
-  // times incl. the gap before each kernel; the ncu launch list measures cold, serialised launches instead)
-  static const bool prof = getenv("CL_PREFILL_PROFILE") && atoi(getenv("CL_PREFILL_PROFILE")) != 0;
-  std::vector<cudaEvent_t> pev;
-  std::vector<const char*> pname;
-  auto mark = [&](const char* name) {
-    if (!prof) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, stream_);
-    pev.push_back(e);
-    pname.push_back(name);
-  };
-#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; mark(#call); } while (0)
-  mark("start");
+  PrefillProfiler pp(stream_);
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; pp.mark(#call); } while (0)
+  pp.mark("start");
   for (int c0 = 0; c0 < n; c0 += w.cap_tokens) {
     const int T = std::min(w.cap_tokens, n - c0);
     const int pos0 = q.len + c0;
@@ -218,27 +255,7 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
   t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = 1;
   CL_LAUNCH(launch_step_tail(t, stream_));
 #undef CL_LAUNCH
-  if (prof && pev.size() > 1) {
-    cudaStreamSynchronize(stream_);
-    std::map<std::string, std::pair<double, int>> acc;
-    double total = 0.0;
-    for (size_t i = 1; i < pev.size(); ++i) {
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, pev[i - 1], pev[i]);
-      std::string key(pname[i]);
-      key = key.substr(0, key.find('('));
-      if (key == "launch_gemm_bf16_epi") key += std::string(pname[i]).find("L.wqkv") != std::string::npos ? ":qkv+rope" : ":gate|up+silu";
-      if (key == "launch_gemm_bf16") {   // split by projection: the 3rd argument names the output buffer
-        const std::string full(pname[i]);
-        key += full.find("L.wqkv") != std::string::npos ? ":qkv" : full.find("L.wo") != std::string::npos ? ":o" : full.find("L.wgu") != std::string::npos ? ":gate|up" : ":down";
-      }
-      acc[key].first += ms; acc[key].second += 1;
-      total += ms;
-    }
-    fprintf(stderr, "[prefill profile] %d tokens, %zu launches, %.3f ms on the device\n", n, pev.size() - 1, total);
-    for (auto& kv : acc) fprintf(stderr, "[prefill profile]   %-32s n=%4d total %8.3f ms  mean %8.2f us\n", kv.first.c_str(), kv.second.second, kv.second.first, 1e3 * kv.second.first / kv.second.second);
-    for (auto e : pev) cudaEventDestroy(e);
-  }
+  pp.report(n, "tile");
   launches_ += launches;
   q.len += n;
   q.history.insert(q.history.end(), ids, ids + n);
