@@ -52,6 +52,13 @@ void cl_default_sampling(cl_sampling* s) {
   s->max_new_tokens = -1;
 }
 
+int cl_sample_token(const float* logits, int32_t vocab, const cl_sampling* s, const int32_t* history, int32_t n_history,
+                    uint64_t step, int32_t* id) {
+  if (!logits || vocab <= 0 || !s || !id || n_history < 0 || (n_history > 0 && !history)) return CL_ERR_INVALID_ARG;
+  *id = cl::sample_token(logits, vocab, *s, history, n_history, step);
+  return CL_OK;
+}
+
 void cl_greedy_sampling(cl_sampling* s, int32_t max_new_tokens) {
   memset(s, 0, sizeof *s);
   s->temperature = 0.f;

@@ -64,7 +64,7 @@ class Stats(C.Structure):
 # every symbol include/clengine.h declares (tests check the library exports all of them)
 EXPORTS = [
     "cl_abi_version", "cl_strerror", "cl_last_error", "cl_default_engine_config", "cl_default_sampling",
-    "cl_greedy_sampling", "cl_model_preset", "cl_engine_create", "cl_engine_destroy", "cl_engine_model_config",
+    "cl_greedy_sampling", "cl_sample_token", "cl_model_preset", "cl_engine_create", "cl_engine_destroy", "cl_engine_model_config",
     "cl_engine_stats", "cl_engine_set_tensor", "cl_checkpoint_info", "cl_generate", "cl_generate_ids", "cl_generate_stream", "cl_result_free",
     "cl_handle_message", "cl_handle_message_stream", "cl_buffer_free", "cl_tokenize", "cl_detokenize", "cl_seq_create", "cl_seq_free",
     "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_decode_step_batch", "cl_seq_fake_fill",
@@ -117,6 +117,7 @@ def lib():
         "cl_tokenize": (C.c_int, [vp, C.c_char_p, sz, vp, i32, P(i32)]),
         "cl_detokenize": (C.c_int, [vp, vp, i32, vp, sz, P(sz)]),
         "cl_seq_create": (C.c_int, [vp, P(i32)]),
+        "cl_sample_token": (C.c_int, [vp, i32, vp, vp, i32, C.c_uint64, P(i32)]),
         "cl_seq_free": (C.c_int, [vp, i32]),
         "cl_seq_len": (C.c_int, [vp, i32, P(i32)]),
         "cl_prefill": (C.c_int, [vp, i32, vp, i32, vp]),
@@ -210,6 +211,15 @@ def greedy(max_new_tokens: int, ignore_eos: bool = False) -> Sampling:
     lib().cl_greedy_sampling(C.byref(s), max_new_tokens)
     s.ignore_eos = 1 if ignore_eos else 0
     return s
+
+
+def sample_token(logits, sampling: Sampling, history=(), step: int = 0) -> int:
+    """The engine's host-side sampler on caller-provided logits (cl_sample_token; no GPU involved)."""
+    lg = np.ascontiguousarray(logits, dtype=np.float32)
+    h = np.ascontiguousarray(list(history), dtype=np.int32)
+    out = C.c_int32()
+    _check(lib().cl_sample_token(_ptr(lg), lg.size, C.byref(sampling), _ptr(h) if h.size else None, h.size, step, C.byref(out)), "cl_sample_token")
+    return int(out.value)
 
 
 def ollama_default_sampling(seed: int = 0, max_new_tokens: int = -1) -> Sampling:

@@ -146,6 +146,12 @@ const char* cl_last_error(void);
 void cl_default_engine_config(cl_engine_config* cfg);
 void cl_default_sampling(cl_sampling* s);        /* Ollama defaults listed above */
 void cl_greedy_sampling(cl_sampling* s, int32_t max_new_tokens);
+/* The engine's host-side sampler on caller-provided logits (no GPU involved): repeat penalty over the last repeat_last_n
+ * ids of `history` -> top-k -> softmax at `temperature` -> top-p -> one draw from the counter-based generator at
+ * (seed, step).  Exposed so that each stage can be checked against an independent implementation
+ * (tests/test_host_logic.py pins it to the HF transformers logits processors). */
+int cl_sample_token(const float* logits, int32_t vocab, const cl_sampling* s, const int32_t* history, int32_t n_history,
+                    uint64_t step, int32_t* id);
 int cl_model_preset(const char* name, cl_model_config* out);
 
 /* replaces: embedded Ollama server start, /root/reference/cmd/crowdllama/main.go:283-297 */

@@ -433,3 +433,49 @@ def test_advertised_metadata_rule():
     assert router.advertised_throughput(11000.0) != router.advertised_throughput(22000.0)
     assert router.advertised_throughput(0.0) == 0.0
     assert [router.advertised_load(x) for x in (0.0, 0.99, 1.0, 1.9, 2.0, 7.5)] == [0.0, 0.0, 0.0, 0.0, 1.0, 1.0]
+
+
+def _hf_filtered_probs(logits, history, temperature, top_k, top_p, penalty):
+    """The same chain built from the HF transformers logits processors (an independent implementation of every stage):
+    repetition penalty -> top-k -> temperature -> top-p, then softmax over what is left."""
+    import torch
+    from transformers.generation.logits_process import (RepetitionPenaltyLogitsProcessor, TemperatureLogitsWarper, TopKLogitsWarper,
+                                                         TopPLogitsWarper)
+    sc = torch.tensor(np.asarray(logits, np.float32))[None, :].double()
+    ids = torch.tensor(list(history), dtype=torch.long)[None, :] if len(history) else torch.zeros((1, 0), dtype=torch.long)
+    if penalty != 1.0 and len(history):
+        sc = RepetitionPenaltyLogitsProcessor(penalty)(ids, sc)
+    if top_k > 0:
+        sc = TopKLogitsWarper(top_k)(ids, sc)
+    sc = TemperatureLogitsWarper(temperature)(ids, sc)
+    if 0.0 < top_p < 1.0:
+        sc = TopPLogitsWarper(top_p)(ids, sc)
+    return torch.softmax(sc, dim=-1)[0].numpy()
+
+
+@pytest.mark.parametrize("case", [
+    dict(temperature=0.8, top_k=40, top_p=0.9, penalty=1.1, hist=24),     # Ollama's defaults (api.go:109-118 sends no options)
+    dict(temperature=1.3, top_k=0, top_p=0.7, penalty=1.0, hist=0),       # nucleus only
+    dict(temperature=0.5, top_k=5, top_p=1.0, penalty=1.6, hist=10),      # top-k only, strong penalty
+    dict(temperature=1.0, top_k=12, top_p=0.5, penalty=1.3, hist=40),
+])
+def test_sampler_stages_match_hf_logits_processors(case):
+    """Pins the sampler (the library's cl_sample_token AND the CPU checker's) to an implementation that is not this
+    repository's: support set and probabilities of the HF transformers processors applied in the same order.  8000
+    draws per case over a 64-token vocabulary: no draw outside HF's support, every token's frequency within 5 sigma."""
+    from oracle import oracle as oc
+    rng = np.random.default_rng(hash(tuple(sorted(case.items()))) % (2 ** 32))
+    V, n = 64, 8000
+    lg = (rng.standard_normal(V) * 2.0).astype(np.float32)
+    hist = [int(x) for x in rng.integers(0, V, size=case["hist"])]
+    p = _hf_filtered_probs(lg, hist, case["temperature"], case["top_k"], case["top_p"], case["penalty"])
+    sp = eng.ollama_default_sampling(seed=4242)
+    sp.temperature, sp.top_k, sp.top_p, sp.repeat_penalty, sp.repeat_last_n = case["temperature"], case["top_k"], case["top_p"], case["penalty"], 64
+    ours = np.bincount([eng.sample_token(lg, sp, hist, step=i) for i in range(n)], minlength=V)
+    chk = np.bincount([oc.sample(lg, case["temperature"], case["top_k"], case["top_p"], case["penalty"], 64, seed=4242, history=hist, step=i)
+                       for i in range(n)], minlength=V)
+    assert (ours == chk).all()                                   # library sampler == CPU checker, draw by draw
+    assert ours[p == 0].sum() == 0, "a token outside the HF support set was drawn"
+    sigma = np.sqrt(n * p * (1 - p)) + 1e-9
+    assert (np.abs(ours - n * p) <= 5 * sigma + 1).all(), (ours, n * p)
+    assert (p > 0).sum() >= 2                                    # the case exercises a real distribution
