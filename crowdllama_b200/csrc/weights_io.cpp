@@ -134,6 +134,29 @@ int model_config_from_dir(const std::string& dir, cl_model_config* out) {
   }
   c.rope_theta = (float)theta;
   c.rms_eps = (float)num("rms_norm_eps", 1e-5);
+  // What the engine does NOT implement must fail here, not produce different tokens quietly:
+  //  * scaled rotary embeddings (Llama-3.1 "llama3", "linear", "dynamic", "yarn" ...) change inv_freq at EVERY position;
+  //  * an activation other than SiLU, attention / MLP biases.
+  // A sliding attention window (Mistral-7B-v0.1: 4096) is honoured by never serving a context beyond it: inside the
+  // window, sliding-window attention IS full attention.
+  auto rope_type_of = [](const JVal* o) -> std::string {
+    if (!o || o->type != JVal::Obj) return "";
+    std::string t = o->str("rope_type", "");
+    if (t.empty()) t = o->str("type", "");
+    return t;
+  };
+  for (const char* key : {"rope_scaling", "rope_parameters"}) {
+    const std::string t = rope_type_of(root.get(key));
+    if (!t.empty() && t != "default") { set_last_error(std::string("config.json: ") + key + " type \"" + t + "\" is not supported (plain rotary embeddings only)"); return CL_ERR_IO; }
+  }
+  const std::string act = root.str("hidden_act", "silu");
+  if (act != "silu") { set_last_error("config.json: hidden_act \"" + act + "\" is not supported (silu)"); return CL_ERR_IO; }
+  for (const char* key : {"attention_bias", "mlp_bias"}) {
+    const JVal* v = root.get(key);
+    if (v && v->type == JVal::Bool && v->b) { set_last_error(std::string("config.json: ") + key + " = true is not supported"); return CL_ERR_IO; }
+  }
+  const double window = num("sliding_window", 0.0);
+  if (window >= 1.0 && window < (double)c.max_seq_len) c.max_seq_len = (int)window;
   if (c.n_layers <= 0 || c.d_model <= 0 || c.n_heads <= 0 || c.d_ff <= 0 || c.vocab_size <= 0) {
     set_last_error("config.json: missing llama-family fields (num_hidden_layers, hidden_size, num_attention_heads, intermediate_size, vocab_size)");
     return CL_ERR_IO;
@@ -193,7 +216,11 @@ int visit_checkpoint(const std::string& path, const cl_model_config& cfg,
     const size_t data_len = m.n - 8 - hlen;
     for (const auto& kv : root.o) {
       int layer = 0, kind = 0;
-      if (kv.first == "__metadata__" || !map_name(kv.first, &layer, &kind)) continue;
+      if (kv.first == "__metadata__") continue;
+      if (kv.first.size() > 5 && kv.first.compare(kv.first.size() - 5, 5, ".bias") == 0 && kv.first.compare(0, 6, "model.") == 0) {
+        set_last_error(kv.first + ": projection biases are not supported by this engine"); return CL_ERR_IO;
+      }
+      if (!map_name(kv.first, &layer, &kind)) continue;
       if (layer >= cfg.n_layers) { set_last_error(kv.first + ": layer index beyond n_layers"); return CL_ERR_IO; }
       const JVal& t = kv.second;
       const JVal* shape = t.get("shape");
@@ -201,7 +228,13 @@ int visit_checkpoint(const std::string& path, const cl_model_config& cfg,
       const std::string dtype = t.str("dtype", "");
       if (!shape || shape->type != JVal::Arr || !offs || offs->type != JVal::Arr || offs->a.size() != 2) { set_last_error(kv.first + ": malformed entry"); return CL_ERR_IO; }
       int64_t n = 1;
-      for (const auto& s : shape->a) n *= (int64_t)s.n;
+      bool nums_ok = offs->a[0].type == JVal::Num && offs->a[1].type == JVal::Num && offs->a[0].n >= 0 && offs->a[1].n >= 0 &&
+                     offs->a[0].n < 9e15 && offs->a[1].n < 9e15 && shape->a.size() <= 2;
+      for (const auto& s : shape->a) {
+        if (s.type != JVal::Num || s.n < 0 || s.n > 2147483647.0) { nums_ok = false; break; }
+        n *= (int64_t)s.n;
+      }
+      if (!nums_ok) { set_last_error(kv.first + ": malformed shape / data_offsets"); return CL_ERR_IO; }
       int64_t rows = 0, cols = 0;
       expect(kind, &rows, &cols);
       const bool shape_ok = cols == 1 ? (shape->a.size() == 1 && (int64_t)shape->a[0].n == rows)

@@ -479,3 +479,44 @@ def test_sampler_stages_match_hf_logits_processors(case):
     sigma = np.sqrt(n * p * (1 - p)) + 1e-9
     assert (np.abs(ours - n * p) <= 5 * sigma + 1).all(), (ours, n * p)
     assert (p > 0).sum() >= 2                                    # the case exercises a real distribution
+
+
+def test_checkpoint_config_rejects_what_the_engine_does_not_implement(tmp_path):
+    """config.json features that would change the tokens must fail loudly (scaled RoPE, another activation, biases); a
+    sliding attention window is honoured by capping the served context at the window."""
+    import json
+    import shutil
+    import numpy as np
+    from st_util import write_safetensors
+    G = Path(__file__).resolve().parent / "golden" / "hf_tiny_llama_ckpt"
+    base = json.loads((G / "config.json").read_text())
+
+    def variant(name, **changes):
+        d = tmp_path / name
+        d.mkdir()
+        shutil.copy(G / "model.safetensors", d / "model.safetensors")
+        cfg = dict(base)
+        cfg.update(changes)
+        (d / "config.json").write_text(json.dumps(cfg))
+        return d
+    assert eng.checkpoint_info(variant("plain"))[0]["max_seq_len"] == 64
+    assert eng.checkpoint_info(variant("swa", sliding_window=32))[0]["max_seq_len"] == 32          # Mistral-7B-v0.1 style
+    assert eng.checkpoint_info(variant("swa_none", sliding_window=None))[0]["max_seq_len"] == 64
+    assert eng.checkpoint_info(variant("old_style", rope_parameters=None, rope_theta=500000.0, rope_scaling=None))[0]["rope_theta"] == 500000.0
+    for name, changes, needle in [
+            ("llama31", dict(rope_parameters={"rope_theta": 500000.0, "rope_type": "llama3", "factor": 8.0}), "llama3"),
+            ("linear", dict(rope_parameters=None, rope_theta=10000.0, rope_scaling={"type": "linear", "factor": 2.0}), "linear"),
+            ("gelu", dict(hidden_act="gelu"), "hidden_act"),
+            ("bias", dict(attention_bias=True), "attention_bias")]:
+        with pytest.raises(eng.EngineError) as ei:
+            eng.checkpoint_info(variant(name, **changes))
+        assert ei.value.status == eng.CL_ERR_IO and needle in ei.value.detail, ei.value.detail
+    # a bias tensor in the file itself (Qwen-style checkpoints) is refused, not ignored
+    cfg, _, _ = eng.checkpoint_info(G)
+    from st_util import hf_tensors_from_fixture
+    t = hf_tensors_from_fixture(np.load(G.parent / "hf_tiny_llama.npz"), cfg)
+    t["model.layers.0.self_attn.q_proj.bias"] = (np.zeros(128, np.uint16), (128,))
+    write_safetensors(tmp_path / "with_bias.safetensors", t)
+    with pytest.raises(eng.EngineError) as ei:
+        eng.checkpoint_info(tmp_path / "with_bias.safetensors", cfg)
+    assert "q_proj.bias" in ei.value.detail
