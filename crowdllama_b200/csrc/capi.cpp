@@ -73,6 +73,9 @@ int cl_model_preset(const char* name, cl_model_config* o) {
       {"llama3-8b", {32, 4096, 32, 8, 128, 14336, 128256, 8192, 5e5f, 1e-5f}},
       {"mistral-7b", {32, 4096, 32, 8, 128, 14336, 32000, 8192 + 512, 1e6f, 1e-5f}},
       {"tinyllama-1.1b", {22, 2048, 32, 4, 64, 5632, 32000, 2048, 1e4f, 1e-5f}},
+      // "llama3" rotary scaling (factor, low / high frequency factor, original context): Llama-3.1 and 3.2
+      {"llama3.1-8b", {32, 4096, 32, 8, 128, 14336, 128256, 32768, 5e5f, 1e-5f, 8.f, 1.f, 4.f, 8192}},
+      {"llama3.2-1b", {16, 2048, 32, 8, 64, 8192, 128256, 8192, 5e5f, 1e-5f, 32.f, 1.f, 4.f, 8192}},
       {"tiny-test", {2, 256, 4, 2, 64, 512, 512, 512, 1e4f, 1e-5f}},
   };
   for (const auto& p : presets)

@@ -211,8 +211,7 @@ int Engine::alloc_weights() {
   std::vector<float2> tab((size_t)cfg.max_seq_len * half);
   for (int p = 0; p < cfg.max_seq_len; ++p)
     for (int i = 0; i < half; ++i) {
-      const double inv = pow((double)cfg.rope_theta, -2.0 * (double)i / (double)cfg.head_dim);
-      const double ang = (double)p * inv;
+      const double ang = (double)p * rope_inv_freq(cfg, i);
       tab[(size_t)p * half + i] = make_float2((float)cos(ang), (float)sin(ang));
     }
   DMALLOC(rope_, tab.size() * sizeof(float2));

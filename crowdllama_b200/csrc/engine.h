@@ -96,6 +96,9 @@ std::unique_ptr<Tokenizer> load_hf_tokenizer(const std::string& path, const std:
 int model_config_from_dir(const std::string& dir, cl_model_config* out);
 
 // ---- sampler (host; mirrors oracle oc_sample) ---------------------------------------------------
+// inverse rotary frequency of dimension pair i: theta^(-2i/head_dim), with the "llama3" scaling of cl_model_config when
+// rope_factor > 1 — the same expression as oracle/llama_oracle.c rope_inv_freq(), so both sides build bit-identical tables
+double rope_inv_freq(const cl_model_config& c, int i);
 int32_t sample_token(const float* logits, int32_t vocab, const cl_sampling& sp, const int32_t* history, int32_t n_history,
                      uint64_t step);
 

@@ -104,6 +104,21 @@ static double uniform01(uint64_t seed, uint64_t step) {
   uint64_t x = mix64h(seed * 0x9E3779B97F4A7C15ull + step + 0x632BE59BD9B4E019ull);
   return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
+// HF transformers modeling_rope_utils.py, _compute_llama3_parameters (Llama-3.1 / 3.2): wavelengths beyond
+// original_max_pos / low_freq_factor are stretched by `factor`, those below original_max_pos / high_freq_factor are kept,
+// the band in between is blended linearly.
+double rope_inv_freq(const cl_model_config& c, int i) {
+  const double pi = 3.14159265358979323846;
+  const double inv = std::pow((double)c.rope_theta, -2.0 * (double)i / (double)c.head_dim);
+  if (!(c.rope_factor > 1.0f) || c.rope_original_max_pos <= 0) return inv;
+  const double factor = c.rope_factor, lo = c.rope_low_freq_factor, hi = c.rope_high_freq_factor, old = c.rope_original_max_pos;
+  const double wavelen = 2.0 * pi / inv;
+  if (wavelen > old / lo) return inv / factor;
+  if (wavelen < old / hi) return inv;
+  const double smooth = (old / wavelen - lo) / (hi - lo);
+  return (1.0 - smooth) * inv / factor + smooth * inv;
+}
+
 int32_t sample_token(const float* logits, int32_t vocab, const cl_sampling& sp, const int32_t* history, int32_t n_history,
                      uint64_t step) {
   if (sp.temperature <= 0.f) {

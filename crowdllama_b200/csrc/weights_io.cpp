@@ -3,7 +3,8 @@
 // The reference worker serves real checkpoints by name through the embedded Ollama server
 // (/root/reference/cmd/crowdllama/main.go:283-297; names advertised at /root/reference/pkg/peer/peer.go:319-343).
 // This engine reads the HF llama-family layout instead: a `.safetensors` file, or a model directory holding
-// `*.safetensors` shards (+ optional `config.json` for the architecture and `tokenizer.json` for the vocabulary).
+// `*.safetensors` shards (+ optional `config.json` for the architecture — incl. the "llama3" rotary scaling of
+// Llama-3.1 / 3.2 — and `tokenizer.json` for the vocabulary).
 //
 // safetensors container: u64 little-endian header length N | N bytes of JSON
 //   { "<tensor name>": {"dtype": "BF16"|"F16"|"F32", "shape": [...], "data_offsets": [begin, end]}, "__metadata__": {...} }
@@ -135,7 +136,7 @@ int model_config_from_dir(const std::string& dir, cl_model_config* out) {
   c.rope_theta = (float)theta;
   c.rms_eps = (float)num("rms_norm_eps", 1e-5);
   // What the engine does NOT implement must fail here, not produce different tokens quietly:
-  //  * scaled rotary embeddings (Llama-3.1 "llama3", "linear", "dynamic", "yarn" ...) change inv_freq at EVERY position;
+  //  * scaled rotary embeddings other than "llama3" ("linear", "dynamic", "yarn" ...) change inv_freq at EVERY position;
   //  * an activation other than SiLU, attention / MLP biases.
   // A sliding attention window (Mistral-7B-v0.1: 4096) is honoured by never serving a context beyond it: inside the
   // window, sliding-window attention IS full attention.
@@ -146,8 +147,19 @@ int model_config_from_dir(const std::string& dir, cl_model_config* out) {
     return t;
   };
   for (const char* key : {"rope_scaling", "rope_parameters"}) {
-    const std::string t = rope_type_of(root.get(key));
-    if (!t.empty() && t != "default") { set_last_error(std::string("config.json: ") + key + " type \"" + t + "\" is not supported (plain rotary embeddings only)"); return CL_ERR_IO; }
+    const JVal* o = root.get(key);
+    const std::string t = rope_type_of(o);
+    if (t.empty() || t == "default") continue;
+    if (t != "llama3") { set_last_error(std::string("config.json: ") + key + " type \"" + t + "\" is not supported (default and llama3 rotary embeddings only)"); return CL_ERR_IO; }
+    auto f = [&](const char* k) { const JVal* v = o->get(k); return v && v->type == JVal::Num ? v->n : 0.0; };
+    c.rope_factor = (float)f("factor");
+    c.rope_low_freq_factor = (float)f("low_freq_factor");
+    c.rope_high_freq_factor = (float)f("high_freq_factor");
+    c.rope_original_max_pos = (int)f("original_max_position_embeddings");
+    if (!(c.rope_factor >= 1.f) || !(c.rope_low_freq_factor > 0.f) || !(c.rope_high_freq_factor > c.rope_low_freq_factor) || c.rope_original_max_pos <= 0) {
+      set_last_error(std::string("config.json: ") + key + " llama3 needs factor >= 1, 0 < low_freq_factor < high_freq_factor, original_max_position_embeddings > 0");
+      return CL_ERR_IO;
+    }
   }
   const std::string act = root.str("hidden_act", "silu");
   if (act != "silu") { set_last_error("config.json: hidden_act \"" + act + "\" is not supported (silu)"); return CL_ERR_IO; }

@@ -25,7 +25,8 @@ KINDS = dict(EMBED=0, LM_HEAD=1, FINAL_NORM=2, ATTN_NORM=3, WQ=4, WK=5, WV=6, WO
 class ModelConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_layers", "d_model", "n_heads", "n_kv_heads", "head_dim", "d_ff",
                                          "vocab_size", "max_seq_len")] + \
-               [("rope_theta", C.c_float), ("rms_eps", C.c_float)]
+               [("rope_theta", C.c_float), ("rms_eps", C.c_float), ("rope_factor", C.c_float), ("rope_low_freq_factor", C.c_float),
+                ("rope_high_freq_factor", C.c_float), ("rope_original_max_pos", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CL_ABI_VERSION 1
+#define CL_ABI_VERSION 2
 
 typedef enum cl_status {
   CL_OK = 0,
@@ -62,6 +62,14 @@ typedef struct cl_model_config {
   int32_t max_seq_len;   /* positions covered by the RoPE table and block tables */
   float rope_theta;
   float rms_eps;
+  /* "llama3" rotary scaling (Llama-3.1 / 3.2 checkpoints; HF config.json rope_scaling / rope_parameters with
+   * rope_type "llama3").  rope_factor <= 1 (e.g. 0): plain rotary embeddings.  Otherwise the inverse frequency of
+   * dimension pair i is divided by rope_factor where its wavelength exceeds rope_original_max_pos / rope_low_freq_factor,
+   * kept where it is below rope_original_max_pos / rope_high_freq_factor, and blended linearly in between. */
+  float rope_factor;
+  float rope_low_freq_factor;
+  float rope_high_freq_factor;
+  int32_t rope_original_max_pos;
 } cl_model_config;
 
 typedef struct cl_engine_config {

@@ -110,13 +110,28 @@ int32_t oc_get_num_threads(void) {
 #endif
 }
 
+/* Inverse frequency of dimension pair i.  Plain: theta^(-2i/hd).  With "llama3" scaling (Llama-3.1 / 3.2; HF transformers
+ * modeling_rope_utils.py, _compute_llama3_parameters): wavelengths beyond original_max_pos / low_freq_factor are
+ * stretched by `factor`, those below original_max_pos / high_freq_factor are kept, the band in between is blended. */
+static double rope_inv_freq(const oc_config* c, int i) {
+  const double pi = 3.14159265358979323846;
+  double inv = pow((double)c->rope_theta, -2.0 * (double)i / (double)c->head_dim);
+  if (!(c->rope_factor > 1.0f) || c->rope_original_max_pos <= 0) return inv;
+  const double factor = c->rope_factor, lo = c->rope_low_freq_factor, hi = c->rope_high_freq_factor, old = c->rope_original_max_pos;
+  const double wavelen = 2.0 * pi / inv;
+  if (wavelen > old / lo) return inv / factor;
+  if (wavelen < old / hi) return inv;
+  const double smooth = (old / wavelen - lo) / (hi - lo);
+  return (1.0 - smooth) * inv / factor + smooth * inv;
+}
+
 /* cos/sin table computed in double on the host, rounded to fp32.  The engine builds the same
  * table with the same expression on the host and uploads it, so both sides share it exactly. */
-static void build_rope(float* tab, int max_len, int hd, float theta) {
-  int half = hd / 2;
+static void build_rope(float* tab, const oc_config* c) {
+  int half = c->head_dim / 2, max_len = c->max_seq_len;
   for (int p = 0; p < max_len; ++p)
     for (int i = 0; i < half; ++i) {
-      double inv = pow((double)theta, -2.0 * (double)i / (double)hd);
+      double inv = rope_inv_freq(c, i);
       double a = (double)p * inv;
       tab[((size_t)p * half + i) * 2 + 0] = (float)cos(a);
       tab[((size_t)p * half + i) * 2 + 1] = (float)sin(a);
@@ -146,7 +161,7 @@ oc_model* oc_model_create(const oc_config* cfg) {
     L->wd = (uint16_t*)xcalloc(d * (size_t)c->d_ff, 2);
   }
   m->rope = (float*)xcalloc((size_t)c->max_seq_len * (c->head_dim / 2) * 2, 4);
-  build_rope(m->rope, c->max_seq_len, c->head_dim, c->rope_theta);
+  build_rope(m->rope, c);
   m->dbg_hidden = (float*)xcalloc((size_t)(c->n_layers + 1) * d, 4);
   m->h = (float*)xcalloc(d, 4); m->xn = (float*)xcalloc(d, 4);
   m->q = (float*)xcalloc(qd, 4); m->k = (float*)xcalloc(kvd, 4); m->v = (float*)xcalloc(kvd, 4);

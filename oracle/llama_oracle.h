@@ -30,6 +30,9 @@ extern "C" {
 typedef struct oc_config {
   int32_t n_layers, d_model, n_heads, n_kv_heads, head_dim, d_ff, vocab_size, max_seq_len;
   float rope_theta, rms_eps;
+  /* "llama3" rotary scaling (HF transformers modeling_rope_utils.py _compute_llama3_parameters); rope_factor <= 1: none */
+  float rope_factor, rope_low_freq_factor, rope_high_freq_factor;
+  int32_t rope_original_max_pos;
 } oc_config;
 
 /* tensor kinds of the synthetic weight generator: key = layer * 16 + kind */

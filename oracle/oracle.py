@@ -25,7 +25,8 @@ NORM_SCALE = np.float32(1.0 / 4096.0)
 class OcConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_layers", "d_model", "n_heads", "n_kv_heads", "head_dim",
                                          "d_ff", "vocab_size", "max_seq_len")] + \
-               [("rope_theta", C.c_float), ("rms_eps", C.c_float)]
+               [("rope_theta", C.c_float), ("rms_eps", C.c_float), ("rope_factor", C.c_float), ("rope_low_freq_factor", C.c_float),
+                ("rope_high_freq_factor", C.c_float), ("rope_original_max_pos", C.c_int32)]
 
 
 class OcSampling(C.Structure):

@@ -7,8 +7,8 @@ architecture that IS importable here: HF transformers' LlamaForCausalLM / Mistra
 run on CPU in float32 over bf16-representable seeded weights.
 
   python tests/golden/make_golden.py      -> tests/golden/hf_tiny_llama.npz, hf_tiny_mistral.npz,
-                                              hf_tiny_llama3geom.npz, synth_kat.npz,
-                                              hf_tiny_llama_ckpt/ (config.json + model.safetensors)
+                                              hf_tiny_llama3geom.npz, hf_tiny_llama31rope.npz, synth_kat.npz,
+                                              hf_tiny_llama_ckpt/, hf_tiny_llama31rope_ckpt/ (config.json + model.safetensors)
 
 Fixtures are small (< 1 MB each) and committed; tests never import transformers.
 """
@@ -37,6 +37,12 @@ def hf_fixture(kind: str, path: Path, seed: int, ckpt_dir: Path | None = None):
         # on a small residual width: pins the oracle's RoPE pairing and GQA grouping for exactly that geometry
         cfg = dict(n_layers=2, d_model=128, n_heads=4, n_kv_heads=1, head_dim=128, d_ff=256, vocab_size=256,
                    max_seq_len=64, rope_theta=500000.0, rms_eps=1e-5)
+    elif kind == "llama31rope":
+        # Llama-3.1 / 3.2 style: "llama3" rotary scaling (scaled to a 16-position original context so that all three
+        # frequency bands — kept, blended, stretched — occur within 48 positions) and tied embeddings
+        cfg = dict(n_layers=2, d_model=128, n_heads=4, n_kv_heads=2, head_dim=64, d_ff=256, vocab_size=256,
+                   max_seq_len=64, rope_theta=500000.0, rms_eps=1e-5, rope_factor=8.0, rope_low_freq_factor=1.0,
+                   rope_high_freq_factor=4.0, rope_original_max_pos=16)
     else:
         cfg = dict(n_layers=2, d_model=128, n_heads=4, n_kv_heads=1, head_dim=64, d_ff=192, vocab_size=320,
                    max_seq_len=64, rope_theta=1e6, rms_eps=1e-5)
@@ -47,7 +53,16 @@ def hf_fixture(kind: str, path: Path, seed: int, ckpt_dir: Path | None = None):
                   head_dim=cfg["head_dim"],
                   attention_bias=False, hidden_act="silu")
     torch.manual_seed(seed)
-    if kind in ("llama", "llama3geom"):
+    n_ids = 24
+    if kind == "llama31rope":
+        common.pop("rope_theta")
+        common["tie_word_embeddings"] = True
+        common["rope_parameters"] = dict(rope_type="llama3", rope_theta=cfg["rope_theta"], factor=cfg["rope_factor"],
+                                         low_freq_factor=cfg["rope_low_freq_factor"], high_freq_factor=cfg["rope_high_freq_factor"],
+                                         original_max_position_embeddings=cfg["rope_original_max_pos"])
+        n_ids = 48
+        model = LlamaForCausalLM(LlamaConfig(mlp_bias=False, **common))
+    elif kind in ("llama", "llama3geom"):
         model = LlamaForCausalLM(LlamaConfig(mlp_bias=False, **common))
     else:
         model = MistralForCausalLM(MistralConfig(sliding_window=None, **common))
@@ -61,7 +76,7 @@ def hf_fixture(kind: str, path: Path, seed: int, ckpt_dir: Path | None = None):
                 p.copy_(0.08 * torch.randn_like(p))
             p.copy_(p.to(torch.bfloat16).to(torch.float32))       # bf16-representable weights
             tensors[name] = p.detach().clone()
-    ids = torch.tensor([[(i * 7919 + 13) % cfg["vocab_size"] for i in range(24)]])
+    ids = torch.tensor([[(i * 7919 + 13) % cfg["vocab_size"] for i in range(n_ids)]])
     with torch.no_grad():
         out = model(ids, output_hidden_states=True)
     logits = out.logits[0].float().numpy()
@@ -73,7 +88,7 @@ def hf_fixture(kind: str, path: Path, seed: int, ckpt_dir: Path | None = None):
     def b16(t):
         return oc.np_bf16_from_f32(t.numpy().astype(np.float32).ravel())
     save["embed"] = b16(tensors["model.embed_tokens.weight"])
-    save["lm_head"] = b16(tensors["lm_head.weight"])
+    save["lm_head"] = b16(tensors.get("lm_head.weight", tensors["model.embed_tokens.weight"]))   # tied: one matrix
     save["final_norm"] = b16(tensors["model.norm.weight"])
     for l in range(cfg["n_layers"]):
         pre = f"model.layers.{l}."
@@ -117,5 +132,7 @@ if __name__ == "__main__":
         hf_fixture("mistral", OUT / "hf_tiny_mistral.npz", 1)
     if only in (None, "llama3geom"):
         hf_fixture("llama3geom", OUT / "hf_tiny_llama3geom.npz", 2)
+    if only in (None, "llama31rope"):
+        hf_fixture("llama31rope", OUT / "hf_tiny_llama31rope.npz", 3, ckpt_dir=OUT / "hf_tiny_llama31rope_ckpt")
     if only in (None, "synth"):
         synth_kat(OUT / "synth_kat.npz")

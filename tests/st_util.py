@@ -50,3 +50,11 @@ def hf_tensors_from_fixture(z, cfg) -> dict:
         for k, nm in HF_NAMES.items():
             t[f"model.layers.{l}.{nm}"] = (z[f"L{l}.{k}"], shp[k])
     return t
+
+
+FLOAT_CFG_KEYS = ("rope_theta", "rms_eps", "rope_factor", "rope_low_freq_factor", "rope_high_freq_factor")
+
+
+def fixture_cfg(z) -> dict:
+    """Model config stored in a golden npz (tests/golden/make_golden.py) as name / value arrays."""
+    return {str(k): (float(v) if str(k) in FLOAT_CFG_KEYS else int(v)) for k, v in zip(z["cfg_keys"], z["cfg_vals"])}

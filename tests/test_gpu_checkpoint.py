@@ -9,14 +9,14 @@ import numpy as np
 import pytest
 
 from crowdllama_b200 import engine as eng
-from st_util import hf_tensors_from_fixture, write_safetensors
+from st_util import hf_tensors_from_fixture, write_safetensors, fixture_cfg
 
 pytestmark = pytest.mark.gpu
 G = Path(__file__).resolve().parent / "golden"
 
 
 def _fixture_cfg(z):
-    return {k: (float(v) if k in ("rope_theta", "rms_eps") else int(v)) for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    return fixture_cfg(z)
 
 
 def _logits(e, ids):
@@ -80,3 +80,22 @@ def test_hf_checkpoint_directory_loads_by_path_and_matches_golden(tmp_path):
     bad = dict(cfg); bad["d_ff"] = cfg["d_ff"] * 2
     with pytest.raises(eng.EngineError):
         eng.Engine(model=bad, weights_path=G / "hf_tiny_llama_ckpt" / "model.safetensors")
+
+
+def test_llama31_style_checkpoint_rope_scaling_and_tied_embeddings():
+    """A directory written by transformers for a Llama-3.1 / 3.2 style config — rope_type "llama3" and
+    tie_word_embeddings — loads by path (scaling parameters from config.json, lm_head from embed_tokens) and reproduces
+    the HF fp32 logits; without the scaling the same weights do not."""
+    z = np.load(G / "hf_tiny_llama31rope.npz")
+    cfg = fixture_cfg(z)
+    ids, ref = z["ids"], z["logits"]
+    rms = float(np.sqrt((ref ** 2).mean()))
+    with eng.Engine(weights_path=G / "hf_tiny_llama31rope_ckpt", decode_path=1) as e:
+        assert (e.cfg["rope_factor"], e.cfg["rope_original_max_pos"]) == (8.0, 16)
+        got = _logits(e, ids)
+    assert np.abs(got - ref).max() < 5e-2 * rms
+    assert (got.argmax(-1) == ref.argmax(-1)).mean() >= 0.9
+    plain = dict(cfg); plain["rope_factor"] = 0.0
+    with eng.Engine(model=plain, weights_path=G / "hf_tiny_llama31rope_ckpt" / "model.safetensors", decode_path=1) as e:
+        off = _logits(e, ids)
+    assert np.abs(off - ref).max() > 0.2 * rms                    # the fixture really exercises the scaling

@@ -4,6 +4,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+from st_util import fixture_cfg
+
 from crowdllama_b200 import engine as eng
 from oracle import oracle as oc
 
@@ -67,11 +69,11 @@ def test_tiny_engine_matches_oracle(decode_path, graph):
         assert e.stats()["kernel_launches"] > 0
 
 
-@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz"])
+@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz", "hf_tiny_llama31rope.npz"])
 def test_engine_matches_hf_golden(fixture):
     """The HF transformers logits (tests/golden/make_golden.py) pin the CUDA engine directly."""
     z = np.load(G / fixture)
-    cfg = {k: (float(v) if k in ("rope_theta", "rms_eps") else int(v)) for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    cfg = fixture_cfg(z)
     with eng.Engine(model=cfg, decode_path=1) as e:
         e.set_tensor(0, "EMBED", z["embed"])
         e.set_tensor(0, "LM_HEAD", z["lm_head"])

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(eng.EXPORTS), declared ^ set(eng.EXPORTS)
-    assert L.cl_abi_version() == 1
+    assert L.cl_abi_version() == 2
     assert b"GenerateRequest" in L.cl_strerror(eng.CL_ERR_BAD_MESSAGE)
 
 
@@ -503,8 +503,12 @@ def test_checkpoint_config_rejects_what_the_engine_does_not_implement(tmp_path):
     assert eng.checkpoint_info(variant("swa", sliding_window=32))[0]["max_seq_len"] == 32          # Mistral-7B-v0.1 style
     assert eng.checkpoint_info(variant("swa_none", sliding_window=None))[0]["max_seq_len"] == 64
     assert eng.checkpoint_info(variant("old_style", rope_parameters=None, rope_theta=500000.0, rope_scaling=None))[0]["rope_theta"] == 500000.0
+    c31 = eng.checkpoint_info(variant("llama31", rope_parameters={"rope_theta": 500000.0, "rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0,
+                                                                   "high_freq_factor": 4.0, "original_max_position_embeddings": 8192}))[0]
+    assert (c31["rope_factor"], c31["rope_low_freq_factor"], c31["rope_high_freq_factor"], c31["rope_original_max_pos"]) == (8.0, 1.0, 4.0, 8192)
     for name, changes, needle in [
-            ("llama31", dict(rope_parameters={"rope_theta": 500000.0, "rope_type": "llama3", "factor": 8.0}), "llama3"),
+            ("yarn", dict(rope_parameters={"rope_theta": 500000.0, "rope_type": "yarn", "factor": 8.0}), "yarn"),
+            ("llama3_incomplete", dict(rope_parameters={"rope_theta": 500000.0, "rope_type": "llama3", "factor": 8.0}), "llama3 needs"),
             ("linear", dict(rope_parameters=None, rope_theta=10000.0, rope_scaling={"type": "linear", "factor": 2.0}), "linear"),
             ("gelu", dict(hidden_act="gelu"), "hidden_act"),
             ("bias", dict(attention_bias=True), "attention_bias")]:

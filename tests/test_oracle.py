@@ -5,6 +5,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+from st_util import fixture_cfg
+
 from oracle import oracle as oc
 
 G = Path(__file__).resolve().parent / "golden"
@@ -12,7 +14,7 @@ G = Path(__file__).resolve().parent / "golden"
 
 def _load_hf(name):
     z = np.load(G / name)
-    cfg = {k: (float(v) if k in ("rope_theta", "rms_eps") else int(v)) for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    cfg = fixture_cfg(z)
     m = oc.Model(cfg)
     m.set_tensor(0, "EMBED", z["embed"])
     m.set_tensor(0, "LM_HEAD", z["lm_head"])
@@ -23,7 +25,7 @@ def _load_hf(name):
     return z, cfg, m
 
 
-@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz", "hf_tiny_llama3geom.npz"])
+@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz", "hf_tiny_llama3geom.npz", "hf_tiny_llama31rope.npz"])
 def test_oracle_matches_hf_fp32(fixture):
     """act_rounding=0 (pure fp32 activations) must reproduce HF float32 logits: pins RoPE pairing,
     GQA head mapping, norm placement, SwiGLU and the untied LM head."""
@@ -38,7 +40,7 @@ def test_oracle_matches_hf_fp32(fixture):
     assert (logits.argmax(-1) == ref.argmax(-1)).all()
 
 
-@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz", "hf_tiny_llama3geom.npz"])
+@pytest.mark.parametrize("fixture", ["hf_tiny_llama.npz", "hf_tiny_mistral.npz", "hf_tiny_llama3geom.npz", "hf_tiny_llama31rope.npz"])
 def test_oracle_v1_rounding_close_to_hf(fixture):
     """cl-llama v1 numerics (bf16 rounding points) stay within a bf16-sized band of HF fp32."""
     z, cfg, m = _load_hf(fixture)
