@@ -161,6 +161,13 @@ PRESETS = {
                        vocab_size=32000, max_seq_len=8192 + 512, rope_theta=1e6, rms_eps=1e-5),
     "tinyllama-1.1b": dict(n_layers=22, d_model=2048, n_heads=32, n_kv_heads=4, head_dim=64, d_ff=5632,
                            vocab_size=32000, max_seq_len=2048, rope_theta=1e4, rms_eps=1e-5),
+    # "llama3" rotary frequency scaling (Llama-3.1 / 3.2), tied embeddings in the real checkpoints
+    "llama3.1-8b": dict(n_layers=32, d_model=4096, n_heads=32, n_kv_heads=8, head_dim=128, d_ff=14336, vocab_size=128256,
+                        max_seq_len=32768, rope_theta=5e5, rms_eps=1e-5, rope_factor=8.0, rope_low_freq_factor=1.0,
+                        rope_high_freq_factor=4.0, rope_original_max_pos=8192),
+    "llama3.2-1b": dict(n_layers=16, d_model=2048, n_heads=32, n_kv_heads=8, head_dim=64, d_ff=8192, vocab_size=128256,
+                        max_seq_len=8192, rope_theta=5e5, rms_eps=1e-5, rope_factor=32.0, rope_low_freq_factor=1.0,
+                        rope_high_freq_factor=4.0, rope_original_max_pos=8192),
     "tiny-test": dict(n_layers=2, d_model=256, n_heads=4, n_kv_heads=2, head_dim=64, d_ff=512,
                       vocab_size=512, max_seq_len=512, rope_theta=1e4, rms_eps=1e-5),
 }

@@ -265,10 +265,13 @@ def test_engine_with_a_tokenizer_json(name):
             e.load_tokenizer(gold)
 
 
-@pytest.mark.parametrize("preset", ["tinyllama-1.1b"])
+@pytest.mark.parametrize("preset", ["tinyllama-1.1b", "llama3.2-1b"])
 def test_tinyllama_shapes_match_oracle(preset):
+    """Model shapes outside the persistent kernels (head_dim 64): per-op decode kernels + tcgen05 prefill.  llama3.2-1b
+    adds the "llama3" rotary frequency scaling and a 128K vocabulary (6 layers of the 16 keep the test short)."""
     cfg = dict(oc.PRESETS[preset])
     cfg["max_seq_len"] = 256
+    cfg["n_layers"] = min(cfg["n_layers"], 22 if preset == "tinyllama-1.1b" else 6)
     m = oc.Model(cfg, seed=1234)
     mc = dict(cfg)
     with eng.Engine(model=mc, seed=1234, max_batch=1) as e:
