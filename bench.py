@@ -129,9 +129,9 @@ class ClockSampler:
 
 
 # ---- CPU arms (the only places that execute oracle/) ---------------------------------------------------------------
-def cpu_baseline(steps_cap_s=25.0, max_tokens=8, warm=1):
+def cpu_baseline(steps_cap_s=12.0, max_tokens=64, warm=2):
     """The CPU oracle port on this box's host cores: Llama-3-8B shapes, synthetic weights, KV cache
-    pre-filled to 4096 positions (timing only), a few greedy decode steps."""
+    pre-filled to 4096 positions (timing only), greedy decode steps for about 12 s (bounded sample of the workload)."""
     from oracle import oracle as oc
     cfg = dict(oc.PRESETS[PRESET])
     cfg["max_seq_len"] = CTX + 64
