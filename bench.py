@@ -45,7 +45,7 @@ MODEL_NAME = "llama3:8b"
 CTX = 4096
 SEED = 1234
 METRIC = "decode tokens/sec (Llama-3-8B bf16, seq 4K; aggregate over local worker peers)"
-BOX_MAX_BATCH = 32
+BOX_MAX_BATCH = int(os.environ.get("CL_BOX_MAX_BATCH", "64"))   # sequences per worker peer's decode batch (r2s: 4.6 ms per step at 64 rows, 4.0 at 32)
 BOX_GEN = 256
 
 
@@ -219,24 +219,72 @@ def _wait_port(addr, timeout_s):
     return False
 
 
-def run_box_client(args):
-    """Gateway stand-in + closed-loop HTTP clients against already running worker peers.  Prints one JSON object."""
+BOX_PROMPT = ("Explain, step by step, why the sky appears blue during the day and red at sunset, and what changes on Mars. " * 2)[:118]
+BOX_SHARD_CLIENTS = 128          # closed-loop clients per gateway stand-in process (one Python GIL each)
+
+
+def run_box_shard(addrs, port, concurrency, n_req, first_id, start_at):
+    """One gateway stand-in (own metadata table, FindBestWorker routing) + `concurrency` closed-loop clients sending
+    `n_req` chats through it.  Returns raw observations; the caller aggregates over shards."""
     import urllib.request
+    from crowdllama_b200 import gateway
+    gw = gateway.make_server(addrs, port=port)
+    threading.Thread(target=gw.serve_forever, daemon=True).start()
+    url = f"http://127.0.0.1:{port}/api/chat"
+    lat, errs = [], []
+
+    def one(i):
+        body = json.dumps({"model": MODEL_NAME, "messages": [{"role": "user", "content": f"{i:04d} {BOX_PROMPT}"}], "stream": False}).encode()
+        t0 = time.time()
+        try:
+            with urllib.request.urlopen(urllib.request.Request(url, body, {"Content-Type": "application/json"}), timeout=900) as r:
+                o = json.loads(r.read())
+            assert o["done"] and o["model"] == MODEL_NAME and o["message"]["role"] == "assistant" and o["message"]["content"]
+            lat.append(time.time() - t0)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(str(ex))
+    while time.time() < start_at:
+        time.sleep(0.005)
+    sem = threading.Semaphore(concurrency)
+    threads = []
+    t0 = time.time()
+    for i in range(n_req):
+        sem.acquire()
+        th = threading.Thread(target=lambda i=i: (one(first_id + i), sem.release()))
+        th.start()
+        threads.append(th)
+    for th in threads:
+        th.join()
+    t1 = time.time()
+    res = {"lat": lat, "errors": errs[:3], "n_err": len(errs), "t0": t0, "t1": t1, "counts": dict(gw.counts),
+           "advertised": {r.peer_id: [r.tokens_throughput, r.load] for r in gw.table.peers.values()}}
+    gw.table.stop()
+    gw.shutdown()
+    gw.server_close()
+    return res
+
+
+def run_box_client(args):
+    """Load generator of the box leg: gateway stand-ins + closed-loop HTTP clients against already running worker peers.
+    Up to BOX_SHARD_CLIENTS clients share one gateway stand-in process; larger scenarios are sharded over several such
+    processes (every shard routes with FindBestWorker over its own metadata table), because one Python process tops out
+    near 500 req/s (measured against instant mock peers) — below what eight peers deliver.  Prints one JSON object."""
     from crowdllama_b200 import gateway
     from crowdllama_b200.worker import STOP_PROTOCOL, STATS_PROTOCOL
     addrs = [("127.0.0.1", args.base_port + i) for i in range(args.workers)]
+    if args.box_shard:                                      # child process: one shard of one scenario
+        conc, n_req, first_id, port, start_at = args.box_shard.split(",")
+        print(json.dumps(run_box_shard(addrs, int(port), int(conc), int(n_req), int(first_id), float(start_at))), flush=True)
+        return 0
     out = {"workers": args.workers, "gen_tokens": BOX_GEN, "max_batch_per_worker": BOX_MAX_BATCH, "router": "find_best_worker (manager.go:338-387), "
-           "metadata refreshed every 2 s, load-independent capacity in half-octave buckets + two-level load (router.py)"}
+           "metadata refreshed every 2 s, load-independent capacity in half-octave buckets + two-level load (router.py)",
+           "clients_per_gateway_process": BOX_SHARD_CLIENTS}
     try:
         for a in addrs:
             if not _wait_port(a, 600):
                 raise RuntimeError(f"worker {a} did not come up")
-        gw = gateway.make_server(addrs, port=args.base_port - 1)
-        threading.Thread(target=gw.serve_forever, daemon=True).start()
-        url = f"http://127.0.0.1:{args.base_port - 1}/api/chat"
-        prompt = ("Explain, step by step, why the sky appears blue during the day and red at sunset, and what changes on Mars. " * 2)[:118]
-        for a in addrs:                                  # warm every worker directly: CUDA graphs of the batch sizes, prefill workspace
-            th = [threading.Thread(target=gateway.request_inference, args=(a, MODEL_NAME, f"warm {i} " + prompt, False)) for i in range(BOX_MAX_BATCH)]
+        for a in addrs:                                  # warm every worker directly: prefill workspaces, every batch size once
+            th = [threading.Thread(target=gateway.request_inference, args=(a, MODEL_NAME, f"warm {i} " + BOX_PROMPT, False)) for i in range(BOX_MAX_BATCH)]
             [t.start() for t in th]
             [t.join() for t in th]
 
@@ -252,34 +300,35 @@ def run_box_client(args):
             return res
 
         def scenario(concurrency, n_req):
-            lat, errs = [], []
+            n_sh = max(1, min(8, -(-concurrency // BOX_SHARD_CLIENTS)))
             st0 = worker_stats()
-
-            def one(i):
-                body = json.dumps({"model": MODEL_NAME, "messages": [{"role": "user", "content": f"{i:04d} {prompt}"}], "stream": False}).encode()
-                t0 = time.time()
-                try:
-                    with urllib.request.urlopen(urllib.request.Request(url, body, {"Content-Type": "application/json"}), timeout=900) as r:
-                        o = json.loads(r.read())
-                    assert o["done"] and o["model"] == MODEL_NAME and o["message"]["role"] == "assistant" and o["message"]["content"]
-                    lat.append(time.time() - t0)
-                except Exception as ex:  # noqa: BLE001
-                    errs.append(str(ex))
-            with gw.lock:
-                gw.counts.clear()
-            sem = threading.Semaphore(concurrency)
-            threads = []
-            t0 = time.time()
-            for i in range(n_req):
-                sem.acquire()
-                th = threading.Thread(target=lambda i=i: (one(i), sem.release()))
-                th.start()
-                threads.append(th)
-            for th in threads:
-                th.join()
-            dt = time.time() - t0
-            ok = len(lat)
+            if n_sh == 1:
+                parts = [run_box_shard(addrs, args.base_port - 1, concurrency, n_req, 0, time.time())]
+            else:
+                start_at = time.time() + 3.0                # the shards import, probe the peers, then start together
+                procs, first = [], 0
+                for i in range(n_sh):
+                    c = concurrency // n_sh + (1 if i < concurrency % n_sh else 0)
+                    r = n_req // n_sh + (1 if i < n_req % n_sh else 0)
+                    procs.append(subprocess.Popen([sys.executable, str(ROOT / "bench.py"), "--box-client", "--workers", str(args.workers), "--base-port", str(args.base_port),
+                                                   "--box-shard", f"{c},{r},{first},{args.base_port - 1 - i},{start_at}"],
+                                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""}))
+                    first += r
+                parts = []
+                for pr in procs:
+                    so, se = pr.communicate(timeout=1200)
+                    if pr.returncode != 0 or not so.strip():
+                        raise RuntimeError(f"box shard failed: {se[-400:]}")
+                    parts.append(json.loads(so.strip().splitlines()[-1]))
             st1 = worker_stats()
+            lat = [x for p_ in parts for x in p_["lat"]]
+            dt = max(p_["t1"] for p_ in parts) - min(p_["t0"] for p_ in parts)
+            counts, adv = {}, {}
+            for p_ in parts:
+                for k, v in p_["counts"].items():
+                    counts[k] = counts.get(k, 0) + v
+                adv.update(p_["advertised"])
+            ok = len(lat)
             acc = {k: sum(b.get(k, 0) - a.get(k, 0) for a, b in zip(st0, st1)) for k in ("tokens_generated", "requests_completed", "preemptions", "sched_decode_steps",
                                                                             "sched_decode_ns", "sched_prefill_calls", "sched_prefill_tokens", "sched_prefill_ns")}
             sched = {"mean_batch": round(acc["tokens_generated"] / max(acc["sched_decode_steps"], 1), 2),
@@ -288,24 +337,23 @@ def run_box_client(args):
                      "prefill_tokens_per_call": round(acc["sched_prefill_tokens"] / max(acc["sched_prefill_calls"], 1), 1),
                      "decode_s_per_worker": round(acc["sched_decode_ns"] * 1e-9 / len(addrs), 3),
                      "prefill_s_per_worker": round(acc["sched_prefill_ns"] * 1e-9 / len(addrs), 3), "preemptions": acc["preemptions"]}
-            return {"scheduler": sched, "concurrency": concurrency, "requests": n_req, "ok": ok, "errors": errs[:3], "wall_s": round(dt, 3),
-                    "req_per_s": round(ok / dt, 3), "tok_per_s": round(ok * BOX_GEN / dt, 1),
-                    "p50_latency_s": round(float(np.median(lat)), 3) if lat else None,
-                    "per_worker_requests": dict(sorted(gw.counts.items())),
-                    "advertised_at_end": {r.peer_id: [r.tokens_throughput, r.load] for r in sorted(gw.table.peers.values(), key=lambda r: r.peer_id)}}
-        # BASELINE.json configs[3]: 64 concurrent chats.  Long enough for request-level statistics: >= 6 waves per worker slot.
+            return {"scheduler": sched, "concurrency": concurrency, "requests": n_req, "ok": ok, "errors": [e for p_ in parts for e in p_["errors"]][:3],
+                    "wall_s": round(dt, 3), "req_per_s": round(ok / dt, 3), "tok_per_s": round(ok * BOX_GEN / dt, 1),
+                    "p50_latency_s": round(float(np.median(lat)), 3) if lat else None, "gateway_processes": n_sh,
+                    "per_worker_requests": dict(sorted(counts.items())), "advertised_at_end": dict(sorted(adv.items()))}
         # untimed warm-up THROUGH the gateway (the first scenario otherwise pays for cold HTTP / thread / routing paths and
         # starts desynchronised: 21.2 req/s first against 25.0 for the same scenario run later, r2o)
-        out["warmup"] = {k: v for k, v in scenario(BOX_MAX_BATCH * args.workers, 2 * BOX_MAX_BATCH * args.workers).items() if k in ("requests", "ok", "wall_s")}
+        out["warmup"] = {k: v for k, v in scenario(min(BOX_MAX_BATCH * args.workers, BOX_SHARD_CLIENTS), 2 * BOX_MAX_BATCH * args.workers).items()
+                         if k in ("requests", "ok", "wall_s")}
+        # BASELINE.json configs[3]: 64 concurrent chats.  Long enough for request-level statistics: >= 6 waves per worker slot.
         for i, tag in enumerate(os.environ.get("CL_BOX_SCENARIOS", "config4,saturated").split(",")):   # the default is the contract
             key = tag if tag not in out else f"{tag}#{i}"
             if tag == "config4":
-                out[key] = scenario(64, max(192, 96 * args.workers))
+                out[key] = scenario(64, max(384, 96 * args.workers))
             elif tag == "saturated":
                 out[key] = scenario(BOX_MAX_BATCH * args.workers, 6 * BOX_MAX_BATCH * args.workers)
             elif tag.startswith("c"):                                         # c<concurrency>: diagnostics
                 out[key] = scenario(int(tag[1:]), 6 * BOX_MAX_BATCH * args.workers)
-        gw.shutdown()
     except Exception as ex:  # noqa: BLE001
         out["error"] = repr(ex)
     for a in addrs:
@@ -514,6 +562,7 @@ def main():
     ap.add_argument("--no-box", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--box-client", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--box-shard", default="", help=argparse.SUPPRESS)
     ap.add_argument("--workers", type=int, default=1, help=argparse.SUPPRESS)
     ap.add_argument("--base-port", type=int, default=21001, help=argparse.SUPPRESS)
     args = ap.parse_args()

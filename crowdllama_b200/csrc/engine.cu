@@ -32,6 +32,7 @@ Engine::~Engine() {
   stop_scheduler();
   if (stream_) cudaStreamSynchronize(stream_);
   for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+  if (step_done_ev_) cudaEventDestroy(step_done_ev_);
   for (void* p : allocs_) cudaFree(p);
   if (h_logits_pinned_) cudaFreeHost(h_logits_pinned_);
   if (h_ids_pinned_) cudaFreeHost(h_ids_pinned_);
@@ -331,8 +332,9 @@ int Engine::alloc_state() {
     CL_CUDA_OK(cudaMemsetAsync(d_timeline_, 0, (size_t)(cfg.n_layers * 5 + 1) * 4 * 8, stream_));
   }
   batch_gemm_min_ = env_int("CL_BATCH_GEMM_MIN", 2);
+  // token tile of the projections = 32 / 64 / 128 rows (gemm_tcgen05.cu picks it from the step's batch size)
   use_batch_gemm_ = env_int("CL_BATCH_GEMM", 1) != 0 && max_batch_ >= 2 && gemm_tcgen05_supported(max_batch_, cfg.d_model, cfg.d_model) &&
-                    max_batch_ <= 32;
+                    max_batch_ <= 128;
   if (use_batch_gemm_) {
     bws_.reset(new BatchWs());
     const size_t Bm = std::max(max_batch_, 32), widest = std::max<size_t>((size_t)qkv_dim_, std::max<size_t>(2 * (size_t)cfg.d_ff, d));   // 32 rows: the persistent batched kernel's token tile
@@ -351,7 +353,7 @@ int Engine::alloc_state() {
     DMALLOC(bws_->part, part_floats * 4);
     DMALLOC(bws_->logits, Bm * (size_t)cfg.vocab_size * 4);
     // persistent batched step: tensor maps of every weight matrix (device array) and of the three token operands
-    use_batch_mega_ = env_int("CL_BATCH_MEGA", kDefaultBatchMega) != 0 && cfg.head_dim == 128 && page_size_ == 32 &&
+    use_batch_mega_ = env_int("CL_BATCH_MEGA", kDefaultBatchMega) != 0 && cfg.head_dim == 128 && page_size_ == 32 && max_batch_ <= 32 &&
                       batch_mega_supported(cfg.d_model, cfg.d_ff, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads, page_size_, cfg.vocab_size);
     if (use_batch_mega_) {
       auto kbp = [&](int N, int K) { const int nkb = K / 64, sp = pick_splits(N, K); return (nkb + sp - 1) / sp; };

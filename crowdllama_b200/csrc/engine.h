@@ -197,6 +197,8 @@ class Engine {
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaEvent_t step_done_ev_ = nullptr;     // scheduler: blocking-sync event behind every batched step (scheduler.cpp)
+  bool sched_blocking_sync_ = true;
   int page_size_ = 32, max_batch_ = 8, max_seqs_ = 8, n_pages_ = 0, max_pages_per_seq_ = 0;
   int gemv_variant_ = 1, nsplit_ = 16;
   bool use_graph_ = true, use_pdl_ = true, skip_attn_ = false;

@@ -207,6 +207,14 @@ void Engine::scheduler_main() {
   std::vector<int> last_slots;
   {
     std::lock_guard<std::mutex> elk(mu_);
+    {
+      const char* v = getenv("CL_SCHED_BLOCKING_SYNC");
+      sched_blocking_sync_ = !v || atoi(v) != 0;
+    }
+    if (sched_blocking_sync_ && !step_done_ev_ && cudaEventCreateWithFlags(&step_done_ev_, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      step_done_ev_ = nullptr;
+    }
     precapture_graphs();   // every batch size's step graph up front, not inside the first steps that meet it
   }
   while (true) {
@@ -340,7 +348,12 @@ void Engine::scheduler_main() {
     int rc = run_step_graph(B);
     if (rc == CL_OK) {
       cudaMemcpyAsync(toks.data(), d_tok_, (size_t)max_seqs_ * 4, cudaMemcpyDeviceToHost, stream_);
-      if (cudaStreamSynchronize(stream_) != cudaSuccess) rc = CL_ERR_CUDA;
+      // Batched steps last 3.5-6 ms: wait on a blocking-sync event instead of spinning in cudaStreamSynchronize, so that
+      // eight worker processes on one box do not burn eight host cores (the box's cgroup quota is 16) while their GPUs
+      // work.  Single-sequence steps (2.8 ms, latency matters) keep the spinning wait.
+      if (B >= 2 && sched_blocking_sync_ && step_done_ev_) {
+        if (cudaEventRecord(step_done_ev_, stream_) != cudaSuccess || cudaEventSynchronize(step_done_ev_) != cudaSuccess) rc = CL_ERR_CUDA;
+      } else if (cudaStreamSynchronize(stream_) != cudaSuccess) rc = CL_ERR_CUDA;
     }
     if (rc) {
       const std::string err = get_last_error();

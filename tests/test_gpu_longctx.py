@@ -129,12 +129,13 @@ def _compare_steps(name, e, seqs, toks, ref_logits, tol, batched):
     return worst, mism
 
 
-def _run_fake_filled(name, e, m, lens, n_layers, batched, ref_key=None):
+def _run_fake_filled(name, e, m, lens, n_layers, batched, ref_key=None, n_steps=None):
+    n_steps = n_steps or N_STEPS
     tol = tol_for(n_layers)
     first = [17 + 101 * b for b in range(len(lens))]
     key = ref_key or (name.split("/")[0] + ":" + name,)
     if key not in _Cache.refs:
-        _Cache.refs[key] = _oracle_steps(m, lens, first, N_STEPS)
+        _Cache.refs[key] = _oracle_steps(m, lens, first, n_steps)
     toks, ref = _Cache.refs[key]
     seqs = []
     for n in lens:
@@ -146,8 +147,8 @@ def _run_fake_filled(name, e, m, lens, n_layers, batched, ref_key=None):
     finally:
         for s in seqs:
             e.seq_free(s)
-    print(f"{name}: lens {lens}: max |dlogit| {worst:.4f} (tolerance {tol:.3f}), near-tie id mismatches {mism} over {N_STEPS} steps")
-    _record(name, lens=list(lens), n_layers=n_layers, steps=N_STEPS, max_abs_dlogit=round(worst, 5), tol=round(tol, 4),
+    print(f"{name}: lens {lens}: max |dlogit| {worst:.4f} (tolerance {tol:.3f}), near-tie id mismatches {mism} over {n_steps} steps")
+    _record(name, lens=list(lens), n_layers=n_layers, steps=n_steps, max_abs_dlogit=round(worst, 5), tol=round(tol, 4),
             near_tie_mismatches=mism)
     return worst
 
@@ -222,7 +223,7 @@ def test_llama3_8b_full_batched_b8_long_context():
 @pytest.mark.parametrize("B", [2, 3, 16])
 @pytest.mark.parametrize("persistent", ["0", "1"])
 def test_llama3_8b_layers_batched_long_context(persistent, B):
-    """B = 2 (GEMV kernels, two sequences), B = 3 and 16 (tensor-core path: KV splits 6 and 1 per sequence) at
+    """B = 2, 3 and 16 (tensor-core path: KV splits 9, 6 and 1 per sequence) at
     Llama-3-8B layer shapes, contexts up to 8188 tokens, 1-token and page-boundary sequences.  persistent = 1: the
     whole batched step as one persistent kernel (decode_mega_batch.cu, CL_BATCH_MEGA=1) on the same inputs."""
     cfg = _cfg("llama3-8b", n_layers=4)
@@ -233,6 +234,19 @@ def test_llama3_8b_layers_batched_long_context(persistent, B):
                      ref_key=("l3x4-ref", B))
     if B == 16 and persistent == "1":
         _Cache.drop("l3x4")
+
+
+@pytest.mark.parametrize("B", [40, 100])
+def test_llama3_8b_layers_wide_batch(B):
+    """Batched steps beyond 32 sequences: the projections switch to the 64- and 128-row token tile.  Short, mixed
+    contexts (0 ... 600 tokens, page boundaries included) keep the CPU checker's share small."""
+    cfg = _cfg("llama3-8b", n_layers=4)
+    m = _Cache.model("l3x4w", cfg, 99)
+    e = _Cache.engine("l3x4-wide", cfg, 99, max_batch=100, max_seqs=100)
+    lens = [(i * 97 + 13) % 600 if i % 7 else (31, 32, 33, 0, 64, 95, 96)[(i // 7) % 7] for i in range(B)]
+    _run_fake_filled(f"llama3-8b/4L/B{B}/batched-wide", e, m, lens, 4, batched=True, ref_key=("l3x4w-ref", B), n_steps=3)
+    if B == 100:
+        _Cache.drop("l3x4w")
 
 
 # ---- Mistral-7B shapes at 8K (BASELINE.json configs[4]) ------------------------------------------------------------

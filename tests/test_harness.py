@@ -178,7 +178,8 @@ def test_bench_box_load_generator_against_two_mock_peers():
         assert out.returncode == 0, out.stderr
         res = json.loads(out.stdout.strip().splitlines()[-1])
         assert "error" not in res, res
-        for key, conc in (("config4", 64), ("saturated", 64)):
+        import bench
+        for key, conc in (("config4", 64), ("saturated", 2 * bench.BOX_MAX_BATCH)):
             sc = res[key]
             assert sc["concurrency"] == conc and sc["ok"] == sc["requests"] and not sc["errors"] and sc["req_per_s"] > 0
             assert sum(sc["per_worker_requests"].values()) == sc["requests"] and len(sc["per_worker_requests"]) == 2
