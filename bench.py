@@ -226,33 +226,46 @@ BOX_SHARD_CLIENTS = 128          # closed-loop clients per gateway stand-in proc
 def run_box_shard(addrs, port, concurrency, n_req, first_id, start_at):
     """One gateway stand-in (own metadata table, FindBestWorker routing) + `concurrency` closed-loop clients sending
     `n_req` chats through it.  Returns raw observations; the caller aggregates over shards."""
-    import urllib.request
     from crowdllama_b200 import gateway
     gw = gateway.make_server(addrs, port=port)
     threading.Thread(target=gw.serve_forever, daemon=True).start()
-    url = f"http://127.0.0.1:{port}/api/chat"
     lat, errs = [], []
+    nxt, nxt_lock = [0], threading.Lock()
 
-    def one(i):
-        body = json.dumps({"model": MODEL_NAME, "messages": [{"role": "user", "content": f"{i:04d} {BOX_PROMPT}"}], "stream": False}).encode()
-        t0 = time.time()
-        try:
-            with urllib.request.urlopen(urllib.request.Request(url, body, {"Content-Type": "application/json"}), timeout=900) as r:
-                o = json.loads(r.read())
-            assert o["done"] and o["model"] == MODEL_NAME and o["message"]["role"] == "assistant" and o["message"]["content"]
-            lat.append(time.time() - t0)
-        except Exception as ex:  # noqa: BLE001
-            errs.append(str(ex))
+    def client():
+        # one closed-loop client = one thread with one keep-alive HTTP connection (the gateway stand-in speaks HTTP/1.1):
+        # no thread or connection set-up per request on either side of the gateway
+        import http.client
+        conn = None
+        while True:
+            with nxt_lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= n_req:
+                break
+            body = json.dumps({"model": MODEL_NAME, "messages": [{"role": "user", "content": f"{first_id + i:04d} {BOX_PROMPT}"}], "stream": False}).encode()
+            t0 = time.time()
+            try:
+                if conn is None:
+                    conn = http.client.HTTPConnection("127.0.0.1", port, timeout=900)
+                conn.request("POST", "/api/chat", body, {"Content-Type": "application/json"})
+                o = json.loads(conn.getresponse().read())
+                assert o["done"] and o["model"] == MODEL_NAME and o["message"]["role"] == "assistant" and o["message"]["content"]
+                lat.append(time.time() - t0)
+            except Exception as ex:  # noqa: BLE001
+                errs.append(str(ex))
+                try:
+                    conn and conn.close()
+                finally:
+                    conn = None
+        if conn:
+            conn.close()
     while time.time() < start_at:
         time.sleep(0.005)
-    sem = threading.Semaphore(concurrency)
-    threads = []
+    threads = [threading.Thread(target=client) for _ in range(min(concurrency, n_req))]
     t0 = time.time()
-    for i in range(n_req):
-        sem.acquire()
-        th = threading.Thread(target=lambda i=i: (one(first_id + i), sem.release()))
+    for th in threads:
         th.start()
-        threads.append(th)
     for th in threads:
         th.join()
     t1 = time.time()
