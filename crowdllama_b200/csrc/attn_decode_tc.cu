@@ -10,6 +10,9 @@
 //   probabilities), then the warp merge, the split partial, and the last split to arrive combines
 //   (same tail as attn_decode_kernel: fp32 output for the GEMV path, bf16 copy = X operand of the o-projection).
 // Shapes: head_dim 128, 4 query heads per kv head, page 32 (Llama-3-8B / Mistral-7B); others use the CUDA-core kernel.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -17,8 +20,13 @@ namespace cl {
 
 namespace {
 
-constexpr int NW = 8, HD = 128, REP = 4, P = 32;
-constexpr int NS = 4;                      // ring slots of 32 KB
+constexpr int HD = 128, REP = 4, P = 32;
+// Two shapes of the same kernel (template parameters NW = consumer warps, NS = ring slots of 32 KB, MINB = CTAs per SM):
+//   <8, 4, 1>  one CTA per SM, 8 warps, 128 KB of KV in flight — few (kv head, split, sequence) items, long chains;
+//   <4, 2, 2>  two CTAs per SM, 4 warps each, 2 x 64 KB in flight — more items than SMs (B >= 19):
+//              the prologue (block table, q) and the epilogue (warp merge, split combine) of one CTA overlap the page
+//              loop of its neighbour.  B = 128 at ctx 256 is 1024 items of ~7 us each: 7 waves become 3.5
+//              (step 5.94 -> 5.56 ms; B = 64: 4.56 -> 4.31; B = 32: 3.95 -> 3.84).
 constexpr uint32_t SLOT = 32 * 1024;
 constexpr int MAXS = 64;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -28,7 +36,8 @@ struct TcArgs {
   long long layer_row0;                    // first row of this layer in the pool-wide tensor maps
 };
 
-__global__ void __launch_bounds__(288, 1)
+template <int NW, int NS, int MINB>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB)
 attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap, const TcArgs t) {
   const AttnDecodeArgs& a = t.a;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -197,7 +206,7 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
       red_acc[(warp * REP + rq) * HD + nd * 8 + 2 * cq + 1] = o[nd][1];
     }
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
 
   // ---- CTA partial (merge of the 8 warps) -> global, or straight to the output when there is one split
   float* part = a.part + ((((size_t)slot * a.n_kv + g) * a.nsplit + sp) * REP) * (HD + 2);
@@ -227,14 +236,14 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
   }
   if (a.nsplit == 1) return;
   __threadfence();
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
   if (tid == 0) {
     unsigned* cnt = a.counters + (size_t)slot * a.n_kv + g;
     const unsigned old = atomicAdd(cnt, 1u);
     *is_last_s = (old == (unsigned)a.nsplit - 1u);
     if (*is_last_s) *cnt = 0u;  // re-arm for the next launch (graph replay)
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
   if (!*is_last_s) return;
   __threadfence();
 
@@ -247,7 +256,7 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
     cm_s[sidx * REP + hh] = __ldcg(ph);
     cw_s[sidx * REP + hh] = __ldcg(ph + 1);   // l for now
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
   if (tid < REP) {
     float M = -INFINITY;
     for (int sidx = 0; sidx < ns; ++sidx) M = fmaxf(M, cm_s[sidx * REP + tid]);
@@ -260,7 +269,7 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
     }
     cL_s[tid] = L;
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
   for (int e = tid; e < REP * HD; e += NW * 32) {
     const int hh = e / HD, i = e % HD;
     float A = 0.f;
@@ -278,23 +287,41 @@ bool attn_decode_tc_supported(int n_heads, int n_kv, int head_dim, int page_size
   return head_dim == HD && n_kv > 0 && n_heads == REP * n_kv && page_size == P && nsplit >= 1 && nsplit <= MAXS;
 }
 
-int launch_attn_decode_tc(const AttnDecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, long long layer_row0, cudaStream_t st,
-                          bool pdl) {
-  if (!attn_decode_tc_supported(a.n_heads, a.n_kv, a.head_dim, a.page_size, a.nsplit)) return -1;
+namespace {
+template <int NW, int NS, int MINB>
+int launch_variant(const AttnDecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, long long layer_row0, cudaStream_t st, bool pdl) {
   constexpr size_t smem = (size_t)NS * SLOT + 2 * NS * 8 + (2 * NW * REP + NW * REP * HD + 2 * MAXS * REP + REP + 4) * 4 + 1024 + 64;
+  auto kern = attn_decode_tc_kernel<NW, NS, MINB>;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(attn_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     attr = true;
   }
   TcArgs t{a, layer_row0};
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(a.n_kv, a.nsplit, a.batch); cfg.blockDim = dim3(288); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(a.n_kv, a.nsplit, a.batch); cfg.blockDim = dim3((NW + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute la[1];
   la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   la[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = la; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, attn_decode_tc_kernel, kmap, vmap, t) == cudaSuccess ? 1 : -1;
+  return cudaLaunchKernelEx(&cfg, kern, kmap, vmap, t) == cudaSuccess ? 1 : -1;
+}
+}  // namespace
+
+// KV splits per sequence and kernel shape for a batched step of `batch` sequences: one wave of 8-warp CTAs while the
+// items fit the machine, otherwise the 4-warp shape with two CTAs per SM (CL_BATCH_ATTN_SMALL = 0 / 1 forces one).
+void attn_decode_tc_plan(int n_kv, int batch, int nsplit_max, int cta_budget, int* nsplit, int* small) {
+  static const int force = getenv("CL_BATCH_ATTN_SMALL") ? atoi(getenv("CL_BATCH_ATTN_SMALL")) : -1;
+  const int items = n_kv * batch;
+  *small = force >= 0 ? (force != 0) : (items > cta_budget);   // r2u: B = 16 (128 items) is faster on the 8-warp shape, B >= 32 on this one
+  const int budget = *small ? 2 * cta_budget : cta_budget;
+  *nsplit = std::max(1, std::min(std::min(nsplit_max, MAXS), budget / std::max(items, 1)));
+}
+
+int launch_attn_decode_tc(const AttnDecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, long long layer_row0, cudaStream_t st,
+                          bool pdl) {
+  if (!attn_decode_tc_supported(a.n_heads, a.n_kv, a.head_dim, a.page_size, a.nsplit)) return -1;
+  return a.tc_small ? launch_variant<4, 2, 2>(a, kmap, vmap, layer_row0, st, pdl) : launch_variant<8, 4, 1>(a, kmap, vmap, layer_row0, st, pdl);
 }
 
 }  // namespace cl

@@ -628,7 +628,8 @@ int Engine::enqueue_step_batched(int B) {
     a.out = d_attn_; a.out_stride = q_dim_; a.out_bf16 = w.attn; a.part = d_attn_part_; a.counters = d_attn_cnt_;   // bf16 copy = X of the o-projection
     a.slots = d_slots_; a.batch = B; a.n_heads = cfg.n_heads; a.n_kv = cfg.n_kv_heads; a.head_dim = cfg.head_dim;
     // many sequences already fill the machine: fewer KV splits per sequence (cheaper combine, fewer CTAs)
-    a.page_size = page_size_; a.nsplit = std::max(1, std::min(nsplit_, batch_attn_ctas / (cfg.n_kv_heads * B))); a.pdl_early = bp ? 1 : 0;
+    a.page_size = page_size_; a.pdl_early = bp ? 1 : 0;
+    attn_decode_tc_plan(cfg.n_kv_heads, B, nsplit_, batch_attn_ctas, &a.nsplit, &a.tc_small);
     static const bool attn_tc = env_int("CL_BATCH_ATTN_TC", 1) != 0;
     if (attn_tc && have_kv_maps_ && attn_decode_tc_supported(cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, page_size_, a.nsplit))
       CL_LAUNCH(launch_attn_decode_tc(a, kmap_, vmap_, (long long)l * n_pages_ * cfg.n_kv_heads * page_size_, stream_, bp));

@@ -79,6 +79,7 @@ struct AttnDecodeArgs {
   StepSync sync;                     // sync.signal != nullptr: publish partials only, the consumer combines
   long long* tl = nullptr;
   int ring_bytes = 0;                // filled by the launcher
+  int tc_small = 0;                  // attn_decode_tc: 4-warp CTAs, two per SM (attn_decode_tc_plan)
 };
 
 struct StepTailArgs {                // argmax over logits, advance the sequence
@@ -104,6 +105,7 @@ int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 // tensor-core variant for the batched step (attn_decode_tc.cu): head_dim 128, 4 q heads per kv head, page 32;
 // kmap / vmap = pool-wide 2-D tensor maps (make_tmap_2d_bf16, box {64, 32}), layer_row0 = first row of this layer
 bool attn_decode_tc_supported(int n_heads, int n_kv, int head_dim, int page_size, int nsplit);
+void attn_decode_tc_plan(int n_kv, int batch, int nsplit_max, int cta_budget, int* nsplit, int* small);   // splits + kernel shape of a batched step
 int launch_attn_decode_tc(const AttnDecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, long long layer_row0, cudaStream_t st,
                           bool pdl);
 int launch_embed(const __nv_bfloat16* table, int d, const int* tok, float* h, int h_stride, const int* slots,
