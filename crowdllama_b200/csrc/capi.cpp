@@ -403,6 +403,18 @@ int cl_prefill(cl_engine* e, cl_seq_t s, const int32_t* ids, int32_t n, float* l
   std::lock_guard<std::mutex> lk(e->impl.mu_);
   CL_GUARD(return e->impl.prefill(s, ids, n, logits_out);)
 }
+int cl_prefill_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs, const int32_t* ids, const int32_t* lens, float* logits_out) {
+  if (!e || !seqs || !ids || !lens || n_seqs <= 0) return CL_ERR_INVALID_ARG;
+  std::vector<const int32_t*> ptrs((size_t)n_seqs);
+  size_t off = 0;
+  for (int i = 0; i < n_seqs; ++i) {
+    if (lens[i] <= 0) return CL_ERR_INVALID_ARG;
+    ptrs[(size_t)i] = ids + off;
+    off += (size_t)lens[i];
+  }
+  std::lock_guard<std::mutex> lk(e->impl.mu_);
+  CL_GUARD(return e->impl.prefill_multi(n_seqs, seqs, ptrs.data(), lens, logits_out);)
+}
 int cl_decode_step(cl_engine* e, cl_seq_t s, int32_t id, float* logits_out, int32_t* argmax_out) {
   if (!e) return CL_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(e->impl.mu_);

@@ -23,6 +23,7 @@ namespace cl {
 constexpr int kDefaultSchedPrefillChunk = 1024; // CL_SCHED_PREFILL_CHUNK: admission token budget per scheduler iteration (0 = whole prompts); validated r2e
 constexpr int kDefaultPrefillSmallMax = 256;    // CL_PREFILL_SMALL_MAX: prompts up to this many tokens take the split-K path (0 = off); validated r2e (128 tokens: 12.1 -> 6.3 ms)
 constexpr int kDefaultPrefillFused = 1;         // CL_PREFILL_FUSED bit mask: 1 = SiLU*mul (validated r2h: 63.2 -> 58.5 ms per 4096-token prefill), 2 = RoPE + cache scatter (correct but slower: r2g) fused into the prefill GEMM epilogues
+constexpr int kDefaultSchedMultiPrefill = 1;    // CL_SCHED_MULTI_PREFILL: scheduler admits the prompts at the head of the queue in one tile-path pass (Engine::prefill_multi; validated r2v: 64 clients x 146-token prompts 38.5 -> 47.4 req/s)
 constexpr int kDefaultBatchMega = 0;            // CL_BATCH_MEGA: persistent batched decode kernel for B >= 2
 
 void set_last_error(const std::string& s);
@@ -150,6 +151,8 @@ class Engine {
   int seq_free(cl_seq_t s);
   int seq_len(cl_seq_t s, int32_t* out) { if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ; *out = seqs_[s].len; return CL_OK; }
   int prefill(cl_seq_t s, const int32_t* ids, int n, float* logits_out);
+  // several prompts in one pass of the tile path (prefill.cu); logits_out: [n_seqs][vocab] or nullptr
+  int prefill_multi(int n_seqs, const cl_seq_t* ss, const int32_t* const* ids, const int* lens, float* logits_out);
   int decode_step(cl_seq_t s, int32_t id, float* logits_out, int32_t* argmax_out);
   int decode_greedy(const cl_seq_t* seqs, int n_seqs, const int32_t* first_ids, int n_steps, int32_t* ids_out,
                     float* device_ms);
@@ -189,7 +192,8 @@ class Engine {
   void precapture_graphs();                       // graph launch (or eager enqueue)
   int read_logits(int slot, float* out);
   int prefill_tokenwise(cl_seq_t s, const int32_t* ids, int n, float* logits_out);
-  int prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits_out);  // tcgen05 path (prefill.cu)
+  int prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits_out);
+  int ensure_prefill_ws(int tokens);  // tcgen05 path (prefill.cu)
   int prefill_small(cl_seq_t s, const int32_t* ids, int n, float* logits_out);    // short prompts: split-K projections (prefill.cu)
   bool prefill_path_ok() const;
   int set_single_slot(cl_seq_t s);
@@ -199,6 +203,7 @@ class Engine {
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   cudaEvent_t step_done_ev_ = nullptr;     // scheduler: blocking-sync event behind every batched step (scheduler.cpp)
   bool sched_blocking_sync_ = true;
+  bool sched_multi_prefill_ = false;       // group admission through prefill_multi (CL_SCHED_MULTI_PREFILL)
   int page_size_ = 32, max_batch_ = 8, max_seqs_ = 8, n_pages_ = 0, max_pages_per_seq_ = 0;
   int gemv_variant_ = 1, nsplit_ = 16;
   bool use_graph_ = true, use_pdl_ = true, skip_attn_ = false;

@@ -164,32 +164,39 @@ int Engine::prefill_small(cl_seq_t s, const int32_t* ids, int n, float* logits_o
   return CL_OK;
 }
 
+// (Re)allocate the tile-path workspace for chunks of up to `tokens` rows; old buffers stay in allocs_ until the engine dies
+// (grows at most once or twice).
+int Engine::ensure_prefill_ws(int tokens) {
+  const int d = cfg.d_model, F = cfg.d_ff;
+  int rc;
+  if (!pws_) pws_.reset(new PrefillWs());
+  if (pws_->cap_tokens >= tokens) return CL_OK;
+  const size_t T = (size_t)std::max(tokens, std::min(prefill_chunk_tokens_, cfg.max_seq_len));
+  auto alloc = [&](auto*& p, size_t bytes) -> int {
+    void* v = nullptr;
+    if (cudaMalloc(&v, bytes) != cudaSuccess) { cudaGetLastError(); set_last_error("prefill workspace: out of memory"); return CL_ERR_OOM; }
+    allocs_.push_back(v);
+    p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(v);
+    return CL_OK;
+  };
+  if ((rc = alloc(pws_->xn, T * d * 2))) return rc;
+  if ((rc = alloc(pws_->qkv, T * qkv_dim_ * 4))) return rc;
+  if ((rc = alloc(pws_->q, T * q_dim_ * 2))) return rc;
+  if ((rc = alloc(pws_->attn, T * q_dim_ * 2))) return rc;
+  if ((rc = alloc(pws_->h, T * d * 4))) return rc;
+  if ((rc = alloc(pws_->gu, T * 2 * F * 4))) return rc;
+  if ((rc = alloc(pws_->act, T * F * 2))) return rc;
+  pws_->cap_tokens = (int)T;
+  return CL_OK;
+}
+
 int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits_out) {
   auto& q = seqs_[s];
   int rc = ensure_capacity(s, q.len + n);
   if (rc) return rc;
   const int d = cfg.d_model, F = cfg.d_ff;
   const int CH = std::min(n, prefill_chunk_tokens_);
-  if (!pws_) pws_.reset(new PrefillWs());
-  if (pws_->cap_tokens < CH) {
-    // (re)allocate the workspace; old buffers stay in allocs_ until the engine dies (grows at most once or twice)
-    const size_t T = (size_t)std::max(CH, std::min(prefill_chunk_tokens_, cfg.max_seq_len));
-    auto alloc = [&](auto*& p, size_t bytes) -> int {
-      void* v = nullptr;
-      if (cudaMalloc(&v, bytes) != cudaSuccess) { cudaGetLastError(); set_last_error("prefill workspace: out of memory"); return CL_ERR_OOM; }
-      allocs_.push_back(v);
-      p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(v);
-      return CL_OK;
-    };
-    if ((rc = alloc(pws_->xn, T * d * 2))) return rc;
-    if ((rc = alloc(pws_->qkv, T * qkv_dim_ * 4))) return rc;
-    if ((rc = alloc(pws_->q, T * q_dim_ * 2))) return rc;
-    if ((rc = alloc(pws_->attn, T * q_dim_ * 2))) return rc;
-    if ((rc = alloc(pws_->h, T * d * 4))) return rc;
-    if ((rc = alloc(pws_->gu, T * 2 * F * 4))) return rc;
-    if ((rc = alloc(pws_->act, T * F * 2))) return rc;
-    pws_->cap_tokens = (int)T;
-  }
+  if ((rc = ensure_prefill_ws(CH))) return rc;
   PrefillWs& w = *pws_;
   const bool fused_silu = (prefill_fused_ & 1) != 0, fused_rope = (prefill_fused_ & 2) != 0;   // CL_PREFILL_FUSED bit mask
   CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, ids, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
@@ -260,6 +267,121 @@ int Engine::prefill_chunked(cl_seq_t s, const int32_t* ids, int n, float* logits
   q.len += n;
   q.history.insert(q.history.end(), ids, ids + n);
   if (logits_out) return read_logits(s, logits_out);
+  CL_CUDA_OK(cudaStreamSynchronize(stream_));
+  return CL_OK;
+}
+
+
+// Several prompts in ONE pass of the tile path (admission of a burst of short chats): the rows of all prompts are
+// concatenated, so every projection streams its weights once for all of them and runs on full 128 x 256 tiles —
+// 64 prompts of 130 tokens cost 64 x 6.0 ms one by one (the split-K short-prompt path streams all weights per prompt)
+// against about 2.3 ms each in passes of 1024-4096 rows.  Everything row-wise (embedding, RMSNorm, the four GEMMs,
+// SiLU) is unchanged; RoPE + cache scatter and the causal attention run per sequence on its row range (pointer
+// offsets into the same workspace; each sequence has its own position offset and block table); the last row of every
+// sequence goes through the batched LM head of the decode step (final norm + tcgen05 GEMM + argmax), which leaves
+// d_tok_ / d_pos_ of every slot ready for the first decode step.  A row's results do not depend on the other rows of
+// the pass: logits and cache contents are bit-identical to prefill_chunked on each prompt alone (tests/test_gpu_prefill.py).
+int Engine::prefill_multi(int n_seqs, const cl_seq_t* ss, const int32_t* const* ids, const int* lens, float* logits_out) {
+  if (n_seqs <= 0 || !ss || !ids || !lens) { set_last_error("prefill_multi: bad arguments"); return CL_ERR_INVALID_ARG; }
+  if (!prefill_path_ok() || !bws_ || n_seqs > max_batch_) { set_last_error("prefill_multi: tensor-core paths unavailable or more sequences than max_batch"); return CL_ERR_INVALID_ARG; }
+  const int d = cfg.d_model, F = cfg.d_ff, V = cfg.vocab_size;
+  int total = 0, rc;
+  for (int i = 0; i < n_seqs; ++i) {
+    const int s = ss[i];
+    if (s < 0 || s >= max_seqs_ || !seqs_[s].live) return CL_ERR_BAD_SEQ;
+    for (int c = 0; c < i; ++c) if (ss[c] == s) { set_last_error("duplicate sequence in batch"); return CL_ERR_INVALID_ARG; }
+    if (lens[i] <= 0 || !ids[i]) { set_last_error("empty prompt"); return CL_ERR_INVALID_ARG; }
+    for (int t = 0; t < lens[i]; ++t)
+      if (ids[i][t] < 0 || ids[i][t] >= V) { set_last_error("token id out of range"); return CL_ERR_INVALID_ARG; }
+    if (seqs_[s].len + lens[i] > cfg.max_seq_len) { set_last_error("sequence exceeds max_seq_len"); return CL_ERR_TOO_LONG; }
+    total += lens[i];
+  }
+  if (total > prefill_chunk_tokens_ || total > prompt_cap_) { set_last_error("prefill_multi: more rows than one pass holds"); return CL_ERR_TOO_LONG; }
+  for (int i = 0; i < n_seqs; ++i)
+    if ((rc = ensure_capacity(ss[i], seqs_[ss[i]].len + lens[i]))) return rc;
+  if ((rc = ensure_prefill_ws(total))) return rc;
+  PrefillWs& w = *pws_;
+  BatchWs& bw = *bws_;
+  const bool fused_silu = (prefill_fused_ & 1) != 0;
+  std::vector<int32_t> all((size_t)total);
+  std::vector<int> row0(n_seqs), pos0(n_seqs);
+  for (int i = 0, r = 0; i < n_seqs; r += lens[i], ++i) {
+    memcpy(all.data() + r, ids[i], (size_t)lens[i] * 4);
+    row0[i] = r;
+    pos0[i] = seqs_[ss[i]].len;
+  }
+  CL_CUDA_OK(cudaMemcpyAsync(d_prompt_, all.data(), (size_t)total * 4, cudaMemcpyHostToDevice, stream_));
+  int launches = 0, r;
+  PrefillProfiler pp(stream_);
+#define CL_LAUNCH(call) do { r = (call); if (r < 0) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); return CL_ERR_CUDA; } launches += r; pp.mark(#call); } while (0)
+  pp.mark("start");
+  const int T = total;
+  CL_LAUNCH(launch_embed_rows(embed_, d, d_prompt_, w.h, T, stream_));
+  for (int l = 0; l < cfg.n_layers; ++l) {
+    const auto& L = layers_[l];
+    __nv_bfloat16* kp = kpool_ + (size_t)l * kv_layer_elems_;
+    __nv_bfloat16* vp = vpool_ + (size_t)l * kv_layer_elems_;
+    CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.attn_norm, cfg.rms_eps, w.xn, T, d, stream_));
+    CL_LAUNCH(launch_gemm_bf16(w.xn, L.wqkv, w.qkv, nullptr, T, qkv_dim_, d, stream_));
+    for (int i = 0; i < n_seqs; ++i) {                    // RoPE at the sequence's own positions, K/V into its own pages
+      const int* bt = d_bt_ + (size_t)ss[i] * max_pages_per_seq_;
+      RopeScatterArgs ra{w.qkv + (size_t)row0[i] * qkv_dim_, qkv_dim_, rope_, pos0[i], lens[i], w.q + (size_t)row0[i] * q_dim_, kp, vp, bt, page_size_,
+                         cfg.n_heads, cfg.n_kv_heads, cfg.head_dim};
+      CL_LAUNCH(launch_rope_scatter(ra, stream_));
+    }
+    for (int i = 0; i < n_seqs; ++i) {                    // causal attention inside each sequence
+      const int* bt = d_bt_ + (size_t)ss[i] * max_pages_per_seq_;
+      AttnPrefillArgs aa{w.q + (size_t)row0[i] * q_dim_, kp, vp, bt, page_size_, pos0[i], lens[i], cfg.n_heads, cfg.n_kv_heads, cfg.head_dim,
+                         w.attn + (size_t)row0[i] * q_dim_};
+      if (have_kv_maps_ && attn_prefill_tc_supported(cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, page_size_, pos0[i], lens[i]))
+        CL_LAUNCH(launch_attn_prefill_tc(aa, kmap_, vmap_, (long long)l * n_pages_ * cfg.n_kv_heads * page_size_, stream_));
+      else
+        CL_LAUNCH(launch_attn_prefill(aa, stream_));
+    }
+    CL_LAUNCH(launch_gemm_bf16(w.attn, L.wo, w.h, w.h, T, d, q_dim_, stream_));
+    CL_LAUNCH(launch_rmsnorm_bf16(w.h, L.ffn_norm, cfg.rms_eps, w.xn, T, d, stream_));
+    if (fused_silu) {
+      GemmEpi eg;
+      eg.kind = 1; eg.act = w.act; eg.ld_act = F;
+      CL_LAUNCH(launch_gemm_bf16_epi(w.xn, L.wgu, T, 2 * F, d, eg, stream_));
+    } else {
+      CL_LAUNCH(launch_gemm_bf16(w.xn, L.wgu, w.gu, nullptr, T, 2 * F, d, stream_));
+      CL_LAUNCH(launch_silu_mul_bf16(w.gu, w.act, T, F, stream_));
+    }
+    CL_LAUNCH(launch_gemm_bf16(w.act, L.wdown, w.h, w.h, T, d, F, stream_));
+  }
+  // last row of every sequence -> its slot's residual row and position, then the decode step's batched head
+  std::vector<int> slots(n_seqs);
+  for (int i = 0; i < n_seqs; ++i) {
+    const int s = ss[i], last_pos = pos0[i] + lens[i] - 1;
+    slots[i] = s;
+    CL_CUDA_OK(cudaMemcpyAsync(d_h_ + (size_t)s * d, w.h + (size_t)(row0[i] + lens[i] - 1) * d, (size_t)d * 4, cudaMemcpyDeviceToDevice, stream_));
+    CL_CUDA_OK(cudaMemcpyAsync(d_pos_ + s, &last_pos, 4, cudaMemcpyHostToDevice, stream_));
+  }
+  CL_CUDA_OK(cudaMemcpyAsync(d_slots_, slots.data(), (size_t)n_seqs * 4, cudaMemcpyHostToDevice, stream_));
+  slots_dirty_ = true;
+  last_single_slot_ = n_seqs == 1 ? slots[0] : -1;
+  CL_LAUNCH(launch_batch_resid_norm(d_h_, d, nullptr, 0, n_seqs, final_norm_, cfg.rms_eps, bw.xn, d_slots_, stream_, false));
+  CL_LAUNCH(launch_gemm_bf16(bw.xn, lm_head_, bw.logits, nullptr, n_seqs, V, d, stream_, 1, false));
+  CL_LAUNCH(launch_batch_scatter_rows(bw.logits, V, d_logits_, V, d_slots_, n_seqs, stream_));
+  StepTailArgs t;
+  t.logits = d_logits_; t.vocab = V; t.tok = d_tok_; t.pos = d_pos_; t.ids_ring = d_ids_ring_;
+  t.step_counter = d_step_counter_; t.ring_steps = ring_steps_; t.ring_stride = max_batch_;
+  t.part_val = d_tail_val_; t.part_idx = d_tail_idx_; t.counters = d_tail_cnt_; t.slots = d_slots_; t.batch = n_seqs;
+  CL_LAUNCH(launch_step_tail(t, stream_));
+#undef CL_LAUNCH
+  pp.report(total, "multi-prompt tile");
+  launches_ += launches;
+  for (int i = 0; i < n_seqs; ++i) {
+    auto& q = seqs_[ss[i]];
+    q.len += lens[i];
+    q.history.insert(q.history.end(), ids[i], ids[i] + lens[i]);
+  }
+  if (logits_out) {
+    for (int i = 0; i < n_seqs; ++i)
+      if ((rc = read_logits(ss[i], logits_out + (size_t)i * V))) return rc;
+    return CL_OK;
+  }
   CL_CUDA_OK(cudaStreamSynchronize(stream_));
   return CL_OK;
 }

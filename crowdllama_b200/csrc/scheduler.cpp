@@ -210,6 +210,8 @@ void Engine::scheduler_main() {
     {
       const char* v = getenv("CL_SCHED_BLOCKING_SYNC");
       sched_blocking_sync_ = !v || atoi(v) != 0;
+      v = getenv("CL_SCHED_MULTI_PREFILL");
+      sched_multi_prefill_ = v ? atoi(v) != 0 : kDefaultSchedMultiPrefill != 0;
     }
     if (sched_blocking_sync_ && !step_done_ev_ && cudaEventCreateWithFlags(&step_done_ev_, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
@@ -230,6 +232,78 @@ void Engine::scheduler_main() {
     // Several short prompts may be admitted in one iteration as long as their tokens fit the same budget (a burst of
     // 128-token chats fills the batch in a few iterations instead of one request per decode step).
     int budget = sched_prefill_chunk_ > 0 ? sched_prefill_chunk_ : (1 << 30);   // 0: unlimited = whole prompts, as in round 1
+    // ---- group admission: the prompts at the head of the queue that fit one pass go through the tile path TOGETHER
+    // (Engine::prefill_multi: one weight stream for all of them).  FIFO: the group is a prefix of the queue.  With running
+    // sequences the pass is bounded by the same token budget as a chunk; with none to stall, by the workspace (4096 rows).
+    if (sched_multi_prefill_ && !prefilling_ && (int)active_.size() < max_batch_ && bws_ && prefill_path_ok()) {
+      const int cap_tokens = active_.empty() ? prefill_chunk_tokens_ : std::min(budget, prefill_chunk_tokens_);
+      std::vector<std::shared_ptr<Request>> group;
+      {
+        std::lock_guard<std::mutex> lk(q_mu_);
+        int tokens = 0, pages = 0;
+        for (auto& r : queue_) {
+          if ((int)(active_.size() + group.size()) >= max_batch_) break;
+          const int n = (int)(r->prompt.size() + r->out.size());
+          const int need = (n + 1 + page_size_ - 1) / page_size_;
+          if (r->cancel.load(std::memory_order_relaxed) || tokens + n > cap_tokens || pages + need > pool_->free_pages()) break;
+          group.push_back(r);
+          tokens += n;
+          pages += need;
+        }
+        if (group.size() >= 2) queue_.erase(queue_.begin(), queue_.begin() + (long)group.size());
+      }
+      if (group.size() >= 2) {
+        std::vector<cl_seq_t> ss;
+        std::vector<const int32_t*> ptrs;
+        std::vector<int> lens;
+        int rc = CL_OK, total = 0;
+        for (auto& r : group) {
+          r->full.assign(r->prompt.begin(), r->prompt.end());
+          r->full.insert(r->full.end(), r->out.begin(), r->out.end());
+          rc = seq_create(&r->seq);
+          if (rc == CL_OK) rc = ensure_capacity(r->seq, (int)r->full.size() + 1);
+          if (rc) break;
+          ss.push_back(r->seq); ptrs.push_back(r->full.data()); lens.push_back((int)r->full.size());
+          total += (int)r->full.size();
+        }
+        const int64_t t0 = now_ns();
+        if (rc == CL_OK) rc = prefill_multi((int)ss.size(), ss.data(), ptrs.data(), lens.data(), nullptr);
+        const int64_t pdt = now_ns() - t0;
+        if (rc == CL_OK) {
+          cudaMemcpyAsync(toks.data(), d_tok_, (size_t)max_seqs_ * 4, cudaMemcpyDeviceToHost, stream_);
+          if (cudaStreamSynchronize(stream_) != cudaSuccess) rc = CL_ERR_CUDA;
+        }
+        sched_prefill_calls_++; sched_prefill_tokens_ += total; sched_prefill_ns_ += pdt;
+        if (rc) {
+          const std::string err = get_last_error();
+          for (auto& r : group) { if (r->seq >= 0) seq_free(r->seq); r->seq = -1; complete(r, rc, err); }
+        } else {
+          for (auto& r : group) {
+            r->prefill_ns += pdt;
+            r->prefilled = r->full.size();
+            int32_t next = toks[r->seq];                       // greedy: the device argmax of the pass
+            if (!r->greedy()) {
+              read_logits(r->seq, logits.data());
+              next = sample_token(logits.data(), V, r->sp, r->full.data(), (int)r->full.size(), (uint64_t)r->out.size());
+              cudaMemcpyAsync(d_tok_ + r->seq, &next, 4, cudaMemcpyHostToDevice, stream_);
+              cudaStreamSynchronize(stream_);
+            }
+            r->out.push_back(next);
+            publish(*r, next);
+            if (finished(*r, *tok, cfg.max_seq_len)) {
+              seq_free(r->seq);
+              requests_completed_++;
+              tokens_generated_ += 1;
+              complete(r, CL_OK, "");
+            } else {
+              active_.push_back(r);
+            }
+          }
+        }
+        slots_dirty_ = true;
+        budget = 0;                        // this iteration's admission is done: on to the decode step
+      }
+    }
     while (budget > 0) {
       if (!prefilling_ && (int)active_.size() < max_batch_) {
         std::shared_ptr<Request> r;

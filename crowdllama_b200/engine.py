@@ -68,7 +68,7 @@ EXPORTS = [
     "cl_greedy_sampling", "cl_sample_token", "cl_model_preset", "cl_engine_create", "cl_engine_destroy", "cl_engine_model_config",
     "cl_engine_stats", "cl_engine_set_tensor", "cl_checkpoint_info", "cl_generate", "cl_generate_ids", "cl_generate_stream", "cl_result_free",
     "cl_handle_message", "cl_handle_message_stream", "cl_buffer_free", "cl_tokenize", "cl_detokenize", "cl_seq_create", "cl_seq_free",
-    "cl_seq_len", "cl_prefill", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_decode_step_batch", "cl_seq_fake_fill",
+    "cl_seq_len", "cl_prefill", "cl_prefill_batch", "cl_decode_step", "cl_decode_greedy", "cl_decode_greedy_batch", "cl_decode_step_batch", "cl_seq_fake_fill",
     "cl_time_dominant_kernel", "cl_debug_kv", "cl_debug_hidden", "cl_debug_timeline",
     "cl_op_gemv", "cl_op_gemv_residual", "cl_op_rmsnorm_gemv", "cl_op_rmsnorm_gateup", "cl_op_qkv_rope_append", "cl_op_attn_decode",
     "cl_op_gemm_bf16", "cl_op_attn_prefill", "cl_op_attn_prefill_variant", "cl_op_synth_weights", "cl_kvpool_create", "cl_kvpool_destroy",
@@ -122,6 +122,7 @@ def lib():
         "cl_seq_free": (C.c_int, [vp, i32]),
         "cl_seq_len": (C.c_int, [vp, i32, P(i32)]),
         "cl_prefill": (C.c_int, [vp, i32, vp, i32, vp]),
+        "cl_prefill_batch": (C.c_int, [vp, vp, i32, vp, vp, vp]),
         "cl_decode_step": (C.c_int, [vp, i32, i32, vp, P(i32)]),
         "cl_decode_greedy": (C.c_int, [vp, i32, i32, i32, vp, P(f32)]),
         "cl_decode_greedy_batch": (C.c_int, [vp, vp, i32, vp, i32, vp, P(f32)]),
@@ -318,6 +319,15 @@ class Engine:
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         out = np.empty(self.cfg["vocab_size"], np.float32) if want_logits else None
         _check(lib().cl_prefill(self._h, s, _ptr(ids), len(ids), _ptr(out) if want_logits else None), "cl_prefill")
+        return out
+
+    def prefill_batch(self, seqs, prompts, want_logits: bool = True):
+        """cl_prefill_batch: several prompts in one pass; returns [n_seqs][vocab] logits of the last positions (or None)."""
+        ss = np.ascontiguousarray(seqs, dtype=np.int32)
+        lens = np.ascontiguousarray([len(p) for p in prompts], dtype=np.int32)
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(p, np.int32) for p in prompts]), dtype=np.int32)
+        out = np.empty((len(ss), self.cfg["vocab_size"]), np.float32) if want_logits else None
+        _check(lib().cl_prefill_batch(self._h, _ptr(ss), len(ss), _ptr(ids), _ptr(lens), _ptr(out) if want_logits else None), "cl_prefill_batch")
         return out
 
     def decode_step(self, s: int, tok: int, want_logits: bool = True):

@@ -225,6 +225,11 @@ int cl_seq_len(cl_engine* e, cl_seq_t seq, int32_t* len_out);
 /* Append n prompt tokens to the sequence.  logits_out (host, may be NULL) receives the
  * vocab_size fp32 logits of the LAST position. */
 int cl_prefill(cl_engine* e, cl_seq_t seq, const int32_t* ids, int32_t n, float* logits_out);
+/* The prompts of n_seqs sequences in ONE pass of the tensor-core path (the scheduler's admission of a burst of short
+ * chats): ids = the prompts back to back, lens[i] tokens for seqs[i]; at most 4096 rows in total and n_seqs <= max_batch.
+ * logits_out (host, may be NULL): [n_seqs][vocab_size] logits of every prompt's last position.  Results are
+ * bit-identical to cl_prefill on each prompt alone through the same (tile) path. */
+int cl_prefill_batch(cl_engine* e, const cl_seq_t* seqs, int32_t n_seqs, const int32_t* ids, const int32_t* lens, float* logits_out);
 /* Append one token and compute the next-token logits (host, may be NULL);
  * argmax_out (may be NULL) receives the greedy next id (lowest index on ties). */
 int cl_decode_step(cl_engine* e, cl_seq_t seq, int32_t id, float* logits_out, int32_t* argmax_out);

@@ -384,3 +384,45 @@ def test_long_prompt_is_admitted_in_chunks_between_decode_steps(monkeypatch):
             assert out[f"s{i}"].n_generated == 10 and out[f"s{i}"].token_ids[0] == s_solo[i][0]
         st = e.stats()
         assert st["kv_pages_used"] == 0 and st["active_seqs"] == 0 and st["requests_completed"] >= 7 + 7
+
+
+def test_group_admission_of_a_burst_matches_requests_run_alone(monkeypatch):
+    """scheduler.cpp group admission (CL_SCHED_MULTI_PREFILL=1): a burst of prompts waiting at the head of the queue is
+    prefilled in ONE pass (Engine::prefill_multi) and joins the batch together.  Every request must return what it
+    returns alone (first token exactly; later tokens up to the near-tie flips of batched vs single-sequence kernels),
+    nothing may leak, and a long prompt in the middle of the queue still takes the chunked path."""
+    import threading
+    monkeypatch.setenv("CL_SCHED_MULTI_PREFILL", "1")
+    monkeypatch.setenv("CL_SCHED_PREFILL_CHUNK", "256")
+    cfg = oc.PRESETS["tiny-test"]
+    V = cfg["vocab_size"]
+    prompts = [np.array([(13 * i + 7 * j + 3) % V for j in range(20 + 9 * (i % 5))], np.int32) for i in range(14)]
+    prompts[6] = np.array([(i * 31 + 7) % V for i in range(400)], np.int32)      # longer than one pass with others running
+    with eng.Engine(preset="tiny-test", seed=77, max_batch=8, max_seqs=8, start_scheduler=True) as e:
+        solo = [e.generate_ids(p, eng.greedy(24, ignore_eos=True)).token_ids for p in prompts]
+        before = e.stats()
+        out = [None] * len(prompts)
+
+        def run(i):
+            out[i] = e.generate_ids(prompts[i], eng.greedy(24, ignore_eos=True))
+        th = [threading.Thread(target=run, args=(i,)) for i in range(len(prompts))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        st = e.stats()
+        for i in range(len(prompts)):
+            assert out[i].n_generated == 24 and out[i].token_ids[0] == solo[i][0], i
+            assert (out[i].token_ids == solo[i]).mean() > 0.7, i
+        assert st["kv_pages_used"] == 0 and st["active_seqs"] == 0 and st["requests_completed"] - before["requests_completed"] == len(prompts)
+        # fewer prefill calls than requests: groups were formed
+        assert st["sched_prefill_calls"] - before["sched_prefill_calls"] < len(prompts)
+        # sampled requests go through the group path too (host sampler on the pass's logits): deterministic per seed
+        sp = eng.ollama_default_sampling(seed=5, max_new_tokens=12)
+        a = [None] * 4
+
+        def run_s(i):
+            a[i] = e.generate_ids(prompts[i], sp).token_ids
+        th = [threading.Thread(target=run_s, args=(i,)) for i in range(4)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        ref = [e.generate_ids(prompts[i], sp).token_ids for i in range(4)]
+        assert all(a[i][0] == ref[i][0] for i in range(4))

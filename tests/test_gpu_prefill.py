@@ -166,3 +166,42 @@ def test_prefill_continuation_at_an_unaligned_position_llama_shapes(monkeypatch,
             assert np.abs(lg - lo).max() < 0.125
             tok = int(lo.argmax())
         assert e.seq_len(s) == 100 + 5 + t2 + 4
+
+
+def test_multi_prompt_prefill_is_bit_identical_to_one_prompt_at_a_time(monkeypatch):
+    """Engine::prefill_multi (cl_prefill_batch): several prompts as the rows of ONE tile-path pass.  A row's results do
+    not depend on its neighbours, so the cached K / V of every position and the greedy continuation must equal, bit for
+    bit, the same prompts prefilled alone through the tile path (CL_PREFILL_SMALL_MAX=0) — at Llama-3-8B layer shapes
+    (tcgen05 attention) and on the tiny preset (head_dim 64).  The last-position logits come from the batched LM head
+    (tcgen05 GEMM) instead of the single-sequence GEMV: same bf16 inputs, another summation order (<= 2e-4)."""
+    monkeypatch.setenv("CL_PREFILL_SMALL_MAX", "0")
+    for preset, layers, lens in (("llama3-8b", 2, [130, 17, 256, 33, 64, 300, 129]), ("tiny-test", 2, [40, 16, 97, 31])):
+        cfg = dict(oc.PRESETS[preset])
+        cfg["n_layers"] = layers
+        cfg["max_seq_len"] = 1024
+        V = cfg["vocab_size"]
+        prompts = [np.array([(i * 7919 + 13 * b + 5) % V for i in range(n)], np.int32) for b, n in enumerate(lens)]
+        with eng.Engine(model=cfg, seed=31, max_batch=8, max_seqs=16) as e:
+            alone, alone_kv, alone_next = [], [], []
+            for p in prompts:
+                s = e.seq_create()
+                alone.append(e.prefill(s, p))
+                alone_kv.append([e.debug_kv(s, layers - 1, w, 0, len(p)) for w in (0, 1)])
+                alone_next.append(e.decode_greedy(s, int(alone[-1].argmax()), 6)[0])
+                e.seq_free(s)
+            seqs = [e.seq_create() for _ in prompts]
+            lg = e.prefill_batch(seqs, prompts)
+            for b, s in enumerate(seqs):
+                assert np.abs(lg[b] - alone[b]).max() < 2e-4 and int(lg[b].argmax()) == int(alone[b].argmax())
+                assert e.seq_len(s) == lens[b]
+                for w in (0, 1):
+                    np.testing.assert_array_equal(e.debug_kv(s, layers - 1, w, 0, lens[b]), alone_kv[b][w])
+            for b, s in enumerate(seqs):                       # the device state left behind (tok / pos) starts decoding correctly
+                np.testing.assert_array_equal(e.decode_greedy(s, int(lg[b].argmax()), 6)[0], alone_next[b])
+            # oracle check of one prompt of the batch (the tile path itself is pinned in the tests above)
+            if preset == "tiny-test":
+                m = oc.Model(cfg, seed=31)
+                ref = m.new_seq().forward(prompts[2])
+                assert np.abs(lg[2] - ref).max() < 0.05 + 0.03 * np.sqrt(layers)
+            with pytest.raises(eng.EngineError):
+                e.prefill_batch([seqs[0], seqs[0]], prompts[:2])   # duplicate sequence
