@@ -24,6 +24,7 @@ constexpr int kDefaultSchedPrefillChunk = 1024; // CL_SCHED_PREFILL_CHUNK: admis
 constexpr int kDefaultPrefillSmallMax = 256;    // CL_PREFILL_SMALL_MAX: prompts up to this many tokens take the split-K path (0 = off); validated r2e (128 tokens: 12.1 -> 6.3 ms)
 constexpr int kDefaultPrefillFused = 1;         // CL_PREFILL_FUSED bit mask: 1 = SiLU*mul (validated r2h: 63.2 -> 58.5 ms per 4096-token prefill), 2 = RoPE + cache scatter (correct but slower: r2g) fused into the prefill GEMM epilogues
 constexpr int kDefaultSchedMultiPrefill = 1;    // CL_SCHED_MULTI_PREFILL: scheduler admits the prompts at the head of the queue in one tile-path pass (Engine::prefill_multi; validated r2v: 64 clients x 146-token prompts 38.5 -> 47.4 req/s)
+constexpr int kDefaultSchedLingerUs = 1000;     // CL_SCHED_LINGER_US: with an empty batch, keep collecting while requests arrive within this gap (max 8x in total)
 constexpr int kDefaultBatchMega = 0;            // CL_BATCH_MEGA: persistent batched decode kernel for B >= 2
 
 void set_last_error(const std::string& s);
@@ -203,6 +204,7 @@ class Engine {
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   cudaEvent_t step_done_ev_ = nullptr;     // scheduler: blocking-sync event behind every batched step (scheduler.cpp)
   bool sched_blocking_sync_ = true;
+  int sched_linger_us_ = 0;                // burst detection before a group admission into an empty batch (CL_SCHED_LINGER_US)
   bool sched_multi_prefill_ = false;       // group admission through prefill_multi (CL_SCHED_MULTI_PREFILL)
   int page_size_ = 32, max_batch_ = 8, max_seqs_ = 8, n_pages_ = 0, max_pages_per_seq_ = 0;
   int gemv_variant_ = 1, nsplit_ = 16;

@@ -212,6 +212,8 @@ void Engine::scheduler_main() {
       sched_blocking_sync_ = !v || atoi(v) != 0;
       v = getenv("CL_SCHED_MULTI_PREFILL");
       sched_multi_prefill_ = v ? atoi(v) != 0 : kDefaultSchedMultiPrefill != 0;
+      v = getenv("CL_SCHED_LINGER_US");
+      sched_linger_us_ = v ? atoi(v) : kDefaultSchedLingerUs;
     }
     if (sched_blocking_sync_ && !step_done_ev_ && cudaEventCreateWithFlags(&step_done_ev_, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
@@ -224,6 +226,20 @@ void Engine::scheduler_main() {
       std::unique_lock<std::mutex> lk(q_mu_);
       q_cv_.wait(lk, [&] { return stop_ || !queue_.empty() || !active_.empty() || prefilling_; });
       if (stop_) break;
+      // Burst detection while nothing is running: requests of one wave reach the worker over a few milliseconds (one
+      // stream per request, pkg/peer/peer.go:177-182).  Waiting as long as new ones keep arriving within
+      // sched_linger_us_ of each other (at most 8x that in total) lets the group admission below take them in one
+      // pass instead of prefilling the first one alone; a lone request pays sched_linger_us_ once, against a
+      // prefill of several milliseconds.
+      if (sched_multi_prefill_ && sched_linger_us_ > 0 && active_.empty() && !prefilling_ && !queue_.empty()) {
+        const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(8 * (int64_t)sched_linger_us_);
+        while ((int)queue_.size() < max_batch_ && std::chrono::steady_clock::now() < t_end) {
+          const size_t n = queue_.size();
+          if (!q_cv_.wait_for(lk, std::chrono::microseconds(sched_linger_us_), [&] { return stop_ || queue_.size() != n; })) break;   // quiet: go
+          if (stop_) break;
+        }
+        if (stop_) break;
+      }
     }
     std::lock_guard<std::mutex> elk(mu_);
     // ---- admission.  A prompt is prefilled in chunks of sched_prefill_chunk_ tokens, ONE chunk per scheduler iteration,
@@ -236,7 +252,8 @@ void Engine::scheduler_main() {
     // (Engine::prefill_multi: one weight stream for all of them).  FIFO: the group is a prefix of the queue.  With running
     // sequences the pass is bounded by the same token budget as a chunk; with none to stall, by the workspace (4096 rows).
     if (sched_multi_prefill_ && !prefilling_ && (int)active_.size() < max_batch_ && bws_ && prefill_path_ok()) {
-      const int cap_tokens = active_.empty() ? prefill_chunk_tokens_ : std::min(budget, prefill_chunk_tokens_);
+      const int pass_rows = std::min(prefill_chunk_tokens_, prompt_cap_);   // what one prefill_multi pass holds
+      const int cap_tokens = active_.empty() ? pass_rows : std::min(budget, pass_rows);
       std::vector<std::shared_ptr<Request>> group;
       {
         std::lock_guard<std::mutex> lk(q_mu_);
