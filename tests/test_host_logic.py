@@ -524,3 +524,10 @@ def test_checkpoint_config_rejects_what_the_engine_does_not_implement(tmp_path):
     with pytest.raises(eng.EngineError) as ei:
         eng.checkpoint_info(tmp_path / "with_bias.safetensors", cfg)
     assert "q_proj.bias" in ei.value.detail
+
+
+def test_graft_entry_build_check():
+    """The driver's "does it build" hook: compiles (incrementally) and checks the ABI version the binding expects."""
+    import importlib
+    g = importlib.import_module("__graft_entry__")
+    g.build()
