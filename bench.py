@@ -220,7 +220,7 @@ def _wait_port(addr, timeout_s):
 
 
 BOX_PROMPT = ("Explain, step by step, why the sky appears blue during the day and red at sunset, and what changes on Mars. " * 2)[:118]
-BOX_SHARD_CLIENTS = 128          # closed-loop clients per gateway stand-in process (one Python GIL each)
+BOX_SHARD_CLIENTS = int(os.environ.get("CL_BOX_SHARD_CLIENTS", "128"))   # closed-loop clients per gateway stand-in process (one Python GIL each)
 
 
 def run_box_shard(addrs, port, concurrency, n_req, first_id, start_at):
