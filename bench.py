@@ -17,7 +17,7 @@ Second half — `box` (configs[3]): every rank also serves as a worker peer (Wor
 protobuf protocol, pkg/peer/peer.go:190-256) and a load generator next to rank 0 drives the gateway stand-in
 (/api/chat -> FindBestWorker, pkg/peermanager/manager.go:338-387 -> RequestInference, pkg/gateway/gateway.go:243-293
 -> cl_handle_message -> continuous-batching scheduler): 64 concurrent chats x 256 greedy tokens as BASELINE states,
-and a saturating load (32 concurrent chats per peer).  Reported: req/s, tok/s, per-worker request counts.
+and a saturating load (BOX_MAX_BATCH = 128 concurrent chats per peer).  Reported: req/s, tok/s, per-worker request counts.
 
 `--impl reference` times the reference arm: the reference worker's CPU path.  The reference's own implementation
 (Ollama v0.9.6) cannot be built or installed offline, so the arm runs the CPU oracle port of the same token step
