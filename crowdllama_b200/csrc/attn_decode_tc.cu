@@ -292,10 +292,10 @@ template <int NW, int NS, int MINB>
 int launch_variant(const AttnDecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, long long layer_row0, cudaStream_t st, bool pdl) {
   constexpr size_t smem = (size_t)NS * SLOT + 2 * NS * 8 + (2 * NW * REP + NW * REP * HD + 2 * MAXS * REP + REP + 4) * 4 + 1024 + 64;
   auto kern = attn_decode_tc_kernel<NW, NS, MINB>;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.pending()) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    attr = true;
+    attr.mark();
   }
   TcArgs t{a, layer_row0};
   cudaLaunchConfig_t cfg{};

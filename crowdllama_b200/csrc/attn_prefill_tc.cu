@@ -409,10 +409,10 @@ int launch_attn_prefill_tc(const AttnPrefillArgs& a, const CUtensorMap& kmap, co
   if (!attn_prefill_tc_supported(a.n_heads, a.n_kv, a.head_dim, a.page_size, a.pos0, a.T)) return -1;
   CUtensorMap qmap;
   if (!make_tmap_2d_bf16(&qmap, a.q, (uint64_t)a.T, (uint64_t)a.n_heads * HD, 64, TQ)) return -1;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.pending()) {
     if (cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) return -1;
-    attr = true;
+    attr.mark();
   }
   AttnTcParams p;
   p.block_table = a.block_table; p.n_bt = (a.pos0 + a.T + PAGE - 1) / PAGE; p.pos0 = a.pos0; p.T = a.T; p.n_heads = a.n_heads; p.n_kv = a.n_kv;

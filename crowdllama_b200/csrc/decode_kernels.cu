@@ -396,11 +396,11 @@ static cudaError_t launch_ring_inst(const GemvArgs& a, cudaStream_t st, bool pdl
   const int max_tiles = U * ((NU + G - 1) / G);
   size_t smem = (size_t)NST * TR * K * 2 + (size_t)2 * NST * 8 + 8 * 4 + (size_t)(max_tiles + 1) * TR * S * 4 + 64;
   auto kern = gemv_ring_kernel<EPI, NORM, TR, S, CPL, NST>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.pending()) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     prefer_max_smem(kern);
-    attr_set = true;
+    attr_set.mark();
   }
   if (smem > 160 * 1024) return cudaErrorInvalidValue;
   if (a.comb.part && (a.comb.nsplit > 32 || (a.K + G - 1) / G > 64)) return cudaErrorInvalidValue;
@@ -428,11 +428,11 @@ template <int EPI, bool NORM>
 static cudaError_t launch_ldg(const GemvArgs& a, cudaStream_t st, bool pdl) {
   auto kern = gemv_ldg_kernel<EPI, NORM>;
   size_t smem = (size_t)a.K * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.pending()) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     prefer_max_smem(kern);
-    attr_set = true;
+    attr_set.mark();
   }
   int G = sm_count() * 2;
   int npairs = a.N / 2;
@@ -746,8 +746,8 @@ int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   AttnDecodeArgs a2 = a;
   a2.ring_bytes = g_attn_ring_bytes;
   cudaError_t e = cudaErrorInvalidValue;
-#define CL_ATT(R, D) do { static bool once = false; if (!once) { prefer_max_smem(attn_decode_kernel<R, D>);                 \
-      cudaFuncSetAttribute(attn_decode_kernel<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnRingBytesMax); once = true; } \
+#define CL_ATT(R, D) do { static PerDeviceOnce once; if (once.pending()) { prefer_max_smem(attn_decode_kernel<R, D>);     \
+      cudaFuncSetAttribute(attn_decode_kernel<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnRingBytesMax); once.mark(); } \
     e = launch_ex(attn_decode_kernel<R, D>, grid, block, smem, st, pdl, a2); } while (0)
   if (a.head_dim == 128) {
     if (rep == 1) CL_ATT(1, 128); else if (rep == 2) CL_ATT(2, 128); else if (rep == 4) CL_ATT(4, 128);
@@ -784,8 +784,8 @@ int launch_embed(const __nv_bfloat16* table, int d, const int* tok, float* h, in
                  cudaStream_t st) {
   int threads = 128;
   int blocks = (d / 8 + threads - 1) / threads;
-  static bool once = false;
-  if (!once) { prefer_max_smem(embed_kernel); once = true; }
+  static PerDeviceOnce once;
+  if (once.pending()) { prefer_max_smem(embed_kernel); once.mark(); }
   embed_kernel<<<dim3(blocks, batch), threads, 0, st>>>(table, d, tok, h, h_stride, slots);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -865,8 +865,8 @@ int launch_zero_u32(unsigned* p, int n, cudaStream_t st) {
 }
 
 int launch_step_tail(const StepTailArgs& a, cudaStream_t st) {
-  static bool once = false;
-  if (!once) { prefer_max_smem(step_tail_kernel); prefer_max_smem(step_bump_kernel); once = true; }
+  static PerDeviceOnce once;
+  if (once.pending()) { prefer_max_smem(step_tail_kernel); prefer_max_smem(step_bump_kernel); once.mark(); }
   step_tail_kernel<<<dim3(kTailBlocks, a.batch), 256, 0, st>>>(a);
   if (cudaGetLastError() != cudaSuccess) return -1;
   step_bump_kernel<<<1, 256, 0, st>>>(a.step_counter, a.sync_counters, a.n_sync_counters);

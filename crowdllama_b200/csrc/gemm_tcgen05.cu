@@ -317,11 +317,11 @@ template <int BT, int NST, int MT = 1, int EPI = EPI_F32>
 cudaError_t launch_inst(const CUtensorMap& mw, const CUtensorMap& mx, const GemmParams& p, cudaStream_t st, bool pdl) {
   auto kern = gemm_tcgen05_kernel<BT, NST, MT, EPI>;
   constexpr size_t smem = (size_t)NST * (MT * BM * BK * 2 + BT * BK * 2) + 1024 + 256;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.pending()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.mark();
   }
   const int tiles = ((p.T + BT - 1) / BT) * ((p.N + BM * MT - 1) / (BM * MT)) * (p.k_splits > 1 ? p.k_splits : 1);
   const int grid = tiles < sm_count() ? tiles : sm_count();

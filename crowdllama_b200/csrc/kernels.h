@@ -203,6 +203,14 @@ int launch_decode_mega_batch(const BatchMegaArgs& a, cudaStream_t st);
 
 bool gemv_variant_supported(int variant, int N, int K);
 int sm_count();
+// "done once" flag per (call site, current device): function attributes (dynamic shared memory limit, carve-out) belong to a
+// device's context, so a process that opens a second GPU must set them again
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool* slot() { int d = 0; cudaGetDevice(&d); return &done[d & 63]; }
+  bool pending() { return !*slot(); }
+  void mark() { *slot() = true; }
+};
 
 // ---- prefill path (prefill_kernels.cu / gemm_tcgen05.cu) -----------------------------------------
 // X bf16 [T][K] row-major, W bf16 [N][K] row-major -> Y fp32 [T][N] (+= resid when resid != nullptr)

@@ -276,8 +276,8 @@ int launch_attn_prefill(const AttnPrefillArgs& a, cudaStream_t st) {
   cudaError_t e = cudaErrorInvalidValue;
   if (a.head_dim == 128) {
     constexpr int smem = 5 * 64 * 128 * 2;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    static PerDeviceOnce attr;
+    if (attr.pending()) { cudaFuncSetAttribute(attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr.mark(); }
     attn_prefill_kernel<128><<<grid, block, smem, st>>>(a);
     e = cudaGetLastError();
   } else if (a.head_dim == 64) {
