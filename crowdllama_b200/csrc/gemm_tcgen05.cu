@@ -348,7 +348,14 @@ int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, c
   // down-projection gains, 1316 vs 1132): wave quantisation (256 instead of 512 tiles on 148 SMs) and the lost
   // epilogue overlap cost more than the L2 traffic saves.  Kept opt-in for the measurements.
   static const int mt_env = getenv("CL_GEMM_MT") ? atoi(getenv("CL_GEMM_MT")) : 1;
-  const int MT = (BT == 256 && k_splits <= 1 && N >= 2 * BM && mt_env >= 2) ? 2 : 1;
+  // 128-row token tile (batched decode steps of 65-128 sequences): the X tile is as large as a 128-row W tile, so the
+  // operand stream from L2 is twice the weight stream; two M sub-tiles per CTA would share one X tile (wide projections
+  // only: with N / 256 tiles the narrow ones no longer fill the machine).  Measured (r2ab, ctx 256): B = 80 / 100 / 128 =
+  // 4.96 / 5.24 / 5.93 ms against 4.90 / 5.18 / 5.86 with one sub-tile — the L2 operand stream is not what bounds these
+  // steps.  Opt-in (CL_GEMM_MT_B128=1), parity-checked by test_llama3_8b_layers_wide_batch under that switch.
+  static const int mt128_env = getenv("CL_GEMM_MT_B128") ? atoi(getenv("CL_GEMM_MT_B128")) : 0;
+  const int MT = (BT == 256 && k_splits <= 1 && N >= 2 * BM && mt_env >= 2) ? 2
+               : (BT == 128 && mt128_env && N >= 16384 && N % (2 * BM) == 0) ? 2 : 1;
   CUtensorMap mw, mx;
   if (!make_map(&mw, W, N, K, BM * MT) || !make_map(&mx, X, T, K, BT)) return -1;
   if (k_splits > 1 && (resid || (K + BK - 1) / BK < k_splits)) return -1;   // every split needs >= 1 k-block (an empty split would never signal its epilogue)
@@ -360,7 +367,7 @@ int launch_gemm_bf16(const __nv_bfloat16* X, const __nv_bfloat16* W, float* Y, c
   cudaError_t e;
   switch (BT) {
     case 256: e = MT == 2 ? launch_inst<256, 3, 2>(mw, mx, p, st, pdl) : launch_inst<256, 4>(mw, mx, p, st, pdl); break;
-    case 128: e = launch_inst<128, 6>(mw, mx, p, st, pdl); break;
+    case 128: e = MT == 2 ? launch_inst<128, 4, 2>(mw, mx, p, st, pdl) : launch_inst<128, 6>(mw, mx, p, st, pdl); break;
     case 64: e = launch_inst<64, 8>(mw, mx, p, st, pdl); break;
     default: e = launch_inst<32, 8>(mw, mx, p, st, pdl); break;
   }
