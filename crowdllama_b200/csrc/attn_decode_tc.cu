@@ -53,14 +53,26 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
   int* is_last_s = reinterpret_cast<int*>(cL_s + REP);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = blockIdx.x, sp = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NW); }
     fence_barrier_init();
   }
   __syncthreads();
   if (a.pdl_early) pdl_launch_dependents();
-
+  const bool is_producer = warp == NW;
+  if (is_producer) {
+    if (!elect_one()) return;
+    prefetch_tmap(&kmap);
+    prefetch_tmap(&vmap);
+  }
+  // Items = (kv head, split, sequence), kv head fastest.  One item per CTA when the grid covers them; with fewer CTAs
+  // (persistent launch, nsplit == 1) every CTA walks its items and the ring keeps running across them: the producer is
+  // already loading the next item's pages while the consumer warps merge and store the current one.
+  const int n_items = a.n_kv * a.nsplit * a.batch;
+  int tile_base = 0;                           // ring tiles of the items this CTA has finished (same in every warp)
+  bool waited = false;                         // producer: griddepcontrol.wait executed
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int g = item % a.n_kv, sp = (item / a.n_kv) % a.nsplit, b = item / (a.n_kv * a.nsplit);
   const int slot = a.slots ? a.slots[b] : b;
   const int pos = a.pos[slot];                 // stable for the whole step
   const int ctx = pos + 1;
@@ -72,17 +84,13 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
   const int n_tiles = (npg + 1) / 2;
   const int* bt = a.block_tables + (size_t)slot * a.bt_stride;
 
-  if (warp == NW) {
+  if (is_producer) {
     // ---------------- producer: everything it touches before griddepcontrol.wait (pos, block table, K/V of EARLIER
     // tokens) is immutable during the step; only the page that receives the current token waits
-    if (!elect_one()) return;
-    prefetch_tmap(&kmap);
-    prefetch_tmap(&vmap);
     const int cur_page = pos / P;
-    bool waited = false;
     for (int it = 0; it < n_tiles; ++it) {
-      const int st = it % NS;
-      mbar_wait(&empty[st], ((uint32_t)(it / NS) & 1u) ^ 1u);
+      const int T = tile_base + it, st = T % NS;
+      mbar_wait(&empty[st], ((uint32_t)(T / NS) & 1u) ^ 1u);
       const int pa = pg0 + 2 * it, pb = pa + 1;
       const bool two = pb < pg1;
       if (!waited && (pa == cur_page || (two && pb == cur_page))) { pdl_wait(); waited = true; }
@@ -97,7 +105,8 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
         tma_load_2d(d + 12288, &vmap, 64, (int)row, &full[st]);
       }
     }
-    return;
+    tile_base += n_tiles;
+    continue;
   }
 
   // ---------------- consumers (warps 0..7)
@@ -125,8 +134,8 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
   for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float mrow = -INFINITY, lrow = 0.f;          // row rq (valid for rq < REP)
   for (int it = 0; it < n_tiles; ++it) {
-    const int st = it % NS;
-    mbar_wait(&full[st], (uint32_t)(it / NS) & 1u);
+    const int T = tile_base + it, st = T % NS;
+    mbar_wait(&full[st], (uint32_t)(T / NS) & 1u);
     const int npage = (pg0 + 2 * it + 1 < pg1) ? 2 : 1;
     for (int pgi = 0; pgi < npage; ++pgi) {
       if (((2 * it + pgi) & (NW - 1)) != warp) continue;   // page -> warp (round robin)
@@ -234,17 +243,20 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
       ph[2 + i] = A;
     }
   }
-  if (a.nsplit == 1) return;
-  __threadfence();
-  asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-  if (tid == 0) {
-    unsigned* cnt = a.counters + (size_t)slot * a.n_kv + g;
-    const unsigned old = atomicAdd(cnt, 1u);
-    *is_last_s = (old == (unsigned)a.nsplit - 1u);
-    if (*is_last_s) *cnt = 0u;  // re-arm for the next launch (graph replay)
+  bool combine = false;                        // uniform over the consumer warps
+  if (a.nsplit > 1) {
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    if (tid == 0) {
+      unsigned* cnt = a.counters + (size_t)slot * a.n_kv + g;
+      const unsigned old = atomicAdd(cnt, 1u);
+      *is_last_s = (old == (unsigned)a.nsplit - 1u);
+      if (*is_last_s) *cnt = 0u;  // re-arm for the next launch (graph replay)
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    combine = *is_last_s != 0;
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-  if (!*is_last_s) return;
+  if (combine) {
   __threadfence();
 
   // ---- the last split to finish combines all partials of this kv head (fixed split order)
@@ -279,6 +291,11 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_con
     out[(size_t)(g * REP + hh) * HD + i] = r;
     if (a.out_bf16) a.out_bf16[(size_t)b * a.out_stride + (size_t)(g * REP + hh) * HD + i] = __float2bfloat16_rn(r);
   }
+  }  // combine
+  tile_base += n_tiles;
+  // the merge buffers (and is_last_s / the combine scratch) are reused by this CTA's next item
+  if (item + (int)gridDim.x < n_items) asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+  }  // items
 }
 
 }  // namespace
@@ -299,7 +316,13 @@ int launch_variant(const AttnDecodeArgs& a, const CUtensorMap& kmap, const CUten
   }
   TcArgs t{a, layer_row0};
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(a.n_kv, a.nsplit, a.batch); cfg.blockDim = dim3((NW + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  // persistent launch (single split, more items than resident CTAs): MINB CTAs per SM walk the items instead of one CTA
+  // per item.  r2ad, ctx 256: B = 64 4.433 -> 4.384 ms per step, B = 128 5.796 -> 5.678 (CL_BATCH_ATTN_PERSIST=0 restores
+  // one CTA per item).
+  static const int persist = getenv("CL_BATCH_ATTN_PERSIST") ? atoi(getenv("CL_BATCH_ATTN_PERSIST")) : 1;
+  const int n_items = a.n_kv * a.nsplit * a.batch, resident = MINB * sm_count();
+  const int grid = (persist && a.nsplit == 1 && n_items > resident) ? resident : n_items;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3((NW + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute la[1];
   la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   la[0].val.programmaticStreamSerializationAllowed = 1;
