@@ -86,7 +86,8 @@ typedef struct cl_engine_config {
   uint64_t weights_seed;   /* seed of the counter-based synthetic weight generator */
   int64_t kv_pool_bytes;   /* bytes of HBM for the paged KV pool; 0 => derive from max_seqs */
   int32_t page_size;       /* tokens per KV page: 16, 32 or 64 (0 => 32) */
-  int32_t max_batch;       /* max concurrently decoding sequences (0 => 8) */
+  int32_t max_batch;       /* max concurrently decoding sequences (0 => 8); the tensor-core batched step serves 2..128,
+                              larger values fall back to per-sequence GEMV kernels */
   int32_t max_seqs;        /* max live sequence handles (0 => max_batch) */
   int32_t use_cuda_graph;  /* 1 => capture the token step in a CUDA graph (default 1; -1 => 0) */
   int32_t decode_path;     /* 0 auto, 1 = generic LDG GEMV kernels, 2 = TMA-ring streaming GEMV */
