@@ -221,3 +221,28 @@ def test_pb_rejects_truncated_fixed_width_fields():
     with pytest.raises(ValueError):
         list(pb._fields(bytes([0x09, 1, 2, 3, 4])))               # field 1, wire type 1 (fixed64), only 4 bytes
     assert [(f, wt) for f, wt, _ in pb._fields(bytes([0x0d, 0, 0, 0x80, 0x3f]))] == [(1, 5)]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, the
+    same metric / unit / config as our arm, `impl: reference`, a cpu_baseline describing this run and an e2e that repeats
+    the value with zero host<->device bytes.  Runs the CPU oracle port on Llama-3-8B shapes for 3 steps (~25 s)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    import bench
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "tokens/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1.0
+    assert d["dtype"] == "bf16" and d["data"] == "synthetic" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["config"]["preset"] == bench.PRESET and d["config"]["ctx"] == bench.CTX and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
