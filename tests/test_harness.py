@@ -246,3 +246,31 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+
+
+def test_committed_bench_line_carries_every_contract_key():
+    """The bench line measured at the round's final commit (profiles/r2z_bench_head.json, produced by `python bench.py` on
+    a B200): every key of the bench contract is present and internally consistent — a reader of profiles/ and the
+    driver parse the same structure."""
+    from pathlib import Path
+    import bench
+    p = Path(__file__).resolve().parents[1] / "profiles" / "r2z_bench_head.json"
+    d = json.loads(p.read_text().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "box", "configs"):
+        assert k in d, k
+    assert d["metric"] == bench.METRIC and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert abs(d["value"] * d["ms_per_step"] - 1000.0) < 1.0                       # tokens/s x ms/token, one replica
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["kernel"] == "decode_mega_kernel"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and 0.5 < r["frac"] < 1.0
+    assert 0.98 < r["traffic"] / r["detail"]["algorithmic_bytes"] < 1.02            # ncu DRAM bytes = algorithmic bytes
+    assert r["prefill"]["bound"] == "tensor" and 0.5 < r["prefill"]["frac"] < 1.0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0.9 < e["value"] / d["value"] <= 1.0
+    assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] > 0.9 * d["clocks"]["sm_max_mhz"]
+    assert "l2" in d["config"] and "workload" in d["config"]
+    for sc in ("config4", "saturated"):
+        b = d["box"][sc]
+        assert b["ok"] == b["requests"] and not b["errors"] and b["req_per_s"] > 0 and sum(b["per_worker_requests"].values()) == b["requests"]
